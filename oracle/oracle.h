@@ -1,0 +1,105 @@
+// oracle/oracle.h -- CPU ORACLE for the stereo front-end. TEST INFRASTRUCTURE ONLY.
+//
+// This is a from-scratch CPU restatement of the hot path of liuzhenboo/Stereo-Visual-Odometry
+// (ORBextractor::operator(), the two brute-force Hamming matches, the four-call pyramidal LK chain and the
+// post-filters around them).  It is the checker for the CUDA path: only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may build, link, import or execute it.  Nothing under
+// stereo-visual-odometry_b200/ links or loads it; the product path has no CPU fallback.
+//
+// PARITY PIN STATUS:  the reference ships no tests, fixtures or golden vectors and cannot
+// be compiled in this image (needs OpenCV C++ 3.x, Sophus, glog, g2o, Pangolin) -> "parity unpinned" against a
+// reference binary.  What IS pinned: every third-party (OpenCV) primitive restated here is checked bit-for-bit
+// against cv2 4.13.0 (tests/test_oracle_vs_cv2.py, fixtures under tests/golden/ made by oracle/make_golden.py);
+// the reference's own loops (cell grid, octree, IC_Angle, steered BRIEF, match / LK post-filters) are restated
+// line by line with file:line citations and one documented canonicalisation (octree tie-break, see
+// distribute_octree()).
+//
+// All citations "ORBextractor.cpp:N" / "tracking.cpp:N" are into /root/reference/src/.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace orc {
+
+// == cv::KeyPoint layout (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id
+struct KeyPoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+};
+
+struct Image {  // non-owning view, 8-bit single channel
+    const uint8_t* data;
+    int w, h;
+    size_t stride;
+};
+
+struct OwnedImage {
+    std::vector<uint8_t> buf;
+    int w = 0, h = 0;
+    Image view() const { return Image{buf.data(), w, h, (size_t)w}; }
+    void create(int w_, int h_) { w = w_; h = h_; buf.assign((size_t)w_ * h_, 0); }
+};
+
+// ---- OpenCV primitive restatements ----
+int cv_round(float v);    // cvRound: round-half-to-even
+int cv_round(double v);
+void resize_linear_u8(const Image& src, uint8_t* dst, int dw, int dh, size_t dstride);            // cv::resize INTER_LINEAR 8UC1
+int fast9_score(const uint8_t* p, size_t stride);                                               // cornerScore<16> with threshold 0
+void fast9_detect(const Image& roi, int threshold, bool nms, std::vector<KeyPoint>& out);       // cv::FAST(TYPE_9_16)
+void gaussian_blur7_sigma2(const Image& src, uint8_t* dst, size_t dstride);                     // cv::GaussianBlur(7x7, 2, 2, REFLECT_101)
+float fast_atan2(float y, float x);                                                             // cv::fastAtan2 (degrees)
+void match_hamming(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* train_idx, int32_t* dist);  // BFMatcher(NORM_HAMMING).match
+void pyr_down(const Image& src, uint8_t* dst, size_t dstride);                                  // cv::pyrDown, dst ((w+1)/2,(h+1)/2)
+// cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, Size(win,win), maxLevel,
+//                          TermCriteria(COUNT+EPS, maxIter, eps), flags=0, minEigThreshold)
+void calc_optical_flow_pyr_lk(const Image& prev, const Image& next, const float* prev_xy, int n, float* next_xy,
+                              uint8_t* status, float* err, int win, int max_level, int max_iter, double eps,
+                              double min_eig);
+
+// ---- reference restatement: ORBextractor ----
+struct OrbParams {
+    int nfeatures;
+    float scaleFactor;
+    int nlevels, iniThFAST, minThFAST;
+};
+
+struct OrbTables {  // ORBextractor::ORBextractor, ORBextractor.cpp:359-418
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> features_per_level;
+    std::vector<int> umax;
+};
+OrbTables make_tables(const OrbParams& p);
+const int8_t* brief_pattern();  // 256 x 4 (x0,y0,x1,y1), the standard ORB learned pattern
+
+struct OctreeStats {
+    int rounds = 0;
+    int break_in_tie_group = 0;  // the final break of round B landed inside a group of equal-count nodes
+};
+
+// DistributeOctTree (ORBextractor.cpp:487-715); keys are (x,y,response) relative to minBorder.
+std::vector<KeyPoint> distribute_octree(const std::vector<KeyPoint>& keys, int minX, int maxX, int minY, int maxY,
+                                        int N, OctreeStats* stats = nullptr);
+
+struct OrbResult {
+    std::vector<OwnedImage> pyramid;                // levels without border
+    std::vector<std::vector<KeyPoint>> candidates;  // per level, output of the cell loop (coords relative to minBorder)
+    std::vector<std::vector<KeyPoint>> level_kps;   // per level after octree + angle (level coords)
+    std::vector<KeyPoint> keypoints;                // final (scaled to level 0)
+    std::vector<uint8_t> descriptors;               // N x 32
+    std::vector<OctreeStats> octree_stats;
+};
+// ORBextractor::operator() (ORBextractor.cpp:990-1055)
+void orb_extract(const OrbParams& p, const Image& img, OrbResult& out, bool keep_intermediates = true);
+
+// ---- reference restatement: Tracking front-end ----
+// Tracking::ORB_Robust_Find_MuliImage_MatchedFeatures (tracking.cpp:534-581). Returns #accepted; fills index triples.
+int orb_match_filter(const int32_t* idx1, const int32_t* dist1, const int32_t* idx2, const int32_t* dist2, int n_last_left,
+                     int n_last_right, int n_cur_left, const KeyPoint* last_left, const KeyPoint* last_right,
+                     double feature_match_error, int32_t* accepted /* n x 3: (lastL idx, lastR idx, curL idx) */);
+// Tracking::deleteBadmatchFeatures (tracking.cpp:623-660): keep[i]=1 if point i survives.
+int lk_chain_filter(int n, const float* p0, const float* p1, const float* p2, const float* p3, const float* p0r,
+                    const uint8_t* s0, const uint8_t* s1, const uint8_t* s2, const uint8_t* s3, double feature_match_error,
+                    uint8_t* keep);
+
+}  // namespace orc
