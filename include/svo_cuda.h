@@ -1,0 +1,169 @@
+/* include/svo_cuda.h -- C ABI of the B200-native stereo front-end (libsvo_b200.so).
+ *
+ * The reference (liuzhenboo/Stereo-Visual-Odometry) has no FFI/plugin layer: its boundary is the C++ class surface
+ * lzb_vio::ORBextractor / lzb_vio::Tracking.  This header is the thin extern "C" layer those
+ * classes call instead of OpenCV; every entry point names the reference call site it replaces.  Plain pointers and
+ * sizes only; host pointers in, host pointers out unless a name ends in _dev; no exceptions cross this ABI.
+ *
+ * Return value: SVO_OK (0) or a negative svo_status; svo_last_error(ctx) gives the message.  A context is bound to one
+ * CUDA device and one stream and is NOT re-entrant (like the reference's ORBextractor, whose mvImagePyramid is
+ * per-object scratch, tracking.cpp:508-509): use one context per host thread / GPU.
+ *
+ * There is no CPU fallback anywhere behind this ABI: without a CUDA device svo_ctx_create fails with SVO_ERR_CUDA.
+ */
+#ifndef SVO_CUDA_H
+#define SVO_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_ABI_VERSION 1
+
+typedef enum svo_status {
+    SVO_OK = 0,
+    SVO_ERR_INVALID = -1,        /* bad argument (null pointer, size out of range, wrong state) */
+    SVO_ERR_CUDA = -2,           /* CUDA runtime error / no device */
+    SVO_ERR_CAPACITY = -3,       /* an internal or caller-provided capacity was exceeded (never silently truncated) */
+    SVO_ERR_NOT_CONFIGURED = -4  /* svo_orb_configure() has not been called */
+} svo_status;
+
+typedef struct svo_ctx svo_ctx;
+
+/* Binary-compatible with cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct svo_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} svo_keypoint;
+
+/* ---- context ------------------------------------------------------------------------------------------------- */
+/* max_images: how many images one batched call may carry (device scratch is sized for it). */
+int svo_ctx_create(svo_ctx** ctx, int device, int max_w, int max_h, int max_images);
+void svo_ctx_destroy(svo_ctx* ctx);
+const char* svo_last_error(const svo_ctx* ctx);
+int svo_abi_version(void);
+/* Run all work of this context on the caller's CUDA stream (a cudaStream_t); NULL restores the context's own. */
+int svo_ctx_set_stream(svo_ctx* ctx, void* cuda_stream);
+int svo_ctx_synchronize(svo_ctx* ctx);
+/* Kernels launched by this context since creation (bench.py's gpu_launches claim). */
+int64_t svo_ctx_launch_count(const svo_ctx* ctx);
+/* Device time of pipeline stages of the most recent device run, measured with CUDA events on the context's stream.
+ * stage: 0 pyramid(K1) 1 fast+cells(K2) 2 compact(K2b) 3 octree(K3) 4 angle+descriptor(K4/K5) 5 match(K6)
+ *        6 fullframe-fast(K9) 7 lk-pyramid(K7) 8 lk-track(K8).  Returns milliseconds, <0 if the stage did not run.
+ * Only recorded while svo_ctx_enable_stage_timing(ctx, 1). */
+int svo_ctx_enable_stage_timing(svo_ctx* ctx, int on);
+float svo_ctx_stage_ms(const svo_ctx* ctx, int stage);
+#define SVO_NUM_STAGES 9
+
+/* ---- ORB extractor ------------------------------------------------------------------------------------------- */
+/* Replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (include/lzb_vio/ORBextractor.h:33-34, src/ORBextractor.cpp:359-418): scale tables, per-level quotas, pattern, umax. */
+int svo_orb_configure(svo_ctx* ctx, int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST);
+/* Getters behind GetScaleFactors()/GetInverseScaleFactors()/GetScaleSigmaSquares()/GetInverseScaleSigmaSquares()
+ * (ORBextractor.h:45-73) and mnFeaturesPerLevel; each array has nlevels entries, any pointer may be NULL. */
+int svo_orb_tables(const svo_ctx* ctx, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                   int32_t* features_per_level);
+/* Upper bound on keypoints returned per image: sum over levels of max(N_l + 3, 4 * nIni). */
+int svo_orb_capacity(const svo_ctx* ctx, int w, int h);
+/* Level geometry for a w x h input (ORBextractor::ComputePyramid, ORBextractor.cpp:1065-1066). */
+int svo_orb_level_size(const svo_ctx* ctx, int w, int h, int level, int* lw, int* lh);
+
+/* Replaces ORBextractor::operator()(image, mask, keypoints, descriptors) (ORBextractor.h:41-43,
+ * ORBextractor.cpp:990-1055).  img: 8-bit single channel, w x h, row stride in bytes.  kps/desc: caller arrays of
+ * `cap` keypoints / cap*32 bytes; *n_out = number written.  An empty image (w==0||h==0||!img) returns SVO_OK with
+ * *n_out = 0 (the reference returns silently, :993-994). */
+int svo_orb_extract(svo_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, svo_keypoint* kps, uint8_t* desc,
+                    int cap, int* n_out);
+/* n_imgs images of identical size in one pass (image i -> kps + i*cap_per_img, desc + i*cap_per_img*32, n_out[i]). */
+int svo_orb_extract_batch(svo_ctx* ctx, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride,
+                          svo_keypoint* kps, uint8_t* desc, int cap_per_img, int* n_out);
+/* Read back pyramid level `level` of image `img_slot` of the last extract call, without border (public member
+ * mvImagePyramid, ORBextractor.h:75; also used by the parity tests).  dst may be NULL to query the size. */
+int svo_orb_read_level(svo_ctx* ctx, int img_slot, int level, uint8_t* dst, size_t dst_stride, int* w, int* h);
+/* Read back the output of the per-cell FAST loop (vToDistributeKeys, ORBextractor.cpp:742-781) for one level, in the
+ * reference's order, coordinates relative to minBorder: x, y, response filled; size=7, angle=-1, octave=0. */
+int svo_orb_read_candidates(svo_ctx* ctx, int img_slot, int level, svo_keypoint* out, int cap, int* n_out);
+
+/* ---- full-frame FAST ----------------------------------------------------------------------------------------- */
+/* Replaces cv::FAST(image, keypoints, threshold, nonmaxSuppression) at tracking.cpp:101 (Detect_OpenCVFASTFeatures).
+ * Output in row-major order: x, y, size=7, angle=-1, response=score, octave=0, class_id=-1. nms must be non-zero. */
+int svo_fast_detect(svo_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, int threshold, int nms,
+                    svo_keypoint* kps, int cap, int* n_out);
+
+/* ---- brute-force Hamming ------------------------------------------------------------------------------------- */
+/* Replaces DescriptorMatcher::create("BruteForce-Hamming")->match(query, train, matches) (tracking.cpp:539-544):
+ * for query i, train_idx[i] = lowest index with minimum popcount distance, dist[i] = that distance (DMatch.distance
+ * as an integer).  nt == 0 gives train_idx = -1 (OpenCV returns no matches for an empty train set). */
+int svo_match_hamming(svo_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* train_idx,
+                      int32_t* dist);
+
+/* ---- pyramidal Lucas-Kanade ---------------------------------------------------------------------------------- */
+/* Replaces cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, Size(win,win), max_level,
+ * TermCriteria(COUNT+EPS, max_iter, eps), 0, min_eig) (tracking.cpp:593,600,607,613).  win must be 21.
+ * prev_xy / next_xy: n x 2 floats; status: n bytes; err: n floats or NULL. */
+int svo_lk_track(svo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, int h, size_t stride,
+                 const float* prev_xy, int n, float* next_xy, uint8_t* status, float* err, int win, int max_level,
+                 int max_iter, double eps, double min_eig);
+
+/* ---- throughput mode: batches of consecutive stereo frames ------------------------------------------------------ */
+/* One unit of work = one new stereo frame t:
+ *   SVO_MODE_ORB: operator() on left_t and right_t (Detect_MyORBFeatures, tracking.cpp:502-532), then
+ *                 match(left_{t-1}, right_{t-1}) and match(left_{t-1}, left_t) (tracking.cpp:543-544);
+ *   SVO_MODE_LK : cv::FAST(left_t, 20, true) (tracking.cpp:101) and the four chained LK calls over frames t-1, t
+ *                 seeded with the FAST corners of left_{t-1} (tracking.cpp:268-271, 593-618).
+ * The context carries frame t-1 between calls (Tracking::last_frame_); after svo_frontend_reset the first frame only
+ * detects (Tracking::StereoInit_f2f, tracking.cpp:78-92) and reports zero queries / seeds. */
+#define SVO_MODE_ORB 1
+#define SVO_MODE_LK 2
+
+typedef struct svo_frontend_out {
+    /* capacities, filled by the caller */
+    int32_t kp_cap; /* keypoints per image  (>= svo_orb_capacity)          */
+    int32_t pt_cap; /* FAST corners / LK seeds per frame                    */
+    /* ORB mode; frame f uses [f*kp_cap, (f+1)*kp_cap).  Any pointer may be NULL (that output stays on the device). */
+    svo_keypoint* kps_left;
+    uint8_t* desc_left;
+    int32_t* n_left;
+    svo_keypoint* kps_right;
+    uint8_t* desc_right;
+    int32_t* n_right;
+    int32_t* n_query;       /* per frame: #queries = n_left of frame f-1 (0 for the first frame after reset) */
+    int32_t* stereo_idx;    /* match(left_{f-1}, right_{f-1}).trainIdx,  kp_cap per frame */
+    int32_t* stereo_dist;
+    int32_t* temporal_idx;  /* match(left_{f-1}, left_f).trainIdx */
+    int32_t* temporal_dist;
+    /* LK mode; frame f uses [f*pt_cap, ...) */
+    svo_keypoint* fast_kps; /* FAST corners of left_f */
+    int32_t* n_fast;
+    int32_t* n_seed;        /* per frame: #LK seeds = n_fast of frame f-1 */
+    float* lk_p1;           /* t-1 right  (call 1: left_{t-1} -> right_{t-1}),  pt_cap*2 floats per frame */
+    float* lk_p2;           /* t   right  (call 2) */
+    float* lk_p3;           /* t   left   (call 3) */
+    float* lk_p0r;          /* t-1 left, returned (call 4) */
+    uint8_t* lk_status;     /* 4 x pt_cap per frame: status1..status4 */
+} svo_frontend_out;
+
+int svo_frontend_configure(svo_ctx* ctx, int w, int h, int mode, int max_frames);
+int svo_frontend_reset(svo_ctx* ctx);
+/* host images -> device (left/right: n_frames contiguous images of h rows, `stride` bytes per row) */
+int svo_frontend_upload(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride);
+/* all kernels for the uploaded frames; inputs and outputs stay in HBM */
+int svo_frontend_run(svo_ctx* ctx);
+/* device -> host for every non-NULL field of out */
+int svo_frontend_download(svo_ctx* ctx, svo_frontend_out* out);
+/* upload + run + download */
+int svo_frontend_batch(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride,
+                       svo_frontend_out* out);
+
+/* ---- deterministic synthetic stereo sequences (bench / tests input; host code, needs no GPU) --------------------- */
+/* Frame `frame` of sequence `seed`: textured canvas, 8-px disparity, 2-px/frame motion, canvas
+ * re-seeded every 16 frames.  left/right: h rows of `stride` bytes. */
+int svo_synth_stereo_frame(uint64_t seed, int frame, int w, int h, uint8_t* left, uint8_t* right, size_t stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_CUDA_H */

@@ -1,0 +1,293 @@
+"""stereo-visual-odometry_b200 -- B200-native stereo visual-odometry front-end.
+
+This package is a thin ctypes view of the C ABI in include/svo_cuda.h (libsvo_b200.so: hand-written sm_100a CUDA
+kernels behind an extern "C" layer).  It exists for the tests and bench.py; the product boundary is the C ABI and the
+drop-in C++ classes under host/.  There is no CPU fallback: if the shared library is missing this module raises, and
+without a CUDA device `Context(...)` raises.
+
+The directory name is not a valid Python identifier; import it with `__graft_entry__.load_package()` (registered as
+`svo_b200`).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+SVO_OK, SVO_ERR_INVALID, SVO_ERR_CUDA, SVO_ERR_CAPACITY, SVO_ERR_NOT_CONFIGURED = 0, -1, -2, -3, -4
+MODE_ORB, MODE_LK = 1, 2
+STAGES = ["pyramid", "fast_cells", "compact", "octree", "describe", "match", "fast_full", "lk_pyramid", "lk_track"]
+
+# every symbol include/svo_cuda.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "svo_ctx_create", "svo_ctx_destroy", "svo_last_error", "svo_abi_version", "svo_ctx_set_stream", "svo_ctx_synchronize",
+    "svo_ctx_launch_count", "svo_ctx_enable_stage_timing", "svo_ctx_stage_ms", "svo_orb_configure", "svo_orb_tables",
+    "svo_orb_capacity", "svo_orb_level_size", "svo_orb_extract", "svo_orb_extract_batch", "svo_orb_read_level",
+    "svo_orb_read_candidates", "svo_fast_detect", "svo_match_hamming", "svo_lk_track", "svo_frontend_configure",
+    "svo_frontend_reset", "svo_frontend_upload", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
+    "svo_synth_stereo_frame",
+]
+
+
+class SvoError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"svo error {code}: {msg}")
+        self.code = code
+
+
+class FrontendOut(C.Structure):
+    _fields_ = [("kp_cap", C.c_int32), ("pt_cap", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
+        "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status")]
+
+
+_lib = None
+
+
+def lib():
+    """Load libsvo_b200.so (fails loudly if the CUDA extension has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.svo_last_error.restype = C.c_char_p
+        L.svo_last_error.argtypes = [C.c_void_p]
+        L.svo_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
+        L.svo_ctx_destroy.argtypes = [C.c_void_p]
+        L.svo_ctx_destroy.restype = None
+        L.svo_ctx_launch_count.restype = C.c_int64
+        L.svo_ctx_launch_count.argtypes = [C.c_void_p]
+        L.svo_ctx_stage_ms.restype = C.c_float
+        L.svo_ctx_stage_ms.argtypes = [C.c_void_p, C.c_int]
+        L.svo_orb_configure.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.svo_synth_stereo_frame.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.svo_lk_track.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def synth_stereo_frame(seed, frame, w, h):
+    """Frame `frame` of the deterministic synthetic stereo sequence `seed`. Host code, no GPU needed."""
+    left = np.empty((h, w), np.uint8)
+    right = np.empty((h, w), np.uint8)
+    rc = lib().svo_synth_stereo_frame(seed, frame, w, h, _p(left), _p(right), w)
+    if rc != 0:
+        raise SvoError(rc, "svo_synth_stereo_frame")
+    return left, right
+
+
+def synth_sequence(seed, first, count, w, h):
+    left = np.empty((count, h, w), np.uint8)
+    right = np.empty((count, h, w), np.uint8)
+    for i in range(count):
+        rc = lib().svo_synth_stereo_frame(seed, first + i, w, h, _p(left[i]), _p(right[i]), w)
+        if rc != 0:
+            raise SvoError(rc, "svo_synth_stereo_frame")
+    return left, right
+
+
+class Context:
+    """One svo_ctx: one device, one stream, not re-entrant (mirrors the reference's per-object scratch)."""
+
+    def __init__(self, device=0, max_w=1241, max_h=376, max_images=2):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.svo_ctx_create(C.byref(h), device, max_w, max_h, max_images)
+        if rc != 0:
+            raise SvoError(rc, "svo_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self._h = h
+        self.max_images = max_images
+        self.nlevels = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.svo_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SvoError(rc, self._L.svo_last_error(self._h).decode())
+
+    # ---- context
+    def set_stream(self, cuda_stream_handle):
+        self._check(self._L.svo_ctx_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def synchronize(self):
+        self._check(self._L.svo_ctx_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self._L.svo_ctx_launch_count(self._h))
+
+    def enable_stage_timing(self, on=True):
+        self._check(self._L.svo_ctx_enable_stage_timing(self._h, int(on)))
+
+    def stage_ms(self):
+        return {name: float(self._L.svo_ctx_stage_ms(self._h, i)) for i, name in enumerate(STAGES)}
+
+    # ---- ORB extractor (ORBextractor.h:33-75)
+    def orb_configure(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self._check(self._L.svo_orb_configure(self._h, nfeatures, scale_factor, nlevels, ini_th, min_th))
+        self.nlevels = nlevels
+
+    def orb_tables(self):
+        n = self.nlevels
+        arrs = [np.empty(n, np.float32) for _ in range(4)] + [np.empty(n, np.int32)]
+        self._check(self._L.svo_orb_tables(self._h, *[_p(a) for a in arrs]))
+        return dict(zip(("scale", "inv_scale", "sigma2", "inv_sigma2", "features_per_level"), arrs))
+
+    def orb_capacity(self, w, h):
+        cap = self._L.svo_orb_capacity(self._h, w, h)
+        if cap < 0:
+            self._check(cap)
+        return cap
+
+    def orb_level_size(self, w, h, level):
+        lw, lh = C.c_int(), C.c_int()
+        self._check(self._L.svo_orb_level_size(self._h, w, h, level, C.byref(lw), C.byref(lh)))
+        return lw.value, lh.value
+
+    def orb_extract(self, img):
+        """ORBextractor::operator() on one image -> (keypoints[KP_DTYPE], descriptors[N,32])."""
+        k, d = self.orb_extract_batch([img])
+        return k[0], d[0]
+
+    def orb_extract_batch(self, imgs):
+        imgs = [np.ascontiguousarray(i, np.uint8) for i in imgs]
+        n = len(imgs)
+        if n == 0:
+            return [], []
+        h, w = imgs[0].shape
+        if w == 0 or h == 0:
+            return [np.zeros(0, KP_DTYPE) for _ in imgs], [np.zeros((0, 32), np.uint8) for _ in imgs]
+        assert all(i.shape == (h, w) for i in imgs)
+        cap = self.orb_capacity(w, h)
+        kps = np.zeros((n, cap), KP_DTYPE)
+        desc = np.zeros((n, cap, 32), np.uint8)
+        nout = np.zeros(n, np.int32)
+        ptrs = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+        self._check(self._L.svo_orb_extract_batch(self._h, ptrs, n, w, h, C.c_size_t(imgs[0].strides[0]), _p(kps), _p(desc), cap, _p(nout)))
+        return [kps[i, :nout[i]].copy() for i in range(n)], [desc[i, :nout[i]].copy() for i in range(n)]
+
+    def orb_read_level(self, slot, level):
+        w, h = C.c_int(), C.c_int()
+        self._check(self._L.svo_orb_read_level(self._h, slot, level, None, C.c_size_t(0), C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        self._check(self._L.svo_orb_read_level(self._h, slot, level, _p(out), C.c_size_t(w.value), C.byref(w), C.byref(h)))
+        return out
+
+    def orb_read_candidates(self, slot, level):
+        n = C.c_int()
+        self._check(self._L.svo_orb_read_candidates(self._h, slot, level, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), KP_DTYPE)
+        self._check(self._L.svo_orb_read_candidates(self._h, slot, level, _p(out), max(n.value, 1), C.byref(n)))
+        return out[:n.value]
+
+    # ---- full-frame FAST (tracking.cpp:101)
+    def fast_detect(self, img, threshold=20, nms=True, cap=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        cap = cap or max(1024, w * h // 16)
+        out = np.zeros(cap, KP_DTYPE)
+        n = C.c_int()
+        self._check(self._L.svo_fast_detect(self._h, _p(img), w, h, C.c_size_t(img.strides[0]), threshold, int(nms), _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    # ---- BF Hamming (tracking.cpp:543-544)
+    def match_hamming(self, q, t):
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        idx = np.full(len(q), -1, np.int32)
+        dist = np.full(len(q), -1, np.int32)
+        self._check(self._L.svo_match_hamming(self._h, _p(q), len(q), _p(t), len(t), _p(idx), _p(dist)))
+        return idx, dist
+
+    # ---- pyramidal LK (tracking.cpp:593-618)
+    def lk_track(self, prev, nxt, pts, win=21, max_level=3, max_iter=30, eps=0.01, min_eig=1e-3):
+        prev = np.ascontiguousarray(prev, np.uint8)
+        nxt = np.ascontiguousarray(nxt, np.uint8)
+        assert prev.shape == nxt.shape
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = len(pts)
+        out = np.zeros((n, 2), np.float32)
+        status = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32)
+        h, w = prev.shape
+        self._check(self._L.svo_lk_track(self._h, _p(prev), _p(nxt), w, h, prev.strides[0], _p(pts), n, _p(out), _p(status), _p(err),
+                                         win, max_level, max_iter, eps, min_eig))
+        return out, status, err
+
+    # ---- throughput mode
+    def frontend_configure(self, w, h, mode, max_frames):
+        self._check(self._L.svo_frontend_configure(self._h, w, h, mode, max_frames))
+        self.fe = dict(w=w, h=h, mode=mode, max_frames=max_frames, kp_cap=self.orb_capacity(w, h) if mode & MODE_ORB else 0)
+
+    def frontend_reset(self):
+        self._check(self._L.svo_frontend_reset(self._h))
+
+    def frontend_upload(self, left, right):
+        assert left.shape == right.shape and left.dtype == np.uint8 and left.flags.c_contiguous and right.flags.c_contiguous
+        self._check(self._L.svo_frontend_upload(self._h, _p(left), _p(right), left.shape[0], C.c_size_t(left.strides[1])))
+        self._n_frames = left.shape[0]
+
+    def frontend_upload_ptr(self, left_ptr, right_ptr, n_frames, stride):
+        self._check(self._L.svo_frontend_upload(self._h, C.c_void_p(left_ptr), C.c_void_p(right_ptr), n_frames, C.c_size_t(stride)))
+        self._n_frames = n_frames
+
+    def frontend_run(self):
+        self._check(self._L.svo_frontend_run(self._h))
+
+    def frontend_download(self, out):
+        self._check(self._L.svo_frontend_download(self._h, C.byref(out.struct)))
+
+    def frontend_batch(self, left, right, out):
+        assert left.shape == right.shape and left.dtype == np.uint8 and left.flags.c_contiguous and right.flags.c_contiguous
+        self._check(self._L.svo_frontend_batch(self._h, _p(left), _p(right), left.shape[0], C.c_size_t(left.strides[1]), C.byref(out.struct)))
+
+
+class FrontendBuffers:
+    """Host-side output arrays of svo_frontend_download / svo_frontend_batch (numpy-owned; `fields` selects what is copied)."""
+
+    ALL = ("kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
+           "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status")
+
+    def __init__(self, n_frames, kp_cap, pt_cap, fields=None):
+        fields = self.ALL if fields is None else fields
+        self.n_frames, self.kp_cap, self.pt_cap = n_frames, kp_cap, pt_cap
+        F, K, P = n_frames, max(kp_cap, 1), max(pt_cap, 1)
+        shapes = dict(kps_left=((F, K), KP_DTYPE), desc_left=((F, K, 32), np.uint8), n_left=((F,), np.int32),
+                      kps_right=((F, K), KP_DTYPE), desc_right=((F, K, 32), np.uint8), n_right=((F,), np.int32),
+                      n_query=((F,), np.int32), stereo_idx=((F, K), np.int32), stereo_dist=((F, K), np.int32),
+                      temporal_idx=((F, K), np.int32), temporal_dist=((F, K), np.int32),
+                      fast_kps=((F, P), KP_DTYPE), n_fast=((F,), np.int32), n_seed=((F,), np.int32),
+                      lk_p1=((F, P, 2), np.float32), lk_p2=((F, P, 2), np.float32), lk_p3=((F, P, 2), np.float32),
+                      lk_p0r=((F, P, 2), np.float32), lk_status=((F, 4, P), np.uint8))
+        self.struct = FrontendOut()
+        self.struct.kp_cap = kp_cap
+        self.struct.pt_cap = pt_cap
+        self.bytes = 0
+        for name in self.ALL:
+            if name in fields:
+                shape, dt = shapes[name]
+                arr = np.zeros(shape, dt)
+                setattr(self, name, arr)
+                setattr(self.struct, name, arr.ctypes.data)
+                self.bytes += arr.nbytes
+            else:
+                setattr(self, name, None)
+                setattr(self.struct, name, None)

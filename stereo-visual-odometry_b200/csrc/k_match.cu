@@ -1,0 +1,108 @@
+// k_match.cu -- K6: brute-force Hamming matching of 256-bit descriptors.
+//
+// Replaces DescriptorMatcher("BruteForce-Hamming")->match(query, train) (tracking.cpp:539-544): one
+// result per query, the LOWEST train index attaining the minimum popcount distance.
+// One thread holds one query descriptor in 8 registers; the train set streams through shared memory in tiles of 128
+// descriptors (broadcast reads, no bank conflicts); distance = 8 x (XOR, POPC).  Strict '<' while scanning train indices
+// in ascending order gives the first-minimum tie-break.
+#include "svo_common.cuh"
+
+namespace {
+
+constexpr int MT = 128;  // queries per CTA == train descriptors per tile
+
+__device__ __forceinline__ void match_core(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
+                                           int* __restrict__ idx_out, int* __restrict__ dist_out) {
+    __shared__ uint4 tile[MT * 2];
+    const int qi = blockIdx.x * MT + threadIdx.x;
+    if (blockIdx.x * MT >= nq) return;  // CTA-uniform
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (qi < nq) {
+        qa = __ldg(reinterpret_cast<const uint4*>(q) + 2 * qi);
+        qb = __ldg(reinterpret_cast<const uint4*>(q) + 2 * qi + 1);
+    }
+    int best = 1 << 30, bi = -1;
+    for (int t0 = 0; t0 < nt; t0 += MT) {
+        const int cnt = min(MT, nt - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += MT) tile[i] = __ldg(reinterpret_cast<const uint4*>(t) + 2 * t0 + i);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+            const int d = __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) + __popc(qb.x ^ b.x) +
+                          __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+            if (d < best) {
+                best = d;
+                bi = t0 + j;
+            }
+        }
+    }
+    if (qi < nq) {
+        idx_out[qi] = bi;
+        dist_out[qi] = bi < 0 ? -1 : best;
+    }
+}
+
+__global__ void __launch_bounds__(MT) k_match_one(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist) {
+    match_core(q, nq, t, nt, idx, dist);
+}
+
+// frontend: problem p = 2 * f + kind for unit frame f of the batch; kind 0 = match(left_{f-1}, right_{f-1}),
+// kind 1 = match(left_{f-1}, left_f).  Frame slots form a ring; left image slot = fs, right image slot = ring + fs.
+__global__ void __launch_bounds__(MT) k_match_frontend(const uint8_t* __restrict__ desc, const int* __restrict__ nkp, int kp_cap,
+                                                       int first, int ring, int skip_first, int* __restrict__ match) {
+    const int f = blockIdx.y >> 1, kind = blockIdx.y & 1;
+    const int cur = (first + f) % ring, prev = (first + f - 1 + ring) % ring;
+    int* out = match + ((size_t)cur * 4 + 2 * kind) * kp_cap;
+    if (f == 0 && skip_first) return;  // no predecessor: StereoInit_f2f only detects (tracking.cpp:78-92)
+    const int qs = prev, ts = kind == 0 ? ring + prev : cur;
+    match_core(desc + (size_t)qs * kp_cap * 32, nkp[qs], desc + (size_t)ts * kp_cap * 32, nkp[ts], out, out + kp_cap);
+}
+
+}  // namespace
+
+int launch_match_frontend(svo_ctx* c, int first, int ring, int n_frames, int skip_first) {
+    StageTimer t(c, 5);
+    dim3 grid((c->kp_cap + MT - 1) / MT, 2 * n_frames);
+    k_match_frontend<<<grid, MT, 0, c->stream>>>(c->d_desc, c->d_nkp, c->kp_cap, first, ring, skip_first, c->d_match);
+    ++c->launches;
+    SVO_CUDA_TRY(c, cudaGetLastError());
+    return SVO_OK;
+}
+
+int svo_ensure_scratch(svo_ctx* c, size_t bytes) {
+    if (c->scratch_bytes >= bytes) return SVO_OK;
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    c->scratch_bytes = 0;
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_scratch, bytes));
+    c->scratch_bytes = bytes;
+    return SVO_OK;
+}
+
+extern "C" int svo_match_hamming(svo_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* train_idx, int32_t* dist) {
+    if (!c) return SVO_ERR_INVALID;
+    if (nq < 0 || nt < 0 || (nq > 0 && (!q || !train_idx || !dist)) || (nt > 0 && !t)) return c->fail(SVO_ERR_INVALID, "svo_match_hamming: bad arguments");
+    if (nq == 0) return SVO_OK;
+    cudaSetDevice(c->device);
+    const size_t qb = svo_align((size_t)nq * 32, 256), tb = svo_align((size_t)std::max(nt, 1) * 32, 256), ob = svo_align((size_t)nq * 4, 256);
+    int rc = svo_ensure_scratch(c, qb + tb + 2 * ob);
+    if (rc != SVO_OK) return rc;
+    uint8_t* dq = (uint8_t*)c->d_scratch;
+    uint8_t* dt = dq + qb;
+    int* di = (int*)(dt + tb);
+    int* dd = (int*)((uint8_t*)di + ob);
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(dq, q, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
+    if (nt > 0) SVO_CUDA_TRY(c, cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
+    {
+        StageTimer tm(c, 5);
+        k_match_one<<<(nq + MT - 1) / MT, MT, 0, c->stream>>>(dq, nq, dt, nt, di, dd);
+        ++c->launches;
+    }
+    SVO_CUDA_TRY(c, cudaGetLastError());
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(train_idx, di, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(dist, dd, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}

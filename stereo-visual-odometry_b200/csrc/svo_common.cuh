@@ -1,0 +1,214 @@
+// svo_common.cuh -- shared definitions of libsvo_b200.so (B200 / sm_100a stereo front-end).
+//
+// Data layout in HBM (all buffers are allocated once per context, sized for `max_images` image slots):
+//   level l of slot s        : lvl[l].base + s * lvl[l].plane, rows of lvl[l].pitch bytes (pitch multiple of 64,
+//                              plane == pitch * h so that consecutive slots form one pitched 2-D array)
+//   FAST tile staging        : tile_buf + s * tile_buf_per_slot + tile.out_off   (packed u32 candidates per tile)
+//   candidates (cell loop)   : cand + s * cand_per_slot + lvl[l].cand_off        (packed u32, reference order)
+//   level keypoints (octree) : lkp  + s * lkp_per_slot  + lvl[l].lkp_off         (packed u32, list order)
+//   keypoints / descriptors  : kps + s * kp_cap (28-byte cv::KeyPoint), desc + s * kp_cap * 32
+// A packed candidate is  response << 24 | y << 12 | x  with x, y relative to minBorder (= pixel - 16).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "svo_cuda.h"
+
+#define SVO_MAX_LEVELS 12
+#define SVO_EDGE 19        // EDGE_THRESHOLD, ORBextractor.cpp:19
+#define SVO_MINB 16        // minBorder = EDGE_THRESHOLD - 3, ORBextractor.cpp:726
+#define SVO_MAX_DIM 4096   // packed candidate coordinates are 12 bits (relative to minBorder)
+#define SVO_LK_LEVELS 4    // maxLevel 3 (tracking.cpp:594)
+#define SVO_LK_WIN 21
+
+struct LevelGeom {
+    uint8_t* base;  // slot 0 of this level
+    int w, h, pitch;
+    uint32_t plane;  // bytes per slot
+    // cell grid (ORBextractor.cpp:731-740)
+    int nCols, nRows, wCell, hCell;
+    // octree (ORBextractor.cpp:491-493)
+    int N, nIni, Wp, Hp;
+    float hX;
+    // per-slot offsets (in elements) into cand / lkp arrays
+    int cand_off, cand_cap, lkp_off, lkp_cap;
+    int tile_begin, tile_count;
+    float scale;     // mvScaleFactor[l]
+    int patch_size;  // int(31 * scale)
+    // resize tables (device), describing level l as resized from level l-1
+    const int* xofs;
+    const short* alpha;  // 2 per dst x
+    const int* yofs;     // 2 per dst y (clamped row indices)
+    const short* beta;   // 2 per dst y
+};
+
+struct PyrGeom {
+    int nlevels;
+    int iniTh, minTh;
+    LevelGeom lvl[SVO_MAX_LEVELS];
+};
+
+// One FAST tile = one cell row x a run of cells of one level (K2), or a full-width strip of rows (K9).
+struct FastTile {
+    short level, cell_i;
+    short cell_j0, ncells;
+    int x0, x1, y0, y1;  // inner pixel domain [x0,x1) x [y0,y1), level coordinates
+    int out_off, out_cap;
+};
+
+// batch image index -> image slot (see svo_ctx.cu: plain batches use slots 0..n-1; the frontend uses a ring of frames)
+struct SlotMap {
+    int sides, side_stride, first, ring;
+    __host__ __device__ inline int slot(int b) const { return (b % sides) * side_stride + (first + b / sides) % ring; }
+};
+
+#define SVO_FLAG_TILE_OVERFLOW 1
+#define SVO_FLAG_CAND_OVERFLOW 2
+#define SVO_FLAG_NODE_OVERFLOW 4
+#define SVO_FLAG_KP_OVERFLOW 8
+#define SVO_FLAG_FAST_OVERFLOW 16
+
+__host__ __device__ inline uint32_t pack_cand(int x, int y, int r) { return ((uint32_t)r << 24) | ((uint32_t)y << 12) | (uint32_t)x; }
+__host__ __device__ inline int cand_x(uint32_t c) { return (int)(c & 0xFFFu); }
+__host__ __device__ inline int cand_y(uint32_t c) { return (int)((c >> 12) & 0xFFFu); }
+__host__ __device__ inline int cand_r(uint32_t c) { return (int)(c >> 24); }
+
+struct LkLevelGeom {
+    uint8_t* base;
+    int w, h, pitch;
+    uint32_t plane;
+};
+
+struct svo_ctx {
+    int device = 0, max_w = 0, max_h = 0, max_images = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[SVO_NUM_STAGES][2] = {};
+    bool ev_used[SVO_NUM_STAGES] = {};
+
+    // ---- ORB configuration (host copies of the reference's tables)
+    bool configured = false;
+    int nfeatures = 0, nlevels = 0, iniTh = 0, minTh = 0;
+    float scaleFactor = 0;
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> features_per_level;
+    int umax[16];
+
+    // ---- geometry for the currently laid-out image size
+    int cur_w = 0, cur_h = 0;
+    PyrGeom geom;
+    std::vector<FastTile> tiles;  // all levels
+    FastTile* d_tiles = nullptr;
+    int n_tiles = 0;
+    uint32_t tile_buf_per_slot = 0, cand_per_slot = 0, lkp_per_slot = 0;
+    int kp_cap = 0;
+    int octree_ncap = 0;
+
+    // ---- device memory
+    uint8_t* d_pyr = nullptr;  // all levels, all slots
+    size_t pyr_bytes = 0;
+    void* d_tables = nullptr;  // resize tables
+    uint32_t* d_tile_buf = nullptr;
+    int* d_tile_cnt = nullptr;
+    uint32_t* d_cand = nullptr;
+    int* d_ncand = nullptr;     // slot * SVO_MAX_LEVELS + l
+    uint16_t* d_knode = nullptr;  // octree scratch, same shape as cand
+    uint32_t* d_lkp = nullptr;
+    int* d_nlkp = nullptr;
+    svo_keypoint* d_kps = nullptr;
+    uint8_t* d_desc = nullptr;
+    int* d_nkp = nullptr;
+    int* d_flags = nullptr;  // per slot
+    int8_t* d_pattern = nullptr;
+
+    // generic scratch for the standalone calls (match / fast / lk)
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    // ---- LK / full-frame FAST
+    LkLevelGeom lk[SVO_LK_LEVELS];
+    int lk_levels = 0;
+    uint8_t* d_lkpyr = nullptr;  // levels 1..3 (level 0 aliases ORB level 0)
+    std::vector<FastTile> ftiles;
+    FastTile* d_ftiles = nullptr;
+    int n_ftiles = 0;
+    uint32_t* d_ftile_buf = nullptr;
+    int* d_ftile_cnt = nullptr;
+    uint32_t ftile_buf_per_slot = 0;
+    svo_keypoint* d_fast_kps = nullptr;  // per frame slot, pt_cap each
+    int* d_nfast = nullptr;
+    int pt_cap = 0;
+    float* d_lk_pts = nullptr;      // per frame slot: 5 lists (p0,p1,p2,p3,p0r) x pt_cap x 2
+    uint8_t* d_lk_status = nullptr;  // per frame slot: 4 x pt_cap
+    float* d_lk_err = nullptr;
+
+    // ---- matches (frontend): per frame slot, kp_cap each
+    int* d_match = nullptr;  // [frame slot][4][kp_cap]: stereo idx, stereo dist, temporal idx, temporal dist
+
+    // ---- frontend state
+    int fe_mode = 0, fe_max_frames = 0, fe_ring = 0, fe_head = -1, fe_pending = 0;
+    bool fe_has_last = false;
+    bool fe_configured = false;
+    int fe_first_query_valid = 0;  // whether frame 0 of the pending batch has a predecessor
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+};
+
+#define SVO_CUDA_TRY(ctx, expr)                                                                          \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            return (ctx)->fail(SVO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+        }                                                                                                \
+    } while (0)
+
+struct StageTimer {
+    svo_ctx* c;
+    int s;
+    StageTimer(svo_ctx* ctx, int stage) : c(ctx), s(stage) {
+        if (c->timing) cudaEventRecord(c->ev[s][0], c->stream);
+    }
+    ~StageTimer() {
+        if (c->timing) {
+            cudaEventRecord(c->ev[s][1], c->stream);
+            c->ev_used[s] = true;
+        }
+    }
+};
+
+// ---- kernel launchers (one per stage; defined in k_*.cu).  n_img batch images mapped to slots through `map`.
+int launch_pyramid(svo_ctx* c, const SlotMap& map, int n_img);                       // K1
+int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img);                    // K2 + K2b
+int launch_octree(svo_ctx* c, const SlotMap& map, int n_img);                        // K3
+int launch_describe(svo_ctx* c, const SlotMap& map, int n_img);                      // K4 + K5
+int launch_match_frontend(svo_ctx* c, int first, int ring, int n_frames, int skip_first);  // K6
+int launch_fast_full(svo_ctx* c, const SlotMap& map, int n_img, int threshold);      // K9 (+ ordered compaction)
+int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img);                    // K7
+// one call of the 4-call LK chain for n_frames unit frames (K8); see k_lk.cu
+struct LkCall {
+    int prev_side, prev_back;  // prev image: side (0 left, 1 right) of frame (current - prev_back)
+    int next_side, next_back;
+    int src_list, dst_list, status_row;
+};
+int launch_lk_track(svo_ctx* c, int first, int ring, int n_frames, int skip_first, const LkCall& call, int max_iter, double eps,
+                    double min_eig);
+
+int svo_orb_run(svo_ctx* c, const SlotMap& map, int n_img);
+int svo_check_flags(svo_ctx* c, const SlotMap& map, int n_img);
+int svo_ensure_scratch(svo_ctx* c, size_t bytes);
+int svo_ensure_pinned(svo_ctx* c, size_t bytes);
+
+// host helpers
+int svo_layout(svo_ctx* c, int w, int h);
+size_t svo_align(size_t v, size_t a);
