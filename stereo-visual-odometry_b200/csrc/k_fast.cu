@@ -268,7 +268,191 @@ __global__ void __launch_bounds__(128) k_compact(PyrGeom g, SlotMap map, const F
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K9: full-frame FAST.  Tile = full-width strip of rows; NMS looks across strip borders (scores of one extra row on
+// each side are computed), the 3-px image frame scores 0 like in cv::FAST.  Output per strip in row-major order.
+// ---------------------------------------------------------------------------------------------------------------
+struct FullSmem {
+    int PW, PH, SW, SH, NI;  // NI: max (row, 32-px chunk) items per strip
+    __host__ __device__ size_t sc_off() const { return (size_t)PW * PH; }
+    __host__ __device__ size_t item_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
+    __host__ __device__ size_t queue_off() const { return item_off() + (size_t)(2 * NI + 16) * sizeof(int); }
+    __host__ __device__ size_t total() const { return queue_off() + (size_t)FW * 64 * sizeof(uint32_t); }
+};
+
+__device__ int block_scan_excl_ft(int* a, int n, int* wtmp) {  // in-place exclusive scan, all FT threads call
+    const int per = (n + FT - 1) / FT;
+    const int b = threadIdx.x * per, e = min(b + per, n);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += a[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wtmp[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < FW; ++w) {
+        const int v = wtmp[w];
+        if (w < warp) wbase += v;
+        total += v;
+    }
+    int run = wbase + incl - sum;
+    for (int i = b; i < e; ++i) {
+        const int v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(FT) k_fast_full(LevelGeom G, SlotMap map, const FastTile* __restrict__ tiles, FullSmem L, int thr,
+                                                  uint32_t* __restrict__ tile_buf, int* __restrict__ tile_cnt, int* __restrict__ flags,
+                                                  uint32_t buf_per_slot, int n_tiles) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const FastTile t = tiles[blockIdx.x];
+    const int slot = map.slot(blockIdx.y);
+    uint8_t* pix = smem;
+    uint8_t* sc = smem + L.sc_off();
+    int* cnt = reinterpret_cast<int*>(smem + L.item_off());
+    uint32_t* masks = reinterpret_cast<uint32_t*>(cnt + L.NI);
+    int* wtmp = reinterpret_cast<int*>(masks + L.NI);
+    uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L.queue_off());
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tw = t.x1 - t.x0, th = t.y1 - t.y0;
+    const int ys0 = max(t.y0 - 1, 3), ys1 = min(t.y1 + 1, G.h - 3), nsr = ys1 - ys0;
+    const int xa = (t.x0 - 3) & ~15;
+    const int nchunk = (t.x1 + 3 - xa + 15) >> 4;
+    load_window(G.base + (size_t)slot * G.plane, G.pitch, xa, ys0 - 3, nsr + 6, nchunk, pix, L.PW);
+    for (int i = threadIdx.x; i < (L.SW * (th + 2) + 15) / 16; i += FT) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    score_region(pix, L.PW, t.x0 - xa, 3, tw, nsr, thr, sc + (ys0 - t.y0) * L.SW, L.SW, queues + warp * 64);
+    __syncthreads();
+    const int nck = (tw + 31) >> 5, ni = th * nck;
+    for (int item = warp; item < ni; item += FW) {
+        const int r = item / nck, ck = item - r * nck;
+        const int lx = ck * 32 + lane;
+        const uint8_t* s1 = sc + (size_t)(r + 1) * L.SW + 1;
+        const int s = lx < tw ? s1[lx] : 0;
+        uint32_t m = 0;
+        if (__ballot_sync(0xFFFFFFFFu, s > 0)) {
+            bool keep = s > 0;
+            if (keep) {
+                const uint8_t* s0 = s1 - L.SW;
+                const uint8_t* s2 = s1 + L.SW;
+                keep = s > s0[lx - 1] && s > s0[lx] && s > s0[lx + 1] && s > s1[lx - 1] && s > s1[lx + 1] && s > s2[lx - 1] && s > s2[lx] &&
+                       s > s2[lx + 1];
+            }
+            m = __ballot_sync(0xFFFFFFFFu, keep);
+        }
+        if (lane == 0) {
+            masks[item] = m;
+            cnt[item] = __popc(m);
+        }
+    }
+    __syncthreads();
+    const int total = block_scan_excl_ft(cnt, ni, wtmp);
+    uint32_t* out = tile_buf + (size_t)slot * buf_per_slot + t.out_off;
+    for (int item = warp; item < ni; item += FW) {
+        const uint32_t m = masks[item];
+        if (!((m >> lane) & 1u)) continue;
+        const int r = item / nck, ck = item - r * nck;
+        const int lx = ck * 32 + lane;
+        const int o = cnt[item] + __popc(m & ((1u << lane) - 1));
+        if (o < t.out_cap) out[o] = pack_cand(t.x0 + lx, t.y0 + r, sc[(size_t)(r + 1) * L.SW + lx + 1]);
+    }
+    if (threadIdx.x == 0) {
+        tile_cnt[(size_t)slot * n_tiles + blockIdx.x] = min(total, t.out_cap);
+        if (total > t.out_cap) atomicOr(flags + slot, SVO_FLAG_FAST_OVERFLOW);
+    }
+}
+
+// one CTA per image: concatenate the strips' lists (row-major order) into cv::KeyPoint records
+__global__ void __launch_bounds__(128) k_compact_full(SlotMap map, const FastTile* __restrict__ tiles, int n_tiles,
+                                                      const uint32_t* __restrict__ tile_buf, const int* __restrict__ tile_cnt,
+                                                      svo_keypoint* __restrict__ kps, int* __restrict__ nkps, int* __restrict__ flags,
+                                                      uint32_t buf_per_slot, int pt_cap) {
+    __shared__ int off[129];
+    __shared__ int wsum[4];
+    __shared__ int running;
+    const int slot = map.slot(blockIdx.x);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    svo_keypoint* dst = kps + (size_t)slot * pt_cap;
+    const uint32_t* src = tile_buf + (size_t)slot * buf_per_slot;
+    for (int t0 = 0; t0 < n_tiles; t0 += 128) {
+        const int ti = t0 + threadIdx.x;
+        const int v = ti < n_tiles ? tile_cnt[(size_t)slot * n_tiles + ti] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += wsum[w];
+        off[threadIdx.x] = wbase + incl - v;
+        if (threadIdx.x == 127) off[128] = wbase + incl;
+        __syncthreads();
+        const int chunk_total = off[128], base = running;
+        for (int e = threadIdx.x; e < chunk_total; e += 128) {
+            int lo = 0, hi = 127;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (off[mid] <= e) lo = mid; else hi = mid - 1;
+            }
+            const int o = base + e;
+            if (o < pt_cap) {
+                const uint32_t c = src[tiles[t0 + lo].out_off + (e - off[lo])];
+                dst[o] = svo_keypoint{(float)cand_x(c), (float)cand_y(c), 7.f, -1.f, (float)cand_r(c), 0, -1};
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running = base + chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        nkps[slot] = min(running, pt_cap);
+        if (running > pt_cap) atomicOr(flags + slot, SVO_FLAG_FAST_OVERFLOW);
+    }
+}
+
 }  // namespace
+
+int launch_fast_full(svo_ctx* c, const SlotMap& map, int n_img, int threshold) {
+    StageTimer t(c, 6);
+    if (c->n_ftiles == 0) return SVO_OK;
+    FullSmem L{};
+    for (const FastTile& ft : c->ftiles) {
+        const int xa = (ft.x0 - 3) & ~15;
+        L.PW = std::max(L.PW, (int)svo_align(ft.x1 + 3 - xa, 16));
+        L.PH = std::max(L.PH, ft.y1 - ft.y0 + 8);
+        L.SW = std::max(L.SW, (int)svo_align(ft.x1 - ft.x0 + 2, 16));
+        L.SH = std::max(L.SH, ft.y1 - ft.y0 + 2);
+        L.NI = std::max(L.NI, (ft.y1 - ft.y0) * ((ft.x1 - ft.x0 + 31) / 32));
+    }
+    const size_t smem = L.total();
+    if (smem > 200 * 1024) return c->fail(SVO_ERR_INVALID, "full-frame FAST strip does not fit in shared memory");
+    SVO_CUDA_TRY(c, cudaFuncSetAttribute(k_fast_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    threshold = std::min(std::max(threshold, 0), 255);
+    dim3 grid(c->n_ftiles, n_img);
+    k_fast_full<<<grid, FT, smem, c->stream>>>(c->geom.lvl[0], map, c->d_ftiles, L, threshold, c->d_ftile_buf, c->d_ftile_cnt, c->d_flags,
+                                               c->ftile_buf_per_slot, c->n_ftiles);
+    ++c->launches;
+    k_compact_full<<<n_img, 128, 0, c->stream>>>(map, c->d_ftiles, c->n_ftiles, c->d_ftile_buf, c->d_ftile_cnt, c->d_fast_kps, c->d_nfast,
+                                                 c->d_flags, c->ftile_buf_per_slot, c->pt_cap);
+    ++c->launches;
+    SVO_CUDA_TRY(c, cudaGetLastError());
+    return SVO_OK;
+}
 
 int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
     const PyrGeom& g = c->geom;

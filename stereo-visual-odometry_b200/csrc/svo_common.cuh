@@ -154,10 +154,12 @@ struct svo_ctx {
     int* d_match = nullptr;  // [frame slot][4][kp_cap]: stereo idx, stereo dist, temporal idx, temporal dist
 
     // ---- frontend state
-    int fe_mode = 0, fe_max_frames = 0, fe_ring = 0, fe_head = -1, fe_pending = 0;
+    int fe_mode = 0, fe_max_frames = 0, fe_ring = 0, fe_head = -1, fe_pending = 0, fe_first = 0;
+    int fe_done_first = 0, fe_done_n = 0, fe_done_skip = 0;  // the last completed run (what download reads)
     bool fe_has_last = false;
     bool fe_configured = false;
-    int fe_first_query_valid = 0;  // whether frame 0 of the pending batch has a predecessor
+    bool aux_ready = false;        // LK pyramid / full-frame FAST buffers laid out for the current size
+    bool user_configured = false;  // svo_orb_configure() was called by the user (not the detector-only default)
 
     int fail(int code, const std::string& msg) {
         err = msg;

@@ -60,6 +60,8 @@ static void free_layout(svo_ctx* c) {
         *p = nullptr;
     }
     c->cur_w = c->cur_h = 0;
+    c->aux_ready = false;
+    c->fe_configured = false;
 }
 
 extern "C" void svo_ctx_destroy(svo_ctx* c) {
@@ -111,7 +113,13 @@ extern "C" float svo_ctx_stage_ms(const svo_ctx* c, int stage) {
 // ---------------------------------------------------------------------------------------------------------------
 // ORBextractor::ORBextractor (ORBextractor.cpp:359-418)
 // ---------------------------------------------------------------------------------------------------------------
+int svo_orb_configure_impl(svo_ctx* c, int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, bool by_user);
+
 extern "C" int svo_orb_configure(svo_ctx* c, int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
+    return svo_orb_configure_impl(c, nfeatures, scaleFactor, nlevels, iniTh, minTh, true);
+}
+
+int svo_orb_configure_impl(svo_ctx* c, int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, bool by_user) {
     if (!c) return SVO_ERR_INVALID;
     if (nfeatures < 0 || nlevels < 1 || nlevels > SVO_MAX_LEVELS || !(scaleFactor > 1.f) || iniTh < 0 || iniTh > 255 ||
         minTh < 0 || minTh > iniTh)
@@ -161,6 +169,7 @@ extern "C" int svo_orb_configure(svo_ctx* c, int nfeatures, float scaleFactor, i
         SVO_CUDA_TRY(c, cudaMemcpy(c->d_pattern, kBriefPattern, sizeof(kBriefPattern), cudaMemcpyHostToDevice));
     }
     c->configured = true;
+    c->user_configured = by_user;
     free_layout(c);  // geometry depends on the tables
     return SVO_OK;
 }
@@ -381,7 +390,6 @@ int svo_layout(svo_ctx* c, int w, int h) {
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_flags, 0, sizeof(int) * S, c->stream));
     c->cur_w = w;
     c->cur_h = h;
-    c->fe_configured = false;
     return SVO_OK;
 }
 
@@ -425,7 +433,7 @@ int svo_orb_run(svo_ctx* c, const SlotMap& map, int n_img) {
 extern "C" int svo_orb_extract_batch(svo_ctx* c, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride,
                                      svo_keypoint* kps, uint8_t* desc, int cap_per_img, int* n_out) {
     if (!c) return SVO_ERR_INVALID;
-    if (!c->configured) return c->fail(SVO_ERR_NOT_CONFIGURED, "svo_orb_configure() first");
+    if (!c->user_configured) return c->fail(SVO_ERR_NOT_CONFIGURED, "svo_orb_configure() first");
     if (n_imgs < 0 || n_imgs > c->max_images || !n_out) return c->fail(SVO_ERR_INVALID, "svo_orb_extract_batch: bad n_imgs / n_out");
     for (int i = 0; i < n_imgs; ++i) n_out[i] = 0;
     if (n_imgs == 0 || w == 0 || h == 0 || !imgs) return SVO_OK;  // empty image: silent return (ORBextractor.cpp:993-994)

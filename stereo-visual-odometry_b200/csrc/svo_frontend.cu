@@ -1,10 +1,333 @@
-// TEMPORARY stubs (replaced by the real implementation in the next milestone)
+// svo_frontend.cu -- host orchestration of the Tracking front-end entry points of the C ABI:
+//   svo_fast_detect   <- Tracking::Detect_OpenCVFASTFeatures            (tracking.cpp:94-113)
+//   svo_lk_track      <- one cv::calcOpticalFlowPyrLK call               (tracking.cpp:593-618)
+//   svo_frontend_*    <- Detect_MyORBFeatures + the two BF matches (tracking.cpp:502-544) and/or FAST + the 4-call LK
+//                        chain (tracking.cpp:258-271, 583-618) for a batch of consecutive stereo frames, with the
+//                        previous frame (Tracking::last_frame_) carried in a ring of frame slots on the device.
+// No pixel arithmetic happens here; see k_*.cu.
+#include <algorithm>
+#include <cstring>
+
 #include "svo_common.cuh"
-extern "C" int svo_fast_detect(svo_ctx* c, const uint8_t*, int, int, size_t, int, int, svo_keypoint*, int, int*) { return c ? c->fail(SVO_ERR_INVALID, "not implemented") : SVO_ERR_INVALID; }
-extern "C" int svo_lk_track(svo_ctx* c, const uint8_t*, const uint8_t*, int, int, size_t, const float*, int, float*, uint8_t*, float*, int, int, int, double, double) { return c ? c->fail(SVO_ERR_INVALID, "not implemented") : SVO_ERR_INVALID; }
-extern "C" int svo_frontend_configure(svo_ctx* c, int, int, int, int) { return c ? c->fail(SVO_ERR_INVALID, "not implemented") : SVO_ERR_INVALID; }
-extern "C" int svo_frontend_reset(svo_ctx* c) { return c ? c->fail(SVO_ERR_INVALID, "not implemented") : SVO_ERR_INVALID; }
-extern "C" int svo_frontend_upload(svo_ctx* c, const uint8_t*, const uint8_t*, int, size_t) { return c ? c->fail(SVO_ERR_INVALID, "not implemented") : SVO_ERR_INVALID; }
-extern "C" int svo_frontend_run(svo_ctx* c) { return c ? c->fail(SVO_ERR_INVALID, "not implemented") : SVO_ERR_INVALID; }
-extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out*) { return c ? c->fail(SVO_ERR_INVALID, "not implemented") : SVO_ERR_INVALID; }
-extern "C" int svo_frontend_batch(svo_ctx* c, const uint8_t*, const uint8_t*, int, size_t, svo_frontend_out*) { return c ? c->fail(SVO_ERR_INVALID, "not implemented") : SVO_ERR_INVALID; }
+
+int launch_lk_standalone(svo_ctx* c, int n, int max_level, int max_iter, double eps, double min_eig, int want_err);
+int svo_orb_configure_impl(svo_ctx* c, int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, bool by_user);
+
+static int ensure_config(svo_ctx* c) {
+    if (c->configured) return SVO_OK;
+    return svo_orb_configure_impl(c, 0, 1.2f, 1, 20, 7, false);  // detector-only layout: level 0 only
+}
+
+// LK pyramid levels 1..3 and the full-frame FAST / LK point buffers for the current image size
+static int layout_aux(svo_ctx* c, int pt_cap) {
+    if (c->aux_ready && c->pt_cap >= pt_cap) return SVO_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    void** ptrs[] = {(void**)&c->d_lkpyr,    (void**)&c->d_ftiles,  (void**)&c->d_ftile_buf, (void**)&c->d_ftile_cnt, (void**)&c->d_fast_kps,
+                     (void**)&c->d_nfast,    (void**)&c->d_lk_pts,  (void**)&c->d_lk_status, (void**)&c->d_lk_err};
+    for (void** p : ptrs) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    c->aux_ready = false;
+    const int S = c->max_images, w = c->cur_w, h = c->cur_h;
+    if (w > SVO_MAX_DIM || h > SVO_MAX_DIM) return c->fail(SVO_ERR_INVALID, "full-frame FAST / LK support images up to 4096 x 4096");
+    const LevelGeom& L0 = c->geom.lvl[0];
+    c->lk[0] = LkLevelGeom{L0.base, L0.w, L0.h, L0.pitch, L0.plane};
+    c->lk_levels = 1;
+    size_t total = 0;
+    std::vector<size_t> off(SVO_LK_LEVELS, 0);
+    for (int l = 1; l < SVO_LK_LEVELS; ++l) {
+        const int lw = (c->lk[l - 1].w + 1) / 2, lh = (c->lk[l - 1].h + 1) / 2;
+        if (lw <= SVO_LK_WIN || lh <= SVO_LK_WIN) break;  // buildOpticalFlowPyramid stops before a level <= winSize
+        c->lk[l].w = lw;
+        c->lk[l].h = lh;
+        c->lk[l].pitch = (int)svo_align(lw, 64);
+        c->lk[l].plane = (uint32_t)c->lk[l].pitch * lh;
+        off[l] = total;
+        total += svo_align((size_t)c->lk[l].plane * S, 256);
+        c->lk_levels = l + 1;
+    }
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkpyr, total + 4096));
+    for (int l = 1; l < c->lk_levels; ++l) c->lk[l].base = c->d_lkpyr + off[l];
+
+    // full-frame FAST strips over the inner domain [3, w-3) x [3, h-3)
+    c->ftiles.clear();
+    uint32_t boff = 0;
+    if (w >= 7 && h >= 7) {
+        const int R = (int)svo_align(w, 16) <= 2048 ? 16 : 8;
+        for (int y0 = 3; y0 < h - 3; y0 += R) {
+            FastTile t{};
+            t.x0 = 3;
+            t.x1 = w - 3;
+            t.y0 = y0;
+            t.y1 = std::min(y0 + R, h - 3);
+            t.out_cap = std::max(64, (t.x1 - t.x0) * (t.y1 - t.y0) / 8);
+            t.out_off = (int)boff;
+            boff += (uint32_t)t.out_cap;
+            c->ftiles.push_back(t);
+        }
+    }
+    c->n_ftiles = (int)c->ftiles.size();
+    c->ftile_buf_per_slot = boff;
+    c->pt_cap = std::max(pt_cap, 256);
+    if (c->n_ftiles) {
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_ftiles, sizeof(FastTile) * c->n_ftiles));
+        SVO_CUDA_TRY(c, cudaMemcpy(c->d_ftiles, c->ftiles.data(), sizeof(FastTile) * c->n_ftiles, cudaMemcpyHostToDevice));
+    }
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_ftile_buf, sizeof(uint32_t) * std::max<size_t>(1, (size_t)boff * S)));
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_ftile_cnt, sizeof(int) * std::max<size_t>(1, (size_t)c->n_ftiles * S)));
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_fast_kps, sizeof(svo_keypoint) * (size_t)c->pt_cap * S));
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_nfast, sizeof(int) * S));
+    SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nfast, 0, sizeof(int) * S, c->stream));
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_pts, sizeof(float) * 2 * 5 * (size_t)c->pt_cap * S));
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_status, (size_t)4 * c->pt_cap * S));
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_err, sizeof(float) * (size_t)c->pt_cap));
+    c->aux_ready = true;
+    return SVO_OK;
+}
+
+extern "C" int svo_fast_detect(svo_ctx* c, const uint8_t* img, int w, int h, size_t stride, int threshold, int nms, svo_keypoint* kps,
+                               int cap, int* n_out) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!n_out) return c->fail(SVO_ERR_INVALID, "n_out is null");
+    *n_out = 0;
+    if (!img || w == 0 || h == 0) return SVO_OK;
+    if (!nms) return c->fail(SVO_ERR_INVALID, "svo_fast_detect: only nonmaxSuppression=true is on the reference path (tracking.cpp:100)");
+    if (w < 0 || h < 0 || stride < (size_t)w || cap < 0 || (cap > 0 && !kps)) return c->fail(SVO_ERR_INVALID, "svo_fast_detect: bad arguments");
+    cudaSetDevice(c->device);
+    int rc;
+    if ((rc = ensure_config(c)) != SVO_OK) return rc;
+    if ((rc = svo_layout(c, w, h)) != SVO_OK) return rc;
+    if ((rc = layout_aux(c, std::max(cap, w * h / 64))) != SVO_OK) return rc;
+    const LevelGeom& L0 = c->geom.lvl[0];
+    SVO_CUDA_TRY(c, cudaMemcpy2DAsync(L0.base, L0.pitch, img, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    SlotMap map{1, 0, 0, c->max_images};
+    if ((rc = launch_fast_full(c, map, 1, threshold)) != SVO_OK) return rc;
+    int n = 0;
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(&n, c->d_nfast, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = svo_check_flags(c, map, 1)) != SVO_OK) return rc;
+    *n_out = n;
+    if (n > cap) return c->fail(SVO_ERR_CAPACITY, "svo_fast_detect: more corners than cap");
+    if (n > 0) SVO_CUDA_TRY(c, cudaMemcpyAsync(kps, c->d_fast_kps, sizeof(svo_keypoint) * n, cudaMemcpyDeviceToHost, c->stream));
+    SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
+extern "C" int svo_lk_track(svo_ctx* c, const uint8_t* prev, const uint8_t* next, int w, int h, size_t stride, const float* prev_xy, int n,
+                            float* next_xy, uint8_t* status, float* err, int win, int max_level, int max_iter, double eps, double min_eig) {
+    if (!c) return SVO_ERR_INVALID;
+    if (win != SVO_LK_WIN) return c->fail(SVO_ERR_INVALID, "svo_lk_track: winSize must be 21x21 (tracking.cpp:594)");
+    if (max_level < 0 || max_level > SVO_LK_LEVELS - 1) return c->fail(SVO_ERR_INVALID, "svo_lk_track: maxLevel must be 0..3");
+    if (!prev || !next || w <= 0 || h <= 0 || stride < (size_t)w || n < 0 || (n > 0 && (!prev_xy || !next_xy || !status)))
+        return c->fail(SVO_ERR_INVALID, "svo_lk_track: bad arguments");
+    if (c->max_images < 2) return c->fail(SVO_ERR_INVALID, "svo_lk_track needs a context with max_images >= 2");
+    if (n == 0) return SVO_OK;
+    cudaSetDevice(c->device);
+    int rc;
+    if ((rc = ensure_config(c)) != SVO_OK) return rc;
+    if ((rc = svo_layout(c, w, h)) != SVO_OK) return rc;
+    if ((rc = layout_aux(c, std::max(n, w * h / 64))) != SVO_OK) return rc;
+    const LevelGeom& L0 = c->geom.lvl[0];
+    SVO_CUDA_TRY(c, cudaMemcpy2DAsync(L0.base, L0.pitch, prev, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    SVO_CUDA_TRY(c, cudaMemcpy2DAsync(L0.base + L0.plane, L0.pitch, next, stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(c->d_lk_pts, prev_xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    SlotMap map{1, 0, 0, c->max_images};
+    if ((rc = launch_lk_pyramid(c, map, 2)) != SVO_OK) return rc;
+    if ((rc = launch_lk_standalone(c, n, max_level, max_iter, eps, min_eig, err != nullptr)) != SVO_OK) return rc;
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(next_xy, c->d_lk_pts + (size_t)1 * c->pt_cap * 2, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(status, c->d_lk_status, n, cudaMemcpyDeviceToHost, c->stream));
+    if (err) SVO_CUDA_TRY(c, cudaMemcpyAsync(err, c->d_lk_err, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// throughput mode
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int max_frames) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!(mode & (SVO_MODE_ORB | SVO_MODE_LK)) || (mode & ~(SVO_MODE_ORB | SVO_MODE_LK)) || w <= 0 || h <= 0 || max_frames < 1)
+        return c->fail(SVO_ERR_INVALID, "svo_frontend_configure: bad mode / size / max_frames");
+    if (2 * (max_frames + 1) > c->max_images) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure: need max_images >= 2 * (max_frames + 1)");
+    if ((mode & SVO_MODE_ORB) && !c->user_configured) return c->fail(SVO_ERR_NOT_CONFIGURED, "svo_orb_configure() first");
+    cudaSetDevice(c->device);
+    int rc;
+    if ((rc = ensure_config(c)) != SVO_OK) return rc;
+    if ((rc = svo_layout(c, w, h)) != SVO_OK) return rc;
+    if (mode & SVO_MODE_LK)
+        if ((rc = layout_aux(c, std::max(1024, w * h / 64))) != SVO_OK) return rc;
+    c->fe_ring = max_frames + 1;
+    if (mode & SVO_MODE_ORB) {
+        if (c->d_match) cudaFree(c->d_match);
+        c->d_match = nullptr;
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_match, sizeof(int) * 4 * (size_t)c->kp_cap * c->fe_ring));
+    }
+    c->fe_mode = mode;
+    c->fe_max_frames = max_frames;
+    c->fe_head = c->fe_ring - 1;
+    c->fe_has_last = false;
+    c->fe_pending = 0;
+    c->fe_done_n = 0;
+    c->fe_configured = true;
+    return SVO_OK;
+}
+
+extern "C" int svo_frontend_reset(svo_ctx* c) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!c->fe_configured) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure() first");
+    c->fe_has_last = false;
+    c->fe_pending = 0;
+    c->fe_done_n = 0;
+    return SVO_OK;
+}
+
+extern "C" int svo_frontend_upload(svo_ctx* c, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!c->fe_configured) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure() first");
+    if (!left || !right || n_frames < 1 || n_frames > c->fe_max_frames || stride < (size_t)c->cur_w)
+        return c->fail(SVO_ERR_INVALID, "svo_frontend_upload: bad arguments");
+    cudaSetDevice(c->device);
+    const LevelGeom& L0 = c->geom.lvl[0];
+    const int ring = c->fe_ring, first = (c->fe_head + 1) % ring, w = c->cur_w, h = c->cur_h;
+    const int run1 = std::min(n_frames, ring - first), run2 = n_frames - run1;
+    const uint8_t* srcs[2] = {left, right};
+    for (int side = 0; side < 2; ++side) {
+        uint8_t* base = L0.base + (size_t)side * ring * L0.plane;
+        SVO_CUDA_TRY(c, cudaMemcpy2DAsync(base + (size_t)first * L0.plane, L0.pitch, srcs[side], stride, w, (size_t)h * run1,
+                                          cudaMemcpyHostToDevice, c->stream));
+        if (run2 > 0)
+            SVO_CUDA_TRY(c, cudaMemcpy2DAsync(base, L0.pitch, srcs[side] + (size_t)run1 * h * stride, stride, w, (size_t)h * run2,
+                                              cudaMemcpyHostToDevice, c->stream));
+    }
+    c->fe_first = first;
+    c->fe_pending = n_frames;
+    return SVO_OK;
+}
+
+extern "C" int svo_frontend_run(svo_ctx* c) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!c->fe_configured || c->fe_pending < 1) return c->fail(SVO_ERR_INVALID, "svo_frontend_run: nothing uploaded");
+    cudaSetDevice(c->device);
+    const int ring = c->fe_ring, first = c->fe_first, n = c->fe_pending, skip_first = c->fe_has_last ? 0 : 1;
+    int rc;
+    const SlotMap both{2, ring, first, ring}, leftonly{1, 0, first, ring};
+    if (c->fe_mode & SVO_MODE_ORB) {
+        if ((rc = svo_orb_run(c, both, 2 * n)) != SVO_OK) return rc;
+        if ((rc = launch_match_frontend(c, first, ring, n, skip_first)) != SVO_OK) return rc;
+    }
+    if (c->fe_mode & SVO_MODE_LK) {
+        if ((rc = launch_fast_full(c, leftonly, n, 20)) != SVO_OK) return rc;  // int fast_threshold = 20 (tracking.cpp:99)
+        if ((rc = launch_lk_pyramid(c, both, 2 * n)) != SVO_OK) return rc;
+        // the 4-call chain (tracking.cpp:593-618): L(t-1)->R(t-1), R(t-1)->R(t), R(t)->L(t), L(t)->L(t-1)
+        const LkCall calls[4] = {{0, 1, 1, 1, 0, 1, 0}, {1, 1, 1, 0, 1, 2, 1}, {1, 0, 0, 0, 2, 3, 2}, {0, 0, 0, 1, 3, 4, 3}};
+        for (int k = 0; k < 4; ++k)
+            if ((rc = launch_lk_track(c, first, ring, n, skip_first, calls[k], 30, 0.01, 0.001)) != SVO_OK) return rc;
+    }
+    c->fe_done_first = first;
+    c->fe_done_n = n;
+    c->fe_done_skip = skip_first;
+    c->fe_head = (first + n - 1) % ring;
+    c->fe_has_last = true;
+    c->fe_pending = 0;
+    return SVO_OK;
+}
+
+namespace {
+// copy `rows_per_frame` rows of `row_bytes` bytes (device row pitch dev_pitch, host row pitch host_pitch) for the frames of
+// the last run; frames occupy at most two contiguous runs of ring slots.
+struct RingCopy {
+    svo_ctx* c;
+    int first, n, ring;
+    int copy(void* host, size_t host_frame_bytes, const void* dev, size_t dev_slot_bytes, size_t width_bytes) {
+        // one "row" per frame
+        const int run1 = std::min(n, ring - first), run2 = n - run1;
+        if (width_bytes == 0) return SVO_OK;
+        SVO_CUDA_TRY(c, cudaMemcpy2DAsync(host, host_frame_bytes, (const uint8_t*)dev + (size_t)first * dev_slot_bytes, dev_slot_bytes,
+                                          width_bytes, run1, cudaMemcpyDeviceToHost, c->stream));
+        if (run2 > 0)
+            SVO_CUDA_TRY(c, cudaMemcpy2DAsync((uint8_t*)host + (size_t)run1 * host_frame_bytes, host_frame_bytes, dev, dev_slot_bytes,
+                                              width_bytes, run2, cudaMemcpyDeviceToHost, c->stream));
+        return SVO_OK;
+    }
+};
+}  // namespace
+
+extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!c->fe_configured || c->fe_done_n < 1 || !out) return c->fail(SVO_ERR_INVALID, "svo_frontend_download: nothing to download");
+    cudaSetDevice(c->device);
+    const int ring = c->fe_ring, first = c->fe_done_first, n = c->fe_done_n, skip = c->fe_done_skip;
+    const int S = c->max_images;
+    int rc;
+    // ---- counts first (one small copy + sync), then exact-width 2-D copies
+    std::vector<int> nkp(S, 0), nfast(S, 0), flags(S, 0);
+    if (c->fe_mode & SVO_MODE_ORB) SVO_CUDA_TRY(c, cudaMemcpyAsync(nkp.data(), c->d_nkp, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    if (c->fe_mode & SVO_MODE_LK) SVO_CUDA_TRY(c, cudaMemcpyAsync(nfast.data(), c->d_nfast, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(flags.data(), c->d_flags, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
+    SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < n; ++f) {
+        const int fs = (first + f) % ring;
+        if (flags[fs] | flags[ring + fs]) {
+            cudaMemsetAsync(c->d_flags, 0, sizeof(int) * S, c->stream);
+            char msg[128];
+            snprintf(msg, sizeof msg, "device capacity exceeded on frame %d (flags 0x%x / 0x%x)", f, flags[fs], flags[ring + fs]);
+            return c->fail(SVO_ERR_CAPACITY, msg);
+        }
+    }
+    RingCopy rcpy{c, first, n, ring};
+    if (c->fe_mode & SVO_MODE_ORB) {
+        const int K = c->kp_cap;
+        if (out->kp_cap < K) return c->fail(SVO_ERR_CAPACITY, "svo_frontend_out.kp_cap < svo_orb_capacity()");
+        int maxL = 0, maxR = 0, maxQ = 0;
+        for (int f = 0; f < n; ++f) {
+            const int fs = (first + f) % ring, ps = (first + f - 1 + ring) % ring;
+            maxL = std::max(maxL, nkp[fs]);
+            maxR = std::max(maxR, nkp[ring + fs]);
+            const int nq = (f == 0 && skip) ? 0 : nkp[ps];
+            maxQ = std::max(maxQ, nq);
+            if (out->n_left) out->n_left[f] = nkp[fs];
+            if (out->n_right) out->n_right[f] = nkp[ring + fs];
+            if (out->n_query) out->n_query[f] = nq;
+        }
+        const size_t hk = (size_t)out->kp_cap;
+        if (out->kps_left && (rc = rcpy.copy(out->kps_left, hk * 28, c->d_kps, (size_t)K * 28, (size_t)maxL * 28))) return rc;
+        if (out->desc_left && (rc = rcpy.copy(out->desc_left, hk * 32, c->d_desc, (size_t)K * 32, (size_t)maxL * 32))) return rc;
+        if (out->kps_right && (rc = rcpy.copy(out->kps_right, hk * 28, c->d_kps + (size_t)ring * K, (size_t)K * 28, (size_t)maxR * 28))) return rc;
+        if (out->desc_right && (rc = rcpy.copy(out->desc_right, hk * 32, c->d_desc + (size_t)ring * K * 32, (size_t)K * 32, (size_t)maxR * 32))) return rc;
+        int32_t* mh[4] = {out->stereo_idx, out->stereo_dist, out->temporal_idx, out->temporal_dist};
+        for (int r = 0; r < 4; ++r)
+            if (mh[r] && (rc = rcpy.copy(mh[r], hk * 4, c->d_match + (size_t)r * K, (size_t)4 * K * 4, (size_t)maxQ * 4))) return rc;
+    }
+    if (c->fe_mode & SVO_MODE_LK) {
+        const int P = c->pt_cap;
+        if (out->pt_cap < 1) return c->fail(SVO_ERR_CAPACITY, "svo_frontend_out.pt_cap < 1");
+        int maxF = 0, maxS = 0;
+        for (int f = 0; f < n; ++f) {
+            const int fs = (first + f) % ring, ps = (first + f - 1 + ring) % ring;
+            const int ns = (f == 0 && skip) ? 0 : nfast[ps];
+            maxF = std::max(maxF, nfast[fs]);
+            maxS = std::max(maxS, ns);
+            if (out->n_fast) out->n_fast[f] = nfast[fs];
+            if (out->n_seed) out->n_seed[f] = ns;
+        }
+        if (maxF > out->pt_cap || maxS > out->pt_cap) return c->fail(SVO_ERR_CAPACITY, "more FAST corners / LK seeds than svo_frontend_out.pt_cap");
+        const size_t hp = (size_t)out->pt_cap;
+        if (out->fast_kps && (rc = rcpy.copy(out->fast_kps, hp * 28, c->d_fast_kps, (size_t)P * 28, (size_t)maxF * 28))) return rc;
+        float* ph[4] = {out->lk_p1, out->lk_p2, out->lk_p3, out->lk_p0r};
+        for (int r = 0; r < 4; ++r)
+            if (ph[r] && (rc = rcpy.copy(ph[r], hp * 8, c->d_lk_pts + (size_t)(r + 1) * P * 2, (size_t)5 * P * 8, (size_t)maxS * 8))) return rc;
+        if (out->lk_status)
+            for (int r = 0; r < 4; ++r)
+                if ((rc = rcpy.copy(out->lk_status + (size_t)r * hp, 4 * hp, c->d_lk_status + (size_t)r * P, (size_t)4 * P, (size_t)maxS))) return rc;
+    }
+    SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SVO_OK;
+}
+
+extern "C" int svo_frontend_batch(svo_ctx* c, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride, svo_frontend_out* out) {
+    int rc;
+    if ((rc = svo_frontend_upload(c, left, right, n_frames, stride)) != SVO_OK) return rc;
+    if ((rc = svo_frontend_run(c)) != SVO_OK) return rc;
+    return svo_frontend_download(c, out);
+}

@@ -1,0 +1,87 @@
+"""GPU parity of the throughput mode: batches of consecutive stereo frames with the previous frame carried on the device."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_chain(orc, l0, r0, l1, r1, seeds):
+    p1, s1, _ = orc.lk_track(l0, r0, seeds)
+    p2, s2, _ = orc.lk_track(r0, r1, p1)
+    p3, s3, _ = orc.lk_track(r1, l1, p2)
+    p0r, s4, _ = orc.lk_track(l1, l0, p3)
+    return (p1, p2, p3, p0r), (s1, s2, s3, s4)
+
+
+@pytest.mark.parametrize("w,h,nfeat,max_frames,n_total", [(640, 200, 500, 3, 7), (1241, 376, 1000, 4, 5)])
+def test_frontend_sequence(pkg, orc, w, h, nfeat, max_frames, n_total):
+    seed = 1000
+    left, right = pkg.synth_sequence(seed, 13, n_total, w, h)  # frames 13..: crosses the canvas re-seed at frame 16
+    ctx = pkg.Context(0, w, h, 2 * (max_frames + 1))
+    ctx.orb_configure(nfeat, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, max_frames)
+    kp_cap, pt_cap = ctx.orb_capacity(w, h), max(1024, w * h // 64)
+    oracle = orc.OrbOracle(nfeat, 1.2, 8, 20, 7)
+    prev = None  # oracle-side last frame
+    f0 = 0
+    while f0 < n_total:
+        n = min(max_frames, n_total - f0)
+        out = pkg.FrontendBuffers(n, kp_cap, pt_cap)
+        ctx.frontend_batch(np.ascontiguousarray(left[f0:f0 + n]), np.ascontiguousarray(right[f0:f0 + n]), out)
+        for i in range(n):
+            f = f0 + i
+            okl, odl = oracle.extract(left[f])
+            okr, odr = oracle.extract(right[f])
+            nl, nr = out.n_left[i], out.n_right[i]
+            assert nl == len(okl) and nr == len(okr)
+            assert np.array_equal(out.kps_left[i, :nl], okl) and np.array_equal(out.kps_right[i, :nr], okr)
+            assert np.unpackbits(out.desc_left[i, :nl] ^ odl).sum() <= 2
+            assert np.unpackbits(out.desc_right[i, :nr] ^ odr).sum() <= 2
+            ofast = orc.fast9(left[f], 20)
+            assert out.n_fast[i] == len(ofast) and np.array_equal(out.fast_kps[i, :len(ofast)], ofast)
+            if prev is None:
+                assert out.n_query[i] == 0 and out.n_seed[i] == 0
+            else:
+                # K6 on the descriptors the GPU produced for the previous / current frame
+                nq = out.n_query[i]
+                assert nq == len(prev["dl"])
+                si, sd = orc.match_hamming(prev["dl"], prev["dr"])
+                ti, td = orc.match_hamming(prev["dl"], out.desc_left[i, :nl])
+                assert np.array_equal(out.stereo_idx[i, :nq], si) and np.array_equal(out.stereo_dist[i, :nq], sd)
+                assert np.array_equal(out.temporal_idx[i, :nq], ti) and np.array_equal(out.temporal_dist[i, :nq], td)
+                # the 4-call LK chain seeded with the previous frame's FAST corners
+                ns = out.n_seed[i]
+                seeds = np.stack([prev["fast"]["x"], prev["fast"]["y"]], 1)
+                assert ns == len(seeds)
+                (p1, p2, p3, p0r), sts = _oracle_chain(orc, prev["l"], prev["r"], left[f], right[f], seeds)
+                cum = np.ones(ns, bool)
+                for k, (gp, op) in enumerate(zip((out.lk_p1, out.lk_p2, out.lk_p3, out.lk_p0r), (p1, p2, p3, p0r))):
+                    gs = out.lk_status[i, k, :ns]
+                    # cumulative status: a failed point carries garbage into the next call (quirk Q5)
+                    assert np.array_equal(gs[cum], sts[k][cum]), f"status of call {k + 1}"
+                    cum &= sts[k] == 1
+                    assert np.abs(gp[i, :ns] - op)[cum].max() <= 0.01, f"points of call {k + 1}"
+                keep_g = orc.lk_chain_filter(seeds, out.lk_p1[i, :ns], out.lk_p2[i, :ns], out.lk_p3[i, :ns], out.lk_p0r[i, :ns],
+                                             *[out.lk_status[i, k, :ns] for k in range(4)])
+                keep_o = orc.lk_chain_filter(seeds, p1, p2, p3, p0r, *sts)
+                assert np.array_equal(keep_g, keep_o)
+            prev = dict(l=left[f], r=right[f], dl=out.desc_left[i, :nl].copy(), dr=out.desc_right[i, :nr].copy(), fast=ofast)
+        f0 += n
+    ctx.close()
+
+
+def test_frontend_reset_and_partial_outputs(pkg):
+    w, h = 640, 200
+    left, right = pkg.synth_sequence(5, 0, 4, w, h)
+    ctx = pkg.Context(0, w, h, 6)
+    ctx.orb_configure(300, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB, 2)
+    kp_cap = ctx.orb_capacity(w, h)
+    a = pkg.FrontendBuffers(2, kp_cap, 1, fields=("n_left", "n_query", "stereo_idx"))
+    ctx.frontend_batch(np.ascontiguousarray(left[:2]), np.ascontiguousarray(right[:2]), a)
+    assert a.n_query[0] == 0 and a.n_query[1] == a.n_left[0]
+    ctx.frontend_reset()
+    b = pkg.FrontendBuffers(2, kp_cap, 1, fields=("n_left", "n_query", "stereo_idx"))
+    ctx.frontend_batch(np.ascontiguousarray(left[:2]), np.ascontiguousarray(right[:2]), b)
+    assert np.array_equal(a.n_left, b.n_left) and np.array_equal(a.n_query, b.n_query) and np.array_equal(a.stereo_idx, b.stereo_idx)
+    ctx.close()

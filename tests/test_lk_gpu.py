@@ -1,0 +1,91 @@
+"""GPU parity: full-frame FAST (tracking.cpp:101) and cv::calcOpticalFlowPyrLK (tracking.cpp:593-618) through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LK_TOL = 0.01  # px, BASELINE.json north_star: "LK tracked points must agree within 0.01 px, with an identical status mask"
+
+
+@pytest.mark.parametrize("w,h,seed", [(1241, 376, 1000), (640, 200, 7), (333, 257, 11), (1920, 1080, 2000)])
+@pytest.mark.parametrize("thr", [20, 7])
+def test_fast_full_frame(pkg, orc, w, h, seed, thr):
+    left, _ = pkg.synth_stereo_frame(seed, 2, w, h)
+    ctx = pkg.Context(0, w, h, 2)
+    g = ctx.fast_detect(left, thr)
+    o = orc.fast9(left, thr)
+    assert len(g) == len(o) and len(g) > 50
+    for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(g[f], o[f]), f  # bit-exact, row-major order included
+    ctx.close()
+
+
+def test_fast_flat_and_tiny(pkg):
+    ctx = pkg.Context(0, 640, 480, 2)
+    assert len(ctx.fast_detect(np.full((480, 640), 9, np.uint8), 20)) == 0
+    assert len(ctx.fast_detect(np.full((6, 6), 9, np.uint8), 20)) == 0  # smaller than the 7x7 FAST footprint
+    ctx.close()
+
+
+def _check_lk(g, o, n_min_ok):
+    (gp, gs, ge), (op, os_, oe) = g, o
+    assert np.array_equal(gs, os_), f"status differs at {np.nonzero(gs != os_)[0][:10]}"
+    ok = os_ == 1
+    assert ok.sum() >= n_min_ok
+    d = np.abs(gp - op)[ok]
+    assert d.max() <= LK_TOL, f"max |dp| = {d.max()}"
+    assert np.abs(ge - oe)[ok].max() <= 1e-3
+    return float(d.max())
+
+
+@pytest.mark.parametrize("w,h,seed", [(1241, 376, 1000), (640, 200, 7), (333, 257, 11)])
+def test_lk_stereo_and_temporal(pkg, orc, w, h, seed):
+    l0, r0 = pkg.synth_stereo_frame(seed, 3, w, h)
+    l1, r1 = pkg.synth_stereo_frame(seed, 4, w, h)
+    ctx = pkg.Context(0, w, h, 2)
+    kp = ctx.fast_detect(l0, 20)
+    pts = np.stack([kp["x"], kp["y"]], 1)
+    worst = 0.0
+    for a, b in ((l0, r0), (r0, r1), (r1, l1), (l1, l0)):
+        worst = max(worst, _check_lk(ctx.lk_track(a, b, pts), orc.lk_track(a, b, pts), len(pts) // 2))
+    print(f"{w}x{h}: {len(pts)} points, max |dp| = {worst:.2e} px")
+    ctx.close()
+
+
+def test_lk_border_and_lost_points(pkg, orc):
+    """Points on/over the image border, in flat regions (minEig), sub-pixel positions, and a scene change (lost tracks)."""
+    w, h = 640, 200
+    l0, r0 = pkg.synth_stereo_frame(21, 0, w, h)
+    other, _ = pkg.synth_stereo_frame(99, 5, w, h)
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([
+        rng.uniform(-15, 30, (200, 2)), rng.uniform(0, 1, (300, 2)) * [w, h],
+        np.stack([rng.uniform(w - 30, w + 15, 200), rng.uniform(h - 30, h + 15, 200)], 1),
+        np.array([[0, 0], [w - 1, h - 1], [-11.5, -11.5], [w + 9.5, h + 9.5], [10.0, 10.0], [-31.0, 5.0], [5.0, -31.5]]),
+    ]).astype(np.float32)
+    ctx = pkg.Context(0, w, h, 2)
+    flat = np.full((h, w), 100, np.uint8)
+    flat[:, w // 2:] = l0[:, w // 2:]
+    for a, b in ((l0, r0), (l0, other), (flat, flat), (l0, flat)):
+        g = ctx.lk_track(a, b, pts)
+        o = orc.lk_track(a, b, pts)
+        assert np.array_equal(g[1], o[1])
+        ok = o[1] == 1
+        if ok.any():
+            assert np.abs(g[0] - o[0])[ok].max() <= LK_TOL
+    ctx.close()
+
+
+def test_lk_levels_and_iterations(pkg, orc):
+    w, h = 500, 120  # only 3 pyramid levels fit a 21-px window: 500x120, 250x60, 125x30 (63x15 is below win)
+    l0, r0 = pkg.synth_stereo_frame(8, 1, w, h)
+    ctx = pkg.Context(0, w, h, 2)
+    kp = ctx.fast_detect(l0, 20)
+    pts = np.stack([kp["x"], kp["y"]], 1)
+    for max_level, max_iter, eps in ((3, 30, 0.01), (0, 30, 0.01), (1, 5, 0.03), (2, 1, 0.01)):
+        g = ctx.lk_track(l0, r0, pts, max_level=max_level, max_iter=max_iter, eps=eps)
+        o = orc.lk_track(l0, r0, pts, max_level=max_level, max_iter=max_iter, eps=eps)
+        assert np.array_equal(g[1], o[1])
+        ok = o[1] == 1
+        assert np.abs(g[0] - o[0])[ok].max() <= LK_TOL
+    ctx.close()
