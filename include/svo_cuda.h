@@ -50,13 +50,17 @@ int svo_ctx_set_stream(svo_ctx* ctx, void* cuda_stream);
 int svo_ctx_synchronize(svo_ctx* ctx);
 /* Kernels launched by this context since creation (bench.py's gpu_launches claim). */
 int64_t svo_ctx_launch_count(const svo_ctx* ctx);
-/* Device time of pipeline stages of the most recent device run, measured with CUDA events on the context's stream.
+/* Device time of pipeline stages, measured with CUDA events on the context's stream while
+ * svo_ctx_enable_stage_timing(ctx, 1).  Events are kept per timing slot (svo_ctx_set_timing_slot, 0..SVO_TIMING_SLOTS-1)
+ * so that a bench can time K back-to-back steps without synchronising in between and read all of them afterwards.
  * stage: 0 pyramid(K1) 1 fast+cells(K2) 2 compact(K2b) 3 octree(K3) 4 angle+descriptor(K4/K5) 5 match(K6)
- *        6 fullframe-fast(K9) 7 lk-pyramid(K7) 8 lk-track(K8).  Returns milliseconds, <0 if the stage did not run.
- * Only recorded while svo_ctx_enable_stage_timing(ctx, 1). */
+ *        6 fullframe-fast(K9) 7 lk-pyramid(K7) 8..11 lk-track calls 1..4 (K8).
+ * svo_ctx_stage_ms returns milliseconds, <0 if the stage did not run in that slot. */
 int svo_ctx_enable_stage_timing(svo_ctx* ctx, int on);
-float svo_ctx_stage_ms(const svo_ctx* ctx, int stage);
-#define SVO_NUM_STAGES 9
+int svo_ctx_set_timing_slot(svo_ctx* ctx, int slot);
+float svo_ctx_stage_ms(const svo_ctx* ctx, int slot, int stage);
+#define SVO_NUM_STAGES 12
+#define SVO_TIMING_SLOTS 64
 
 /* ---- ORB extractor ------------------------------------------------------------------------------------------- */
 /* Replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
@@ -150,6 +154,8 @@ int svo_frontend_configure(svo_ctx* ctx, int w, int h, int mode, int max_frames)
 int svo_frontend_reset(svo_ctx* ctx);
 /* host images -> device (left/right: n_frames contiguous images of h rows, `stride` bytes per row) */
 int svo_frontend_upload(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride);
+/* same, but left/right are DEVICE pointers (images already resident in HBM, e.g. written by a decoder or a torch tensor) */
+int svo_frontend_upload_dev(svo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, int n_frames, size_t stride);
 /* all kernels for the uploaded frames; inputs and outputs stay in HBM */
 int svo_frontend_run(svo_ctx* ctx);
 /* device -> host for every non-NULL field of out */

@@ -22,15 +22,17 @@ assert KP_DTYPE.itemsize == 28
 
 SVO_OK, SVO_ERR_INVALID, SVO_ERR_CUDA, SVO_ERR_CAPACITY, SVO_ERR_NOT_CONFIGURED = 0, -1, -2, -3, -4
 MODE_ORB, MODE_LK = 1, 2
-STAGES = ["pyramid", "fast_cells", "compact", "octree", "describe", "match", "fast_full", "lk_pyramid", "lk_track"]
+STAGES = ["pyramid", "fast_cells", "compact", "octree", "describe", "match", "fast_full", "lk_pyramid", "lk_track1", "lk_track2",
+          "lk_track3", "lk_track4"]
+TIMING_SLOTS = 64
 
 # every symbol include/svo_cuda.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "svo_ctx_create", "svo_ctx_destroy", "svo_last_error", "svo_abi_version", "svo_ctx_set_stream", "svo_ctx_synchronize",
-    "svo_ctx_launch_count", "svo_ctx_enable_stage_timing", "svo_ctx_stage_ms", "svo_orb_configure", "svo_orb_tables",
+    "svo_ctx_launch_count", "svo_ctx_enable_stage_timing", "svo_ctx_set_timing_slot", "svo_ctx_stage_ms", "svo_orb_configure", "svo_orb_tables",
     "svo_orb_capacity", "svo_orb_level_size", "svo_orb_extract", "svo_orb_extract_batch", "svo_orb_read_level",
     "svo_orb_read_candidates", "svo_fast_detect", "svo_match_hamming", "svo_lk_track", "svo_frontend_configure",
-    "svo_frontend_reset", "svo_frontend_upload", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
+    "svo_frontend_reset", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
     "svo_synth_stereo_frame",
 ]
 
@@ -66,7 +68,7 @@ def lib():
         L.svo_ctx_launch_count.restype = C.c_int64
         L.svo_ctx_launch_count.argtypes = [C.c_void_p]
         L.svo_ctx_stage_ms.restype = C.c_float
-        L.svo_ctx_stage_ms.argtypes = [C.c_void_p, C.c_int]
+        L.svo_ctx_stage_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.svo_orb_configure.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
         L.svo_synth_stereo_frame.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.svo_lk_track.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
@@ -137,8 +139,11 @@ class Context:
     def enable_stage_timing(self, on=True):
         self._check(self._L.svo_ctx_enable_stage_timing(self._h, int(on)))
 
-    def stage_ms(self):
-        return {name: float(self._L.svo_ctx_stage_ms(self._h, i)) for i, name in enumerate(STAGES)}
+    def set_timing_slot(self, slot):
+        self._check(self._L.svo_ctx_set_timing_slot(self._h, slot))
+
+    def stage_ms(self, slot=0):
+        return {name: float(self._L.svo_ctx_stage_ms(self._h, slot, i)) for i, name in enumerate(STAGES)}
 
     # ---- ORB extractor (ORBextractor.h:33-75)
     def orb_configure(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
@@ -249,6 +254,11 @@ class Context:
         self._check(self._L.svo_frontend_upload(self._h, C.c_void_p(left_ptr), C.c_void_p(right_ptr), n_frames, C.c_size_t(stride)))
         self._n_frames = n_frames
 
+    def frontend_upload_dev(self, left_ptr, right_ptr, n_frames, stride):
+        """left_ptr / right_ptr: device addresses of n_frames contiguous images (rows of `stride` bytes)."""
+        self._check(self._L.svo_frontend_upload_dev(self._h, C.c_void_p(left_ptr), C.c_void_p(right_ptr), n_frames, C.c_size_t(stride)))
+        self._n_frames = n_frames
+
     def frontend_run(self):
         self._check(self._L.svo_frontend_run(self._h))
 
@@ -266,7 +276,7 @@ class FrontendBuffers:
     ALL = ("kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
            "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status")
 
-    def __init__(self, n_frames, kp_cap, pt_cap, fields=None):
+    def __init__(self, n_frames, kp_cap, pt_cap, fields=None, alloc=None):
         fields = self.ALL if fields is None else fields
         self.n_frames, self.kp_cap, self.pt_cap = n_frames, kp_cap, pt_cap
         F, K, P = n_frames, max(kp_cap, 1), max(pt_cap, 1)
@@ -284,10 +294,26 @@ class FrontendBuffers:
         for name in self.ALL:
             if name in fields:
                 shape, dt = shapes[name]
-                arr = np.zeros(shape, dt)
+                arr = alloc(shape, dt) if alloc else np.zeros(shape, dt)
+                arr[...] = 0
                 setattr(self, name, arr)
                 setattr(self.struct, name, arr.ctypes.data)
                 self.bytes += arr.nbytes
             else:
                 setattr(self, name, None)
                 setattr(self.struct, name, None)
+
+    def copied_bytes(self):
+        """Bytes svo_frontend_download moved device->host for the last call (per-frame widths are the batch maxima)."""
+        F, total = self.n_frames, 0
+
+        def mx(a):
+            return int(a.max()) if a is not None and len(a) else 0
+        ml, mr, mq, mf, ms = mx(self.n_left), mx(self.n_right), mx(self.n_query), mx(self.n_fast), mx(self.n_seed)
+        for name, width in (("kps_left", ml * 28), ("desc_left", ml * 32), ("kps_right", mr * 28), ("desc_right", mr * 32),
+                            ("stereo_idx", mq * 4), ("stereo_dist", mq * 4), ("temporal_idx", mq * 4), ("temporal_dist", mq * 4),
+                            ("fast_kps", mf * 28), ("lk_p1", ms * 8), ("lk_p2", ms * 8), ("lk_p3", ms * 8), ("lk_p0r", ms * 8),
+                            ("lk_status", ms * 4)):
+            if getattr(self, name) is not None:
+                total += width * F
+        return total + 3 * 4 * 2 * (F + 1)  # the count / flag arrays

@@ -330,7 +330,7 @@ static void fill_params(svo_ctx* c, LkParams& P, int max_level, int max_iter, do
 
 int launch_lk_track(svo_ctx* c, int first, int ring, int n_frames, int skip_first, const LkCall& call, int max_iter, double eps,
                     double min_eig) {
-    StageTimer t(c, 8);
+    StageTimer t(c, 8 + call.status_row);
     LkParams P{};
     fill_params(c, P, SVO_LK_LEVELS - 1, max_iter, eps, min_eig);
     P.first = first;

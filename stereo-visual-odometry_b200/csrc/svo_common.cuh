@@ -89,8 +89,9 @@ struct svo_ctx {
     std::string err;
     int64_t launches = 0;
     bool timing = false;
-    cudaEvent_t ev[SVO_NUM_STAGES][2] = {};
-    bool ev_used[SVO_NUM_STAGES] = {};
+    cudaEvent_t (*ev)[SVO_NUM_STAGES][2] = nullptr;  // [SVO_TIMING_SLOTS], created when timing is first enabled
+    bool ev_used[SVO_TIMING_SLOTS][SVO_NUM_STAGES] = {};
+    int tslot = 0;
 
     // ---- ORB configuration (host copies of the reference's tables)
     bool configured = false;
@@ -179,12 +180,12 @@ struct StageTimer {
     svo_ctx* c;
     int s;
     StageTimer(svo_ctx* ctx, int stage) : c(ctx), s(stage) {
-        if (c->timing) cudaEventRecord(c->ev[s][0], c->stream);
+        if (c->timing) cudaEventRecord(c->ev[c->tslot][s][0], c->stream);
     }
     ~StageTimer() {
         if (c->timing) {
-            cudaEventRecord(c->ev[s][1], c->stream);
-            c->ev_used[s] = true;
+            cudaEventRecord(c->ev[c->tslot][s][1], c->stream);
+            c->ev_used[c->tslot][s] = true;
         }
     }
 };

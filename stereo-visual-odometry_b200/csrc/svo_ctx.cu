@@ -40,10 +40,6 @@ extern "C" int svo_ctx_create(svo_ctx** out, int device, int max_w, int max_h, i
         return SVO_ERR_CUDA;
     }
     c->stream = c->own_stream;
-    for (int s = 0; s < SVO_NUM_STAGES; ++s) {
-        cudaEventCreate(&c->ev[s][0]);
-        cudaEventCreate(&c->ev[s][1]);
-    }
     *out = c;
     return SVO_OK;
 }
@@ -72,9 +68,13 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
     if (c->d_pattern) cudaFree(c->d_pattern);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    for (int s = 0; s < SVO_NUM_STAGES; ++s) {
-        cudaEventDestroy(c->ev[s][0]);
-        cudaEventDestroy(c->ev[s][1]);
+    if (c->ev) {
+        for (int k = 0; k < SVO_TIMING_SLOTS; ++k)
+            for (int s = 0; s < SVO_NUM_STAGES; ++s) {
+                cudaEventDestroy(c->ev[k][s][0]);
+                cudaEventDestroy(c->ev[k][s][1]);
+            }
+        delete[] c->ev;
     }
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -97,16 +97,33 @@ extern "C" int64_t svo_ctx_launch_count(const svo_ctx* c) { return c ? c->launch
 
 extern "C" int svo_ctx_enable_stage_timing(svo_ctx* c, int on) {
     if (!c) return SVO_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (on && !c->ev) {
+        c->ev = new cudaEvent_t[SVO_TIMING_SLOTS][SVO_NUM_STAGES][2];
+        for (int k = 0; k < SVO_TIMING_SLOTS; ++k)
+            for (int s = 0; s < SVO_NUM_STAGES; ++s) {
+                SVO_CUDA_TRY(c, cudaEventCreate(&c->ev[k][s][0]));
+                SVO_CUDA_TRY(c, cudaEventCreate(&c->ev[k][s][1]));
+            }
+    }
     c->timing = on != 0;
-    for (int s = 0; s < SVO_NUM_STAGES; ++s) c->ev_used[s] = false;
+    c->tslot = 0;
+    std::memset(c->ev_used, 0, sizeof(c->ev_used));
     return SVO_OK;
 }
 
-extern "C" float svo_ctx_stage_ms(const svo_ctx* c, int stage) {
-    if (!c || stage < 0 || stage >= SVO_NUM_STAGES || !c->ev_used[stage]) return -1.f;
+extern "C" int svo_ctx_set_timing_slot(svo_ctx* c, int slot) {
+    if (!c || slot < 0 || slot >= SVO_TIMING_SLOTS) return SVO_ERR_INVALID;
+    c->tslot = slot;
+    for (int s = 0; s < SVO_NUM_STAGES; ++s) c->ev_used[slot][s] = false;
+    return SVO_OK;
+}
+
+extern "C" float svo_ctx_stage_ms(const svo_ctx* c, int slot, int stage) {
+    if (!c || !c->ev || slot < 0 || slot >= SVO_TIMING_SLOTS || stage < 0 || stage >= SVO_NUM_STAGES || !c->ev_used[slot][stage]) return -1.f;
     float ms = -1.f;
-    if (cudaEventSynchronize(c->ev[stage][1]) != cudaSuccess) return -1.f;
-    if (cudaEventElapsedTime(&ms, c->ev[stage][0], c->ev[stage][1]) != cudaSuccess) return -1.f;
+    if (cudaEventSynchronize(c->ev[slot][stage][1]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, c->ev[slot][stage][0], c->ev[slot][stage][1]) != cudaSuccess) return -1.f;
     return ms;
 }
 

@@ -182,7 +182,17 @@ extern "C" int svo_frontend_reset(svo_ctx* c) {
     return SVO_OK;
 }
 
+static int frontend_upload_impl(svo_ctx* c, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride, cudaMemcpyKind kind);
+
 extern "C" int svo_frontend_upload(svo_ctx* c, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride) {
+    return frontend_upload_impl(c, left, right, n_frames, stride, cudaMemcpyHostToDevice);
+}
+
+extern "C" int svo_frontend_upload_dev(svo_ctx* c, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride) {
+    return frontend_upload_impl(c, left, right, n_frames, stride, cudaMemcpyDeviceToDevice);
+}
+
+static int frontend_upload_impl(svo_ctx* c, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride, cudaMemcpyKind kind) {
     if (!c) return SVO_ERR_INVALID;
     if (!c->fe_configured) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure() first");
     if (!left || !right || n_frames < 1 || n_frames > c->fe_max_frames || stride < (size_t)c->cur_w)
@@ -194,11 +204,9 @@ extern "C" int svo_frontend_upload(svo_ctx* c, const uint8_t* left, const uint8_
     const uint8_t* srcs[2] = {left, right};
     for (int side = 0; side < 2; ++side) {
         uint8_t* base = L0.base + (size_t)side * ring * L0.plane;
-        SVO_CUDA_TRY(c, cudaMemcpy2DAsync(base + (size_t)first * L0.plane, L0.pitch, srcs[side], stride, w, (size_t)h * run1,
-                                          cudaMemcpyHostToDevice, c->stream));
+        SVO_CUDA_TRY(c, cudaMemcpy2DAsync(base + (size_t)first * L0.plane, L0.pitch, srcs[side], stride, w, (size_t)h * run1, kind, c->stream));
         if (run2 > 0)
-            SVO_CUDA_TRY(c, cudaMemcpy2DAsync(base, L0.pitch, srcs[side] + (size_t)run1 * h * stride, stride, w, (size_t)h * run2,
-                                              cudaMemcpyHostToDevice, c->stream));
+            SVO_CUDA_TRY(c, cudaMemcpy2DAsync(base, L0.pitch, srcs[side] + (size_t)run1 * h * stride, stride, w, (size_t)h * run2, kind, c->stream));
     }
     c->fe_first = first;
     c->fe_pending = n_frames;
