@@ -55,7 +55,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                                           str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
@@ -123,7 +123,8 @@ def run_b200(a):
     ctx = pkg.Context(local, w, h, 2 * (B + 1))
     ctx.orb_configure(a.nfeatures, 1.2, 8, 20, 7)
     ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-null) stream shared by torch events and the library's kernels
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     kp_cap, pt_cap = ctx.orb_capacity(w, h), max(1024, w * h // 64)
     plane = w * h
@@ -260,8 +261,8 @@ def run_reference(a):
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
     p.add_argument("--width", type=int, default=1241)
