@@ -1,0 +1,173 @@
+"""CPU suite: the oracle against the committed golden vectors (made by cv2, oracle/make_golden.py) and, when cv2 is
+importable, against cv2 live on fresh inputs.  No GPU needed."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "cv2_primitives.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _kp3(k):
+    return np.stack([k["x"], k["y"], k["response"]], 1)
+
+
+def test_golden_resize_chain(orc, gold):
+    cur = gold["left0"]
+    for l in range(1, 5):
+        ref = gold[f"resize_l{l}"]
+        got = orc.resize_linear(cur, ref.shape[1], ref.shape[0])
+        assert np.array_equal(got, ref), f"level {l}"
+        cur = ref
+
+
+def test_golden_fast(orc, gold):
+    for thr in (20, 7):
+        assert np.array_equal(_kp3(orc.fast9(gold["left0"], thr)), gold[f"fast_{thr}"])
+    roi = np.ascontiguousarray(gold["left0"][16:16 + 37, 40:40 + 38])
+    assert np.array_equal(_kp3(orc.fast9(roi, 7)), gold["fast_roi_7"])
+
+
+def test_golden_blur_pyrdown_atan2_match(orc, gold):
+    assert np.array_equal(orc.gaussian_blur7(gold["left0"]), gold["blur"])
+    assert np.array_equal(orc.pyr_down(gold["left0"]), gold["pyrdown"])
+    assert np.array_equal(orc.fast_atan2(gold["atan2_y"], gold["atan2_x"]), gold["atan2"])
+    idx, dist = orc.match_hamming(gold["bf_q"], gold["bf_t"])
+    assert np.array_equal(idx, gold["bf_idx"]) and np.array_equal(dist, gold["bf_dist"])
+    assert idx[5] == 11  # duplicate train rows 11 and 40: the lowest index wins
+
+
+def test_golden_lk(orc, gold):
+    pts = gold["fast_20"][:, :2]
+    for name, a, b in (("lk_stereo", "left0", "right0"), ("lk_temporal", "left0", "left1")):
+        p, st, err = orc.lk_track(gold[a], gold[b], pts)
+        assert np.array_equal(st, gold[name + "_status"])
+        ok = st == 1
+        assert np.abs(p - gold[name + "_pts"])[ok].max() <= 1e-3  # OpenCV sums in f32 SIMD lanes, the oracle in exact integers
+        assert np.abs(err - gold[name + "_err"])[ok].max() <= 1e-2
+
+
+def test_tables(orc):
+    scale, inv, fpl, umax = orc.orb_tables(1000, 1.2, 8)
+    assert list(fpl) == [217, 181, 151, 126, 105, 87, 73, 60]
+    assert list(orc.orb_tables(2000, 1.2, 8)[2]) == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert list(orc.orb_tables(4000, 1.2, 8)[2]) == [869, 724, 603, 503, 419, 349, 291, 242]
+    assert list(umax) == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    assert scale[1] == np.float32(1.2) and inv[0] == 1.0
+
+
+def test_brief_pattern_checksum(orc, pkg):
+    pat = orc.brief_pattern()
+    assert hashlib.sha256(pat.astype(np.int8).tobytes()).hexdigest() == "2164181aea6ff9ac426ca512d5130d15e1f6e3cd47b1cbdd568bbe1e55d49023"
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = open(os.path.join(here, "oracle", "brief_pattern.inc")).read()
+    b = open(os.path.join(here, "stereo-visual-odometry_b200", "csrc", "brief_pattern.inc")).read()
+    assert a == b  # oracle and product carry the same table
+
+
+def test_orb_extract_structure(orc, pkg):
+    """ORBextractor restatement: level-major order, quotas, borders, descriptor determinism."""
+    left, _ = pkg.synth_stereo_frame(1000, 0, 1241, 376)
+    o = orc.OrbOracle(1000)
+    k, d = o.extract(left)
+    assert 1000 <= len(k) <= 1000 + 3 * 8 and d.shape == (len(k), 32)
+    assert (np.diff(k["octave"]) >= 0).all()
+    _, _, fpl, _ = orc.orb_tables(1000, 1.2, 8)
+    for l in range(8):
+        lk = o.level_keypoints(l)
+        assert fpl[l] <= len(lk) <= fpl[l] + 3
+        lvl = o.level(l)
+        assert (lk["x"] >= 19).all() and (lk["x"] < lvl.shape[1] - 19).all() and (lk["y"] >= 19).all() and (lk["y"] < lvl.shape[0] - 19).all()
+        c = o.candidates(l)
+        cs = {(x, y) for x, y in zip(c["x"], c["y"])}
+        assert all((x - 16, y - 16) in cs for x, y in zip(lk["x"], lk["y"]))  # every selected keypoint is a candidate
+    k2, d2 = orc.OrbOracle(1000).extract(left)
+    assert np.array_equal(k, k2) and np.array_equal(d, d2)
+    kf, df = o.extract(np.full((376, 1241), 50, np.uint8))
+    assert len(kf) == 0
+
+
+def test_octree_properties(orc):
+    rng = np.random.default_rng(3)
+    for trial in range(30):
+        W, H = int(rng.integers(60, 1300)), int(rng.integers(40, 400))
+        if W < H // 2 + 1:
+            continue
+        n = int(rng.integers(0, 3000))
+        pos = rng.permutation(W * H)[:n]
+        keys = np.zeros(n, orc.KP_DTYPE)
+        keys["x"], keys["y"] = pos % W, pos // W
+        keys["response"] = rng.integers(7, 120, n)
+        N = int(rng.integers(1, 400))
+        out, st = orc.distribute_octree(keys, 16, 16 + W, 16, 16 + H, N)
+        nini = int(np.round(np.float32(W) / np.float32(H)))
+        assert len(out) <= max(N + 3, 4 * max(nini, 1))
+        assert len(out) == len({(a, b) for a, b in zip(out["x"], out["y"])})  # one key per node, nodes are disjoint
+        if n >= N * 6:
+            assert len(out) >= N
+        if n:
+            assert len(out) >= 1
+
+
+def test_match_and_lk_filters(orc):
+    rng = np.random.default_rng(0)
+    n = 50
+    ll = np.zeros(n, orc.KP_DTYPE)
+    lr = np.zeros(n, orc.KP_DTYPE)
+    ll["y"] = rng.integers(0, 100, n)
+    lr["y"] = ll["y"] + rng.integers(-5, 6, n)
+    idx1 = np.arange(n, dtype=np.int32)
+    d1 = rng.integers(0, 80, n).astype(np.int32)
+    d2 = rng.integers(0, 80, n).astype(np.int32)
+    acc = orc.orb_match_filter(idx1, d1, idx1, d2, n, n - 5, ll, lr, 3.0)  # des_index = n - 5 truncates the loop (quirk Q3)
+    mind = np.maximum(d1, d2)[:n - 5].min()
+    lim = max(2 * mind, 30)
+    exp = [i for i in range(n - 5) if d1[i] <= lim and d2[i] <= lim and abs(ll["y"][i] - lr["y"][i]) < 3]
+    assert list(acc[:, 0]) == exp
+    p = rng.uniform(-2, 50, (5, n, 2)).astype(np.float32)
+    s = (rng.uniform(0, 1, (4, n)) > 0.1).astype(np.uint8)
+    keep = orc.lk_chain_filter(*p, *s, 3.0)
+    exp = [(p[:, i] >= 0).all() and s[:, i].all() and abs(p[0, i, 1] - p[1, i, 1]) <= 3 and abs(p[2, i, 1] - p[3, i, 1]) <= 3 for i in range(n)]
+    assert list(keep) == exp
+
+
+def test_live_cv2_cross_check(orc, pkg):
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    left, right = pkg.synth_stereo_frame(77, 3, 500, 300)
+    assert np.array_equal(orc.resize_linear(left, 417, 250), cv2.resize(left, (417, 250), interpolation=cv2.INTER_LINEAR))
+    assert np.array_equal(orc.gaussian_blur7(left), cv2.GaussianBlur(left, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+    kp = cv2.FastFeatureDetector_create(20, True).detect(left)
+    assert np.array_equal(_kp3(orc.fast9(left, 20)), np.array([(k.pt[0], k.pt[1], k.response) for k in kp], np.float32).reshape(-1, 3))
+    pts = np.array([k.pt for k in kp], np.float32)
+    p, st, _ = cv2.calcOpticalFlowPyrLK(left, right, pts.reshape(-1, 1, 2), None, winSize=(21, 21), maxLevel=3,
+                                        criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01), flags=0, minEigThreshold=1e-3)
+    op, ost, _ = orc.lk_track(left, right, pts)
+    assert np.array_equal(ost, st.ravel()) and np.abs(op - p.reshape(-1, 2))[ost == 1].max() <= 1e-3
+    # the per-cell FAST loop of the extractor against cv2.FAST called per cell (ORBextractor.cpp:742-781)
+    o = orc.OrbOracle(500)
+    o.extract(left)
+    lvl = o.level(1)
+    H, W = lvl.shape
+    maxBX, maxBY = W - 16, H - 16
+    nC, nR = int(np.float32(maxBX - 16) / np.float32(30)), int(np.float32(maxBY - 16) / np.float32(30))
+    wC, hC = int(np.ceil(np.float32(maxBX - 16) / nC)), int(np.ceil(np.float32(maxBY - 16) / nR))
+    f20, f7 = cv2.FastFeatureDetector_create(20, True), cv2.FastFeatureDetector_create(7, True)
+    exp = []
+    for i in range(nR):
+        y0, y1 = 16 + i * hC, min(16 + i * hC + hC + 6, maxBY)
+        if y0 >= maxBY - 3:
+            continue
+        for j in range(nC):
+            x0, x1 = 16 + j * wC, min(16 + j * wC + wC + 6, maxBX)
+            if x0 >= maxBX - 6:
+                continue
+            kk = f20.detect(lvl[y0:y1, x0:x1]) or f7.detect(lvl[y0:y1, x0:x1])
+            exp += [(k.pt[0] + j * wC, k.pt[1] + i * hC, k.response) for k in kk]
+    assert np.array_equal(_kp3(o.candidates(1)), np.array(exp, np.float32).reshape(-1, 3))
