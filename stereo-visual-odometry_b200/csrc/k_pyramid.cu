@@ -55,7 +55,32 @@ __global__ void __launch_bounds__(256) k_resize_half(LevelGeom S, LevelGeom D, S
     D.base[(size_t)slot * D.plane + (size_t)dy * D.pitch + dx] = (uint8_t)((src[0] + src[1] + src[S.pitch] + src[S.pitch + 1] + 2) >> 2);
 }
 
+// frontend upload: rows of `stride` bytes (device memory: the H2D staging buffer or the caller's own tensor) -> the pitched
+// level-0 planes of the frame ring.  One CTA per (row, frame, side); each thread writes 4 aligned bytes.
+__global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ left, const uint8_t* __restrict__ right, size_t stride,
+                                                 LevelGeom L0, int first, int ring) {
+    const int y = blockIdx.x, f = blockIdx.y, side = blockIdx.z;
+    const uint8_t* __restrict__ src = (side ? right : left) + ((size_t)f * L0.h + y) * stride;
+    uint8_t* dst = L0.base + (size_t)(side * ring + (first + f) % ring) * L0.plane + (size_t)y * L0.pitch;
+    for (int x = threadIdx.x * 4; x < L0.w; x += 256 * 4) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (x + i < L0.w) v |= (uint32_t)__ldg(src + x + i) << (8 * i);
+        *reinterpret_cast<uint32_t*>(dst + x) = v;
+    }
+}
+
 }  // namespace
+
+int launch_repitch(svo_ctx* c, const uint8_t* left, const uint8_t* right, size_t stride, int first, int ring, int n_frames) {
+    const LevelGeom& L0 = c->geom.lvl[0];
+    dim3 grid(L0.h, n_frames, 2);
+    k_repitch<<<grid, 256, 0, c->stream>>>(left, right, stride, L0, first, ring);
+    ++c->launches;
+    SVO_CUDA_TRY(c, cudaGetLastError());
+    return SVO_OK;
+}
 
 int launch_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
     StageTimer t(c, 0);

@@ -159,6 +159,17 @@ struct svo_ctx {
     int fe_done_first = 0, fe_done_n = 0, fe_done_skip = 0;  // the last completed run (what download reads)
     bool fe_has_last = false;
     bool fe_configured = false;
+    // upload staging: linear H2D copies on a copy stream, double-buffered; rows are re-pitched into the ring by a kernel
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {}, ev_repitch[2] = {};
+    bool ev_repitch_valid[2] = {false, false};
+    uint8_t* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    int stage_idx = 0;
+    const uint8_t* pend_left = nullptr;
+    const uint8_t* pend_right = nullptr;
+    size_t pend_stride = 0;
+    bool pend_staged = false;
     bool aux_ready = false;        // LK pyramid / full-frame FAST buffers laid out for the current size
     bool user_configured = false;  // svo_orb_configure() was called by the user (not the detector-only default)
 
@@ -192,6 +203,7 @@ struct StageTimer {
 
 // ---- kernel launchers (one per stage; defined in k_*.cu).  n_img batch images mapped to slots through `map`.
 int launch_pyramid(svo_ctx* c, const SlotMap& map, int n_img);                       // K1
+int launch_repitch(svo_ctx* c, const uint8_t* left, const uint8_t* right, size_t stride, int first, int ring, int n_frames);
 int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img);                    // K2 + K2b
 int launch_octree(svo_ctx* c, const SlotMap& map, int n_img);                        // K3
 int launch_describe(svo_ctx* c, const SlotMap& map, int n_img);                      // K4 + K5

@@ -68,6 +68,15 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
     if (c->d_pattern) cudaFree(c->d_pattern);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+            cudaEventDestroy(c->ev_copy[i]);
+            cudaEventDestroy(c->ev_repitch[i]);
+        }
+        cudaStreamDestroy(c->copy_stream);
+    }
     if (c->ev) {
         for (int k = 0; k < SVO_TIMING_SLOTS; ++k)
             for (int s = 0; s < SVO_NUM_STAGES; ++s) {
@@ -413,6 +422,15 @@ int svo_layout(svo_ctx* c, int w, int h) {
 int svo_ensure_pinned(svo_ctx* c, size_t bytes) {
     if (c->pinned_bytes >= bytes) return SVO_OK;
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+            cudaEventDestroy(c->ev_copy[i]);
+            cudaEventDestroy(c->ev_repitch[i]);
+        }
+        cudaStreamDestroy(c->copy_stream);
+    }
     c->h_pinned = nullptr;
     c->pinned_bytes = 0;
     SVO_CUDA_TRY(c, cudaMallocHost(&c->h_pinned, bytes));

@@ -163,6 +163,22 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
         c->d_match = nullptr;
         SVO_CUDA_TRY(c, cudaMalloc(&c->d_match, sizeof(int) * 4 * (size_t)c->kp_cap * c->fe_ring));
     }
+    if (!c->copy_stream) {
+        SVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SVO_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+            SVO_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_repitch[i], cudaEventDisableTiming));
+        }
+    }
+    SVO_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; ++i) {
+        if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+        c->d_stage[i] = nullptr;
+        c->ev_repitch_valid[i] = false;
+    }
+    c->stage_bytes = 2 * svo_align((size_t)max_frames * h * (2 * (size_t)w), 256);  // 2 sides, stride up to 2 x width
+    for (int i = 0; i < 2; ++i) SVO_CUDA_TRY(c, cudaMalloc(&c->d_stage[i], c->stage_bytes));
+    c->stage_idx = 0;
     c->fe_mode = mode;
     c->fe_max_frames = max_frames;
     c->fe_head = c->fe_ring - 1;
@@ -193,22 +209,36 @@ extern "C" int svo_frontend_upload_dev(svo_ctx* c, const uint8_t* left, const ui
 }
 
 static int frontend_upload_impl(svo_ctx* c, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride, cudaMemcpyKind kind) {
+    // Host images: ONE linear H2D copy per side into a staging buffer on the context's copy stream (full PCIe rate; a 2-D
+    // copy of 1241-byte rows is several times slower), double-buffered so that the upload of batch k+1 overlaps the kernels
+    // of batch k.  Device images: nothing is copied here.  In both cases svo_frontend_run() moves the rows into the pitched
+    // level-0 planes of the frame ring with a kernel (k_repitch).
     if (!c) return SVO_ERR_INVALID;
     if (!c->fe_configured) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure() first");
     if (!left || !right || n_frames < 1 || n_frames > c->fe_max_frames || stride < (size_t)c->cur_w)
         return c->fail(SVO_ERR_INVALID, "svo_frontend_upload: bad arguments");
     cudaSetDevice(c->device);
-    const LevelGeom& L0 = c->geom.lvl[0];
-    const int ring = c->fe_ring, first = (c->fe_head + 1) % ring, w = c->cur_w, h = c->cur_h;
-    const int run1 = std::min(n_frames, ring - first), run2 = n_frames - run1;
-    const uint8_t* srcs[2] = {left, right};
-    for (int side = 0; side < 2; ++side) {
-        uint8_t* base = L0.base + (size_t)side * ring * L0.plane;
-        SVO_CUDA_TRY(c, cudaMemcpy2DAsync(base + (size_t)first * L0.plane, L0.pitch, srcs[side], stride, w, (size_t)h * run1, kind, c->stream));
-        if (run2 > 0)
-            SVO_CUDA_TRY(c, cudaMemcpy2DAsync(base, L0.pitch, srcs[side] + (size_t)run1 * h * stride, stride, w, (size_t)h * run2, kind, c->stream));
+    const int h = c->cur_h;
+    if (kind == cudaMemcpyHostToDevice) {
+        const int sb = c->stage_idx ^ 1;  // the buffer the previous run did not read
+        const size_t bytes = (size_t)n_frames * h * stride;
+        if (bytes > c->stage_bytes / 2) return c->fail(SVO_ERR_INVALID, "svo_frontend_upload: stride larger than 2 x width is not supported");
+        if (c->ev_repitch_valid[sb]) SVO_CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_repitch[sb], 0));
+        uint8_t* dl = c->d_stage[sb];
+        uint8_t* dr = dl + c->stage_bytes / 2;
+        SVO_CUDA_TRY(c, cudaMemcpyAsync(dl, left, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        SVO_CUDA_TRY(c, cudaMemcpyAsync(dr, right, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        SVO_CUDA_TRY(c, cudaEventRecord(c->ev_copy[sb], c->copy_stream));
+        c->stage_idx = sb;
+        c->pend_left = dl;
+        c->pend_right = dr;
+        c->pend_staged = true;
+    } else {
+        c->pend_left = left;
+        c->pend_right = right;
+        c->pend_staged = false;
     }
-    c->fe_first = first;
+    c->pend_stride = stride;
     c->fe_pending = n_frames;
     return SVO_OK;
 }
@@ -217,9 +247,15 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
     if (!c) return SVO_ERR_INVALID;
     if (!c->fe_configured || c->fe_pending < 1) return c->fail(SVO_ERR_INVALID, "svo_frontend_run: nothing uploaded");
     cudaSetDevice(c->device);
-    const int ring = c->fe_ring, first = c->fe_first, n = c->fe_pending, skip_first = c->fe_has_last ? 0 : 1;
+    const int ring = c->fe_ring, first = (c->fe_head + 1) % ring, n = c->fe_pending, skip_first = c->fe_has_last ? 0 : 1;
     int rc;
     const SlotMap both{2, ring, first, ring}, leftonly{1, 0, first, ring};
+    if (c->pend_staged) SVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copy[c->stage_idx], 0));
+    if ((rc = launch_repitch(c, c->pend_left, c->pend_right, c->pend_stride, first, ring, n)) != SVO_OK) return rc;
+    if (c->pend_staged) {
+        SVO_CUDA_TRY(c, cudaEventRecord(c->ev_repitch[c->stage_idx], c->stream));
+        c->ev_repitch_valid[c->stage_idx] = true;
+    }
     if (c->fe_mode & SVO_MODE_ORB) {
         if ((rc = svo_orb_run(c, both, 2 * n)) != SVO_OK) return rc;
         if ((rc = launch_match_frontend(c, first, ring, n, skip_first)) != SVO_OK) return rc;
