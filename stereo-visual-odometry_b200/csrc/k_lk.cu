@@ -3,12 +3,13 @@
 //
 //  K7  k_pyr_down   cv::pyrDown: 5x5 [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, round half up; levels 1..3 of each image.
 //                   Built once per image (the reference rebuilds both pyramids inside each of its 4 calls).
-//  K8  k_lk_track   one warp per point, all pyramid levels in one launch.  Per level the warp stages the 24x24 patch of
-//                   the previous image in shared memory (REFLECT_101 outside the image), derives the Scharr gradients
-//                   on the fly (constant 0 outside the image, exactly like OpenCV's padded derivative buffer -- no
-//                   derivative image is ever written to HBM), keeps the 21x21 interpolated window (I, Ix, Iy as int16)
-//                   in registers -- lane r owns window row r -- and iterates Gauss-Newton on 22x22 patches of the next
-//                   image.  All window sums are exact integers (int64 across the warp), converted to float once.
+//  K8  k_lk_track   one warp per point, all pyramid levels in one launch, fully register-resident (no shared memory): lane l
+//                   owns one image column of the 24x24 neighbourhood of the previous image (REFLECT_101 outside the
+//                   image), derives the Scharr gradients on the fly with a sliding 3-row window + warp shuffles
+//                   (constant 0 outside the image, exactly like OpenCV's padded derivative buffer -- no derivative image is
+//                   ever written to HBM), keeps its column of the 21x21 interpolated window (I, Ix, Iy as int16) in
+//                   registers and iterates Gauss-Newton on 22x22 neighbourhoods of the next image read straight from
+//                   L1/L2.  All window sums are exact integers (int64 across the warp), converted to float once.
 //
 // f32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) to follow OpenCV's scalar expressions.
 #include <cfloat>
@@ -19,8 +20,6 @@ namespace {
 
 constexpr int WIN = SVO_LK_WIN;  // 21
 constexpr int LW = 8;            // warps (points) per CTA
-constexpr int IP = 36;           // byte pitch of the staged image patches (9 words: conflict-free row-per-lane access)
-constexpr int DP = 23;           // word pitch of the gradient patch
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     // |offset| <= WIN beyond the image and n > WIN on every level, so one reflection suffices
@@ -64,10 +63,11 @@ struct LkParams {
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
-__device__ __forceinline__ long long warp_sum64(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
+// exact warp-wide sum of one int32 per lane as a 64-bit value: two hardware reductions (REDUX.SUM) on the 16-bit halves
+__device__ __forceinline__ long long warp_sum64(int v) {
+    const int lo = __reduce_add_sync(0xFFFFFFFFu, v & 0xFFFF);  // <= 32 * 65535
+    const int hi = __reduce_add_sync(0xFFFFFFFFu, v >> 16);     // signed halves, |sum| <= 32 * 32768
+    return ((long long)hi << 16) + (long long)lo;
 }
 
 __device__ __forceinline__ void weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
@@ -78,20 +78,26 @@ __device__ __forceinline__ void weights(float a, float b, int& w00, int& w01, in
     w11 = 16384 - w00 - w01 - w10;
 }
 
-// stage rows [y0, y0+rows) x cols [x0, x0+cols) of a level image (REFLECT_101 outside) into shared memory
-__device__ __forceinline__ void stage_patch(const uint8_t* __restrict__ img, int w, int h, int pitch, int x0, int y0, int cols, int rows,
-                                            uint8_t* dst, int lane) {
-    if (lane < cols) {
-        const int cx = reflect101(x0 + lane, w);
-        for (int r = 0; r < rows; ++r) dst[r * IP + lane] = __ldg(img + (size_t)reflect101(y0 + r, h) * pitch + cx);
+// rows [y0, y0 + N) of image column x (REFLECT_101 outside the image); `interior` is warp-uniform: no reflection needed
+template <int N>
+__device__ __forceinline__ void load_column(const uint8_t* __restrict__ img, const LkLevelGeom& G, int x, int y0, bool interior, int (&out)[N]) {
+    if (interior) {
+        const uint8_t* __restrict__ p = img + (size_t)y0 * G.pitch + x;
+#pragma unroll
+        for (int r = 0; r < N; ++r) out[r] = __ldg(p + (size_t)r * G.pitch);
+    } else {
+        const uint8_t* __restrict__ col = img + reflect101(x, G.w);
+#pragma unroll
+        for (int r = 0; r < N; ++r) out[r] = __ldg(col + (size_t)reflect101(y0 + r, G.h) * G.pitch);
     }
 }
 
+// One warp per point; lane l owns image column (ip.x - 1 + l) of the 24-column neighbourhood, so window column x lives in
+// lane x + 1.  Everything is register-resident: the lane walks down its column (sliding 3-row window for the Scharr
+// gradient), horizontal neighbours come from warp shuffles, and the interpolated window (I, Ix, Iy of 21 rows) stays in
+// registers for the Gauss-Newton iterations.  No shared memory, no derivative image.
 __global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
                                                       float* __restrict__ lk_pts, uint8_t* __restrict__ lk_status, float* __restrict__ lk_err) {
-    __shared__ __align__(16) uint8_t s_I[LW][24 * IP];
-    __shared__ __align__(16) uint32_t s_D[LW][22 * DP];
-    __shared__ __align__(16) uint8_t s_J[LW][22 * IP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     if (f == 0 && P.skip_first) return;
@@ -116,13 +122,11 @@ __global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keyp
     float* dst = lk_pts + ((size_t)cur * 5 + P.call.dst_list) * P.pt_cap * 2;
     uint8_t* st_out = lk_status + ((size_t)cur * 4 + P.call.status_row) * P.pt_cap;
 
-    uint8_t* sI = s_I[warp];
-    uint32_t* sD = s_D[warp];
-    uint8_t* sJ = s_J[warp];
-    const float half = 10.f;  // (win - 1) * 0.5
+    const float half = 10.f;   // (win - 1) * 0.5
     float nx = 0.f, ny = 0.f;  // nextPts[pt] carried across levels
     int status = 1;
     float err = 0.f;
+    const bool wlane = lane >= 1 && lane <= WIN;  // lanes that own a window column
 
     for (int level = P.levels - 1; level >= 0; --level) {
         const LkLevelGeom& G = P.lv[level];
@@ -150,68 +154,43 @@ __global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keyp
         int iw00, iw01, iw10, iw11;
         weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
 
-        // previous-image patch: rows/cols [ip-1, ip+22]
-        __syncwarp();
-        stage_patch(I, G.w, G.h, G.pitch, ipx - 1, ipy - 1, 24, 24, sI, lane);
-        __syncwarp();
-        // Scharr gradients at the 22x22 positions (ipx+c, ipy+r); 0 outside the image
-        if (lane < 22) {
-            const int X = ipx + lane;
+        // ---- previous image: column X = ipx - 1 + lane, rows ipy - 1 .. ipy + 22 (REFLECT_101 outside the image)
+        short Iw[WIN], Ixw[WIN], Iyw[WIN];
+        int a11 = 0, a12 = 0, a22 = 0;
+        {
+            const int X = ipx - 1 + min(lane, 23);
             const bool xin = X >= 0 && X < G.w;
+            int pix[24];
+            load_column<24>(I, G, X, ipy - 1, ipx - 1 >= 0 && ipx + 22 < G.w && ipy - 1 >= 0 && ipy + 22 < G.h, pix);
+            int tp = 0, tpn = 0, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;  // the row above (top taps of the bilinear stencil)
+#pragma unroll
             for (int r = 0; r < 22; ++r) {
+                // Scharr gradient at (X, Y = ipy + r); zero outside the image like OpenCV's constant-0 padded derivative
+                const int V = 3 * (pix[r] + pix[r + 2]) + 10 * pix[r + 1], Dv = pix[r + 2] - pix[r];
+                const int Vl = __shfl_up_sync(0xFFFFFFFFu, V, 1), Vr = __shfl_down_sync(0xFFFFFFFFu, V, 1);
+                const int Dl = __shfl_up_sync(0xFFFFFFFFu, Dv, 1), Dr = __shfl_down_sync(0xFFFFFFFFu, Dv, 1);
                 const int Y = ipy + r;
-                uint32_t packed = 0;
-                if (xin && Y >= 0 && Y < G.h) {
-                    const uint8_t* p = sI + (r + 1) * IP + lane + 1;
-                    const int a0 = p[-IP - 1], a1 = p[-IP], a2 = p[-IP + 1];
-                    const int b0 = p[-1], b2 = p[1];
-                    const int c0 = p[IP - 1], c1 = p[IP], c2 = p[IP + 1];
-                    const int dxv = 3 * (a2 + c2) + 10 * b2 - 3 * (a0 + c0) - 10 * b0;
-                    const int dyv = 3 * (c0 - a0) + 10 * (c1 - a1) + 3 * (c2 - a2);
-                    packed = ((uint32_t)dxv & 0xFFFFu) | ((uint32_t)dyv << 16);
+                const bool in = xin && Y >= 0 && Y < G.h;
+                const int gx = in ? Vr - Vl : 0;
+                const int gy = in ? 3 * (Dl + Dr) + 10 * Dv : 0;
+                const int p = pix[r + 1];
+                const int pn = __shfl_down_sync(0xFFFFFFFFu, p, 1);
+                const int gxn = __shfl_down_sync(0xFFFFFFFFu, gx, 1), gyn = __shfl_down_sync(0xFFFFFFFFu, gy, 1);
+                if (r >= 1) {
+                    const int ival = descale(tp * iw00 + tpn * iw01 + p * iw10 + pn * iw11, 9);
+                    const int ixv = descale(tgx * iw00 + tgxn * iw01 + gx * iw10 + gxn * iw11, 14);
+                    const int iyv = descale(tgy * iw00 + tgyn * iw01 + gy * iw10 + gyn * iw11, 14);
+                    Iw[r - 1] = (short)ival;
+                    Ixw[r - 1] = (short)ixv;
+                    Iyw[r - 1] = (short)iyv;
+                    a11 += ixv * ixv;
+                    a12 += ixv * iyv;
+                    a22 += iyv * iyv;
                 }
-                sD[r * DP + lane] = packed;
+                tp = p; tpn = pn; tgx = gx; tgxn = gxn; tgy = gy; tgyn = gyn;
             }
         }
-        __syncwarp();
-
-        // interpolated window: lane r owns row r
-        short Iw[WIN];
-        uint32_t dIw[WIN];  // lo: Ix, hi: Iy
-        long long sA11 = 0, sA12 = 0, sA22 = 0;
-        if (lane < WIN) {
-            const uint8_t* r0 = sI + (lane + 1) * IP + 1;
-            const uint8_t* r1 = r0 + IP;
-            const uint32_t* d0 = sD + lane * DP;
-            const uint32_t* d1 = d0 + DP;
-            int a11 = 0, a12 = 0, a22 = 0;
-#pragma unroll
-            for (int x = 0; x < WIN; ++x) {
-                const int ival = descale(r0[x] * iw00 + r0[x + 1] * iw01 + r1[x] * iw10 + r1[x + 1] * iw11, 9);
-                const uint32_t q00 = d0[x], q01 = d0[x + 1], q10 = d1[x], q11 = d1[x + 1];
-                const int ixv = descale((short)(q00 & 0xFFFF) * iw00 + (short)(q01 & 0xFFFF) * iw01 + (short)(q10 & 0xFFFF) * iw10 +
-                                            (short)(q11 & 0xFFFF) * iw11, 14);
-                const int iyv = descale((short)(q00 >> 16) * iw00 + (short)(q01 >> 16) * iw01 + (short)(q10 >> 16) * iw10 +
-                                            (short)(q11 >> 16) * iw11, 14);
-                Iw[x] = (short)ival;
-                dIw[x] = ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16);
-                a11 += ixv * ixv;
-                a12 += ixv * iyv;
-                a22 += iyv * iyv;
-            }
-            sA11 = a11;
-            sA12 = a12;
-            sA22 = a22;
-        } else {
-#pragma unroll
-            for (int x = 0; x < WIN; ++x) {
-                Iw[x] = 0;
-                dIw[x] = 0;
-            }
-        }
-        sA11 = warp_sum64(sA11);
-        sA12 = warp_sum64(sA12);
-        sA22 = warp_sum64(sA22);
+        const long long sA11 = warp_sum64(wlane ? a11 : 0), sA12 = warp_sum64(wlane ? a12 : 0), sA22 = warp_sum64(wlane ? a22 : 0);
         const float FLT_SCALE = 1.f / (1 << 20);
         const float A11 = __fmul_rn((float)sA11, FLT_SCALE), A12 = __fmul_rn((float)sA12, FLT_SCALE), A22 = __fmul_rn((float)sA22, FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -234,25 +213,20 @@ __global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keyp
                 break;
             }
             weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
-            __syncwarp();
-            stage_patch(J, G.w, G.h, G.pitch, inx, iny, 22, 22, sJ, lane);
-            __syncwarp();
-            long long sb1 = 0, sb2 = 0;
-            if (lane < WIN) {
-                const uint8_t* r0 = sJ + lane * IP;
-                const uint8_t* r1 = r0 + IP;
-                int b1 = 0, b2 = 0;
+            int jp[22];
+            load_column<22>(J, G, inx - 1 + min(lane, 23), iny, inx - 1 >= 0 && inx + 22 < G.w && iny >= 0 && iny + 21 < G.h, jp);
+            int b1 = 0, b2 = 0;
+            int top = jp[0], topn = __shfl_down_sync(0xFFFFFFFFu, top, 1);
 #pragma unroll
-                for (int x = 0; x < WIN; ++x) {
-                    const int diff = descale(r0[x] * iw00 + r0[x + 1] * iw01 + r1[x] * iw10 + r1[x + 1] * iw11, 9) - Iw[x];
-                    b1 += diff * (short)(dIw[x] & 0xFFFF);
-                    b2 += diff * (short)(dIw[x] >> 16);
-                }
-                sb1 = b1;
-                sb2 = b2;
+            for (int y = 0; y < WIN; ++y) {
+                const int bot = jp[y + 1], botn = __shfl_down_sync(0xFFFFFFFFu, bot, 1);
+                const int diff = descale(top * iw00 + topn * iw01 + bot * iw10 + botn * iw11, 9) - Iw[y];
+                b1 += diff * Ixw[y];
+                b2 += diff * Iyw[y];
+                top = bot;
+                topn = botn;
             }
-            sb1 = warp_sum64(sb1);
-            sb2 = warp_sum64(sb2);
+            const long long sb1 = warp_sum64(wlane ? b1 : 0), sb2 = warp_sum64(wlane ? b2 : 0);
             const float b1f = __fmul_rn((float)sb1, FLT_SCALE), b2f = __fmul_rn((float)sb2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2f), __fmul_rn(A22, b1f)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1f), __fmul_rn(A11, b2f)), D);
@@ -278,20 +252,18 @@ __global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keyp
                 status = 0;
             } else if (P.want_err) {
                 weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), iw00, iw01, iw10, iw11);
-                __syncwarp();
-                stage_patch(J, G.w, G.h, G.pitch, inx, iny, 22, 22, sJ, lane);
-                __syncwarp();
-                long long se = 0;
-                if (lane < WIN) {
-                    const uint8_t* r0 = sJ + lane * IP;
-                    const uint8_t* r1 = r0 + IP;
-                    int e = 0;
+                const uint8_t* __restrict__ col = J + reflect101(inx - 1 + min(lane, 23), G.w);
+                int e = 0;
+                int top = __ldg(col + (size_t)reflect101(iny, G.h) * G.pitch), topn = __shfl_down_sync(0xFFFFFFFFu, top, 1);
 #pragma unroll
-                    for (int x = 0; x < WIN; ++x) e += abs(descale(r0[x] * iw00 + r0[x + 1] * iw01 + r1[x] * iw10 + r1[x + 1] * iw11, 9) - Iw[x]);
-                    se = e;
+                for (int y = 0; y < WIN; ++y) {
+                    const int bot = __ldg(col + (size_t)reflect101(iny + y + 1, G.h) * G.pitch), botn = __shfl_down_sync(0xFFFFFFFFu, bot, 1);
+                    e += abs(descale(top * iw00 + topn * iw01 + bot * iw10 + botn * iw11, 9) - Iw[y]);
+                    top = bot;
+                    topn = botn;
                 }
-                se = warp_sum64(se);
-                err = __fdiv_rn(__fmul_rn((float)se, 1.f), (float)(32 * WIN * WIN));
+                const long long se = warp_sum64(wlane ? e : 0);
+                err = __fdiv_rn((float)se, (float)(32 * WIN * WIN));
             }
         }
     }
