@@ -6,50 +6,47 @@
 //                     which p is still a corner, cornerScore<16>) and S'(p) = S(p) if S(p) >= minTh else 0,
 //                         M(p)      = S'(p) > 0  and  S'(p) > S'(q) for the 8 neighbours q INSIDE the cell's inner region
 //                         cell out  = { p : M(p), S'(p) >= iniTh }   if non-empty,   else { p : M(p) }.
-//                     One CTA = one tile = one cell row x a run of <= 32 cells.  The tile window is staged in shared
-//                     memory with 16-byte loads; a cheap necessary test (opposite ring pairs) rejects most pixels and
-//                     survivors are compacted into per-warp queues so that the full arc score runs on dense warps.
-//                     The score uses packed s16x2 min/max (VIMNMX3): low half = v - ring, high half = ring - v, so one
-//                     instruction stream scores the dark and the bright arcs at once.
+//                     One CTA = one tile = one cell row x a run of <= 32 cells, staged in shared memory with 16-byte loads.
 //  K2b k_compact      concatenates the per-tile lists of a level in tile order == the reference's cell-row-major order.
 //  K9  k_fast_full    cv::FAST(image, 20, true) on the whole frame (Tracking::Detect_OpenCVFASTFeatures,
-//                     tracking.cpp:94-113): same score stage on full-width row strips, NMS across strip borders, output
-//                     in row-major order.
+//                     tracking.cpp:94-113): the same score stage on full-width row strips, NMS across strip borders,
+//                     output in row-major order.
 //
-// Roofline: every level pixel is read from HBM once (window halos come from L2); the kernels are ALU-bound (about
-// 40 integer instructions per pixel), see DESIGN.md.
+// Score stage (shared by K2 and K9), three steps per CTA:
+//   1. byte-SIMD pre-test, 4 pixels per thread: |centre - ring| for the 4 compass ring pixels with VABSDIFF4 on 32-bit
+//      words of the staged window, thresholded per byte with one shift/and/add.  A pixel can be a corner at threshold t
+//      only if one pixel of each opposite ring pair differs by more than t (necessary, deliberately conservative by the
+//      halving); ~91 % of pixels stop here.
+//   2. survivors are compacted into per-warp queues (ballot + popc) so that the exact score runs on dense warps.
+//   3. exact score with packed s16x2 arithmetic: ring * 0xFFFF0001 gives (-ring, +ring) in the two halves, one VIADD.16x2
+//      adds (+v, -v), and VIMNMX3.S16x2 min/max trees score the dark and the bright arcs in one instruction stream.
+//      Non-zero scores also set a bit in a per-row bitmap, so non-maximum suppression, the per-cell threshold selection
+//      and the ordered emission only ever touch the ~4 % of pixels that are corners (one thread per bitmap word).
+// Ordered output without atomics on the order: per-cell (K2) / per-word (K9) keep masks, a scan, then positional writes.
+//
+// Roofline: every level pixel is read from HBM once (window halos come from L2); the kernels are integer-ALU bound.
 #include "svo_common.cuh"
 
 namespace {
 
 constexpr int FT = 256;  // threads per CTA
 constexpr int FW = FT / 32;
-
-struct FastSmem {
-    int PW, PH;  // pixel window pitch (multiple of 16) / rows
-    int SW, SH;  // score map pitch / rows (1-px zero frame)
-    int MC, CH, CK;  // max cells per tile, max rows per cell, 32-px chunks per cell row
-    __host__ __device__ size_t pix_off() const { return 0; }
-    __host__ __device__ size_t sc_off() const { return (size_t)PW * PH; }
-    __host__ __device__ size_t mask_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
-    __host__ __device__ size_t cell_off() const { return mask_off() + (size_t)MC * CH * CK * 2 * sizeof(uint32_t); }
-    __host__ __device__ size_t queue_off() const { return cell_off() + (size_t)(3 * MC + 4) * sizeof(int); }
-    __host__ __device__ size_t total() const { return queue_off() + (size_t)FW * 64 * sizeof(uint32_t); }
-};
+constexpr int QCAP = 192;  // per-warp queue: up to 31 left over + 128 new entries per pre-test iteration
 
 // FAST-9 corner score of the pixel at p (shared memory, row pitch `pw`): max over the 16 arcs of 9 contiguous ring
 // pixels of min(v - ring) [dark arc] and of min(ring - v) [bright arc], minus 1 (== cv cornerScore<16>).
 __device__ __forceinline__ int fast9_score(const uint8_t* p, int pw) {
     const int v = p[0];
-    const uint32_t base = ((uint32_t)((-v) & 0xFFFF) << 16) | (uint32_t)(v + 1);
+    const uint32_t base = ((uint32_t)v << 16) | (uint32_t)((-v) & 0xFFFF);  // hi: +v, lo: -v
     uint32_t d[16];
     {
         const int r0 = p[3 * pw], r1 = p[3 * pw + 1], r2 = p[2 * pw + 2], r3 = p[pw + 3], r4 = p[3], r5 = p[-pw + 3],
                   r6 = p[-2 * pw + 2], r7 = p[-3 * pw + 1], r8 = p[-3 * pw], r9 = p[-3 * pw - 1], r10 = p[-2 * pw - 2],
                   r11 = p[-pw - 3], r12 = p[-3], r13 = p[pw - 3], r14 = p[2 * pw - 2], r15 = p[3 * pw - 1];
         const int r[16] = {r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15};
+        // r * 0xFFFF0001 = r - (r << 16): hi half = -r, lo half = +r (no borrow); + base -> hi: v - r, lo: r - v
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = __vadd2(((uint32_t)r[k] * 0x10001u) ^ 0x0000FFFFu, base);  // hi: r-v, lo: v-r
+        for (int k = 0; k < 16; ++k) d[k] = __vadd2((uint32_t)r[k] * 0xFFFF0001u, base);
     }
     uint32_t m3[16];
 #pragma unroll
@@ -65,14 +62,6 @@ __device__ __forceinline__ int fast9_score(const uint8_t* p, int pw) {
     return max(lo, hi) - 1;
 }
 
-// Necessary condition for a corner at threshold t: every 9-arc holds one pixel of each opposite ring pair.
-__device__ __forceinline__ bool fast9_pretest(const uint8_t* p, int pw, int t) {
-    const int v = p[0];
-    const bool a = abs(v - (int)p[3 * pw]) > t || abs(v - (int)p[-3 * pw]) > t;
-    const bool b = abs(v - (int)p[3]) > t || abs(v - (int)p[-3]) > t;
-    return a && b;
-}
-
 __device__ __forceinline__ void load_window(const uint8_t* __restrict__ img, int pitch, int xa, int ya, int rows, int nchunk,
                                             uint8_t* pix, int PW) {
     for (int idx = threadIdx.x; idx < rows * nchunk; idx += FT) {
@@ -82,38 +71,85 @@ __device__ __forceinline__ void load_window(const uint8_t* __restrict__ img, int
     }
 }
 
-// Score stage shared by K2 and K9: scores of the pixels [sx0, sx0+sw) x [sy0, sy0+sh) (window coordinates of the pixel
-// array) that reach `thr` are written to sc at (+1,+1); sc must be zero-initialised.
+__device__ __forceinline__ void score_one(const uint8_t* pix, int PW, int sx0, int sy0, uint32_t e, int thr, uint8_t* sc, int SW,
+                                          uint32_t* nz, int NWB) {
+    const int ey = (int)(e >> 16), ex = (int)(e & 0xFFFF);
+    const int s = fast9_score(pix + (size_t)(sy0 + ey) * PW + sx0 + ex, PW);
+    if (s >= thr && s > 0) {
+        sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
+        atomicOr(nz + (ey + 1) * NWB + (ex >> 5), 1u << (ex & 31));
+    }
+}
+
+// Score stage: scores >= thr of the pixels [sx0, sx0+sw) x [sy0, sy0+sh) (window coordinates; sx0 >= 3, PW % 4 == 0) are
+// written to sc at (+1,+1) and flagged in the row bitmap nz at row +1; sc and nz must be zero-initialised.
 __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0, int sy0, int sw, int sh, int thr, uint8_t* sc,
-                                             int SW, uint32_t* wq) {
+                                             int SW, uint32_t* nz, int NWB, uint32_t* wq) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t8 = (thr + 1) >> 1;
+    const uint32_t K = (uint32_t)(0x80 - t8) * 0x01010101u;
+    const int w0 = sx0 >> 2, w1 = (sx0 + sw - 1) >> 2;  // first / last 4-pixel word of the region
+    const uint32_t lt_mask = (1u << lane) - 1;
     int qn = 0;
     for (int yy = warp; yy < sh; yy += FW) {
-        const uint8_t* row = pix + (size_t)(sy0 + yy) * PW + sx0;
-        for (int xb = 0; xb < sw; xb += 32) {
-            const int xx = xb + lane;
-            const bool pass = xx < sw && fast9_pretest(row + xx, PW, thr);
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
-            if (pass) wq[qn + __popc(m & ((1u << lane) - 1))] = ((uint32_t)yy << 16) | (uint32_t)xx;
-            qn += __popc(m);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy) * PW);
+        const uint32_t* rup = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy - 3) * PW);
+        const uint32_t* rdn = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy + 3) * PW);
+        for (int wb = w0; wb <= w1; wb += 32) {
+            const int wi = wb + lane;
+            uint32_t pass = 0;
+            if (wi <= w1) {
+                const uint32_t c0 = row[wi], cm = row[wi - 1], cp = row[wi + 1];
+                const uint32_t dl = __vabsdiffu4(c0, __funnelshift_r(cm, c0, 8));    // pixels x - 3
+                const uint32_t dr = __vabsdiffu4(c0, __funnelshift_r(c0, cp, 24));   // pixels x + 3
+                const uint32_t du = __vabsdiffu4(c0, rup[wi]), dd = __vabsdiffu4(c0, rdn[wi]);
+                const uint32_t ml = ((dl >> 1) & 0x7F7F7F7Fu) + K, mr = ((dr >> 1) & 0x7F7F7F7Fu) + K;
+                const uint32_t mu = ((du >> 1) & 0x7F7F7F7Fu) + K, md = ((dd >> 1) & 0x7F7F7F7Fu) + K;
+                pass = (ml | mr) & (mu | md) & 0x80808080u;
+                const int lo = sx0 - 4 * wi, hi = sx0 + sw - 4 * wi;  // valid bytes: lo <= b < hi
+                if (lo > 0) pass &= 0x80808080u << (8 * lo);
+                if (hi < 4) pass &= 0x80808080u >> (8 * (4 - hi));
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const bool p = (pass >> (8 * b + 7)) & 1u;
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, p);
+                if (p) wq[qn + __popc(m & lt_mask)] = ((uint32_t)yy << 16) | (uint32_t)(4 * wi + b - sx0);
+                qn += __popc(m);
+            }
             __syncwarp();
-            if (qn >= 32) {
+            while (qn >= 32) {
                 qn -= 32;
-                const uint32_t e = wq[qn + lane];
-                const int ey = (int)(e >> 16), ex = (int)(e & 0xFFFF);
-                const int s = fast9_score(pix + (size_t)(sy0 + ey) * PW + sx0 + ex, PW);
-                if (s >= thr) sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
+                score_one(pix, PW, sx0, sy0, wq[qn + lane], thr, sc, SW, nz, NWB);
                 __syncwarp();
             }
         }
     }
-    if (lane < qn) {
-        const uint32_t e = wq[lane];
-        const int ey = (int)(e >> 16), ex = (int)(e & 0xFFFF);
-        const int s = fast9_score(pix + (size_t)(sy0 + ey) * PW + sx0 + ex, PW);
-        if (s >= thr) sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
-    }
+    if (lane < qn) score_one(pix, PW, sx0, sy0, wq[lane], thr, sc, SW, nz, NWB);
 }
+
+// bits [x0, x0 + n) (n <= 64) of a bitmap row
+__device__ __forceinline__ unsigned long long row_bits(const uint32_t* nzrow, int x0, int n) {
+    const int w = x0 >> 5, sh = x0 & 31;
+    unsigned long long lo = (unsigned long long)nzrow[w] | ((unsigned long long)nzrow[w + 1] << 32);
+    unsigned long long m = lo >> sh;
+    if (sh) m |= (unsigned long long)nzrow[w + 2] << (64 - sh);
+    return n >= 64 ? m : (m & ((1ull << n) - 1ull));
+}
+
+struct FastSmem {
+    int PW, PH;  // pixel window pitch (multiple of 16) / rows
+    int SW, SH;  // score map pitch / rows (1-px zero frame)
+    int NWB;     // bitmap words per row (+3 slack words so that row_bits may read past the end)
+    int MC, CH;  // max cells per tile, max rows per cell
+    __host__ __device__ size_t sc_off() const { return (size_t)PW * PH; }
+    __host__ __device__ size_t nz_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
+    __host__ __device__ size_t mask_off() const { return nz_off() + (((size_t)NWB * SH * 4 + 15) & ~(size_t)15); }
+    __host__ __device__ size_t rowbase_off() const { return mask_off() + (size_t)MC * CH * 2 * sizeof(unsigned long long); }
+    __host__ __device__ size_t cell_off() const { return rowbase_off() + (size_t)MC * CH * sizeof(int); }
+    __host__ __device__ size_t queue_off() const { return cell_off() + (size_t)(4 * MC + 4) * sizeof(int); }
+    __host__ __device__ size_t total() const { return queue_off() + (size_t)FW * QCAP * sizeof(uint32_t); }
+};
 
 __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const FastTile* __restrict__ tiles, FastSmem L,
                                                    uint32_t* __restrict__ tile_buf, int* __restrict__ tile_cnt, int* __restrict__ flags,
@@ -122,12 +158,15 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
     const FastTile t = tiles[blockIdx.x];
     const int slot = map.slot(blockIdx.y);
     const LevelGeom& G = g.lvl[t.level];
-    uint8_t* pix = smem + L.pix_off();
+    uint8_t* pix = smem;
     uint8_t* sc = smem + L.sc_off();
-    uint32_t* masks = reinterpret_cast<uint32_t*>(smem + L.mask_off());
+    uint32_t* nz = reinterpret_cast<uint32_t*>(smem + L.nz_off());
+    unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + L.mask_off());  // [cell][row][all, strong]
+    int* rowbase = reinterpret_cast<int*>(smem + L.rowbase_off());
     int* cellflag = reinterpret_cast<int*>(smem + L.cell_off());
-    int* cellcnt = cellflag + L.MC;
-    int* cellbase = cellcnt + L.MC;  // MC + 1 entries
+    int* cntAll = cellflag + L.MC;
+    int* cntStr = cntAll + L.MC;
+    int* cellbase = cntStr + L.MC;  // MC + 1 entries
     uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L.queue_off());
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -135,54 +174,50 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
     const int xa = (t.x0 - 3) & ~15;
     const int nchunk = (t.x1 + 3 - xa + 15) >> 4;
     load_window(G.base + (size_t)slot * G.plane, G.pitch, xa, t.y0 - 3, th + 6, nchunk, pix, L.PW);
-    for (int i = threadIdx.x; i < (L.SW * (th + 2) + 15) / 16; i += FT) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
+    {  // zero the score map, the bitmap and the per-cell counters (contiguous regions up to mask_off, then the cell block)
+        uint4* z = reinterpret_cast<uint4*>(sc);
+        const int nz16 = (int)((L.mask_off() - L.sc_off()) >> 4);
+        for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < 4 * L.MC + 4; i += FT) cellflag[i] = 0;
+    }
     __syncthreads();
 
-    score_region(pix, L.PW, t.x0 - xa, 3, tw, th, g.minTh, sc, L.SW, queues + warp * 64);
+    score_region(pix, L.PW, t.x0 - xa, 3, tw, th, g.minTh, sc, L.SW, nz, L.NWB, queues + warp * QCAP);
     __syncthreads();
 
-    // ---- non-maximum suppression clipped to the cell, per-cell threshold selection
-    const int wCell = G.wCell;
-    for (int cidx = warp; cidx < t.ncells; cidx += FW) {
+    // ---- one thread per (cell, row): non-maximum suppression clipped to the cell, per-cell threshold statistics
+    const int wCell = G.wCell, nitems = t.ncells * th;
+    for (int it = threadIdx.x; it < nitems; it += FT) {
+        const int cidx = it / th, ly = it - cidx * th;
         const int cx0 = cidx * wCell, cw = min(cx0 + wCell, tw) - cx0;
-        uint32_t strongAny = 0;
-        int cntAll = 0, cntStr = 0;
-        for (int ly = 0; ly < th; ++ly) {
-            const uint8_t* s1 = sc + (size_t)(ly + 1) * L.SW + cx0 + 1;
-            for (int ck = 0; ck < L.CK; ++ck) {
-                const int lx = ck * 32 + lane;
-                const int s = lx < cw ? s1[lx] : 0;
-                uint32_t mAll = 0, mStr = 0;
-                if (__ballot_sync(0xFFFFFFFFu, s > 0)) {
-                    bool keep = s > 0;
-                    if (keep) {
-                        const uint8_t* s0 = s1 - L.SW;
-                        const uint8_t* s2 = s1 + L.SW;
-                        keep = s > s0[lx] && s > s2[lx];
-                        if (lx > 0) keep = keep && s > s0[lx - 1] && s > s1[lx - 1] && s > s2[lx - 1];
-                        if (lx < cw - 1) keep = keep && s > s0[lx + 1] && s > s1[lx + 1] && s > s2[lx + 1];
-                    }
-                    mAll = __ballot_sync(0xFFFFFFFFu, keep);
-                    mStr = __ballot_sync(0xFFFFFFFFu, keep && s >= g.iniTh);
-                }
-                if (lane == 0) {
-                    uint32_t* mrow = masks + ((size_t)(cidx * L.CH + ly) * L.CK + ck) * 2;
-                    mrow[0] = mAll;
-                    mrow[1] = mStr;
-                }
-                strongAny |= mStr;
-                cntAll += __popc(mAll);
-                cntStr += __popc(mStr);
+        unsigned long long m = row_bits(nz + (ly + 1) * L.NWB, cx0, cw), all = 0, strong = 0;
+        const uint8_t* s1 = sc + (size_t)(ly + 1) * L.SW + cx0 + 1;
+        while (m) {
+            const int lx = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const int s = s1[lx];
+            const uint8_t* s0 = s1 - L.SW;
+            const uint8_t* s2 = s1 + L.SW;
+            bool keep = s > s0[lx] && s > s2[lx];
+            if (lx > 0) keep = keep && s > s0[lx - 1] && s > s1[lx - 1] && s > s2[lx - 1];
+            if (lx < cw - 1) keep = keep && s > s0[lx + 1] && s > s1[lx + 1] && s > s2[lx + 1];
+            if (keep) {
+                all |= 1ull << lx;
+                if (s >= g.iniTh) strong |= 1ull << lx;
             }
         }
-        if (lane == 0) {
-            cellflag[cidx] = strongAny != 0;
-            cellcnt[cidx] = strongAny ? cntStr : cntAll;
+        masks[2 * it] = all;
+        masks[2 * it + 1] = strong;
+        if (all) atomicAdd(&cntAll[cidx], __popcll(all));
+        if (strong) {
+            atomicAdd(&cntStr[cidx], __popcll(strong));
+            cellflag[cidx] = 1;
         }
     }
     __syncthreads();
-    if (warp == 0) {  // exclusive scan over <= 32 cells
-        int v = lane < t.ncells ? cellcnt[lane] : 0, incl = v;
+    if (warp == 0) {  // exclusive scan over <= 32 cells of the selected counts
+        const int v = lane < t.ncells ? (cellflag[lane] ? cntStr[lane] : cntAll[lane]) : 0;
+        int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -190,26 +225,31 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
         }
         cellbase[lane] = incl - v;
         if (lane == 31) cellbase[32] = incl;
+        // row offsets inside each cell (one lane per cell walks its rows)
+        if (lane < t.ncells) {
+            const int which = cellflag[lane];
+            int run = incl - v;
+            for (int ly = 0; ly < th; ++ly) {
+                rowbase[lane * th + ly] = run;
+                run += __popcll(masks[2 * (lane * th + ly) + which]);
+            }
+        }
     }
     __syncthreads();
     const int total = cellbase[32];
     uint32_t* out = tile_buf + (size_t)slot * tile_buf_per_slot + t.out_off;
-    for (int cidx = warp; cidx < t.ncells; cidx += FW) {
+    for (int it = threadIdx.x; it < nitems; it += FT) {
+        const int cidx = it / th, ly = it - cidx * th;
+        unsigned long long m = masks[2 * it + cellflag[cidx]];
+        if (!m) continue;
         const int cx0 = cidx * wCell;
-        const int which = cellflag[cidx];
-        int pos = cellbase[cidx];
-        for (int ly = 0; ly < th; ++ly)
-            for (int ck = 0; ck < L.CK; ++ck) {
-                const uint32_t m = masks[((size_t)(cidx * L.CH + ly) * L.CK + ck) * 2 + which];
-                if (!m) continue;
-                if ((m >> lane) & 1u) {
-                    const int lx = ck * 32 + lane;
-                    const int o = pos + __popc(m & ((1u << lane) - 1));
-                    const int s = sc[(size_t)(ly + 1) * L.SW + cx0 + lx + 1];
-                    if (o < t.out_cap) out[o] = pack_cand(t.x0 + cx0 + lx - SVO_MINB, t.y0 + ly - SVO_MINB, s);
-                }
-                pos += __popc(m);
-            }
+        int o = rowbase[it];
+        while (m) {
+            const int lx = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            if (o < t.out_cap) out[o] = pack_cand(t.x0 + cx0 + lx - SVO_MINB, t.y0 + ly - SVO_MINB, sc[(size_t)(ly + 1) * L.SW + cx0 + lx + 1]);
+            ++o;
+        }
     }
     if (threadIdx.x == 0) {
         tile_cnt[(size_t)slot * n_tiles + blockIdx.x] = min(total, t.out_cap);
@@ -273,11 +313,12 @@ __global__ void __launch_bounds__(128) k_compact(PyrGeom g, SlotMap map, const F
 // each side are computed), the 3-px image frame scores 0 like in cv::FAST.  Output per strip in row-major order.
 // ---------------------------------------------------------------------------------------------------------------
 struct FullSmem {
-    int PW, PH, SW, SH, NI;  // NI: max (row, 32-px chunk) items per strip
+    int PW, PH, SW, SH, NWB, NI;  // NI: max bitmap words (row x 32-px chunk) of the strip's own rows
     __host__ __device__ size_t sc_off() const { return (size_t)PW * PH; }
-    __host__ __device__ size_t item_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
+    __host__ __device__ size_t nz_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
+    __host__ __device__ size_t item_off() const { return nz_off() + (((size_t)NWB * SH * 4 + 15) & ~(size_t)15); }
     __host__ __device__ size_t queue_off() const { return item_off() + (size_t)(2 * NI + 16) * sizeof(int); }
-    __host__ __device__ size_t total() const { return queue_off() + (size_t)FW * 64 * sizeof(uint32_t); }
+    __host__ __device__ size_t total() const { return queue_off() + (size_t)FW * QCAP * sizeof(uint32_t); }
 };
 
 __device__ int block_scan_excl_ft(int* a, int n, int* wtmp) {  // in-place exclusive scan, all FT threads call
@@ -319,52 +360,60 @@ __global__ void __launch_bounds__(FT) k_fast_full(LevelGeom G, SlotMap map, cons
     const int slot = map.slot(blockIdx.y);
     uint8_t* pix = smem;
     uint8_t* sc = smem + L.sc_off();
+    uint32_t* nz = reinterpret_cast<uint32_t*>(smem + L.nz_off());
     int* cnt = reinterpret_cast<int*>(smem + L.item_off());
     uint32_t* masks = reinterpret_cast<uint32_t*>(cnt + L.NI);
     int* wtmp = reinterpret_cast<int*>(masks + L.NI);
     uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L.queue_off());
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int tw = t.x1 - t.x0, th = t.y1 - t.y0;
     const int ys0 = max(t.y0 - 1, 3), ys1 = min(t.y1 + 1, G.h - 3), nsr = ys1 - ys0;
     const int xa = (t.x0 - 3) & ~15;
     const int nchunk = (t.x1 + 3 - xa + 15) >> 4;
     load_window(G.base + (size_t)slot * G.plane, G.pitch, xa, ys0 - 3, nsr + 6, nchunk, pix, L.PW);
-    for (int i = threadIdx.x; i < (L.SW * (th + 2) + 15) / 16; i += FT) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0, 0, 0, 0);
+    {
+        uint4* z = reinterpret_cast<uint4*>(sc);
+        const int nz16 = (int)((L.item_off() - L.sc_off()) >> 4);
+        for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
-    score_region(pix, L.PW, t.x0 - xa, 3, tw, nsr, thr, sc + (ys0 - t.y0) * L.SW, L.SW, queues + warp * 64);
+    // map row of image row y is y - (t.y0 - 1); the score stage writes row (y - ys0) + 1, hence the shift
+    const int shift = ys0 - t.y0;
+    score_region(pix, L.PW, t.x0 - xa, 3, tw, nsr, thr, sc + shift * L.SW, L.SW, nz + shift * L.NWB, L.NWB, queues + warp * QCAP);
     __syncthreads();
+    // ---- one thread per bitmap word of the strip's own rows: 3x3 non-maximum suppression
     const int nck = (tw + 31) >> 5, ni = th * nck;
-    for (int item = warp; item < ni; item += FW) {
+    for (int item = threadIdx.x; item < ni; item += FT) {
         const int r = item / nck, ck = item - r * nck;
-        const int lx = ck * 32 + lane;
-        const uint8_t* s1 = sc + (size_t)(r + 1) * L.SW + 1;
-        const int s = lx < tw ? s1[lx] : 0;
-        uint32_t m = 0;
-        if (__ballot_sync(0xFFFFFFFFu, s > 0)) {
-            bool keep = s > 0;
-            if (keep) {
-                const uint8_t* s0 = s1 - L.SW;
-                const uint8_t* s2 = s1 + L.SW;
-                keep = s > s0[lx - 1] && s > s0[lx] && s > s0[lx + 1] && s > s1[lx - 1] && s > s1[lx + 1] && s > s2[lx - 1] && s > s2[lx] &&
-                       s > s2[lx + 1];
-            }
-            m = __ballot_sync(0xFFFFFFFFu, keep);
+        uint32_t m = nz[(r + 1) * L.NWB + ck], keep = 0;
+        const uint8_t* s1 = sc + (size_t)(r + 1) * L.SW + ck * 32 + 1;
+        while (m) {
+            const int b = __ffs((int)m) - 1;
+            m &= m - 1;
+            const int s = s1[b];
+            const uint8_t* s0 = s1 - L.SW;
+            const uint8_t* s2 = s1 + L.SW;
+            if (s > s0[b - 1] && s > s0[b] && s > s0[b + 1] && s > s1[b - 1] && s > s1[b + 1] && s > s2[b - 1] && s > s2[b] && s > s2[b + 1])
+                keep |= 1u << b;
         }
-        if (lane == 0) {
-            masks[item] = m;
-            cnt[item] = __popc(m);
-        }
+        masks[item] = keep;
+        cnt[item] = __popc(keep);
     }
     __syncthreads();
     const int total = block_scan_excl_ft(cnt, ni, wtmp);
     uint32_t* out = tile_buf + (size_t)slot * buf_per_slot + t.out_off;
-    for (int item = warp; item < ni; item += FW) {
-        const uint32_t m = masks[item];
-        if (!((m >> lane) & 1u)) continue;
+    for (int item = threadIdx.x; item < ni; item += FT) {
+        uint32_t m = masks[item];
+        if (!m) continue;
         const int r = item / nck, ck = item - r * nck;
-        const int lx = ck * 32 + lane;
-        const int o = cnt[item] + __popc(m & ((1u << lane) - 1));
-        if (o < t.out_cap) out[o] = pack_cand(t.x0 + lx, t.y0 + r, sc[(size_t)(r + 1) * L.SW + lx + 1]);
+        int o = cnt[item];
+        while (m) {
+            const int b = __ffs((int)m) - 1;
+            m &= m - 1;
+            const int lx = ck * 32 + b;
+            if (o < t.out_cap) out[o] = pack_cand(t.x0 + lx, t.y0 + r, sc[(size_t)(r + 1) * L.SW + lx + 1]);
+            ++o;
+        }
     }
     if (threadIdx.x == 0) {
         tile_cnt[(size_t)slot * n_tiles + blockIdx.x] = min(total, t.out_cap);
@@ -433,10 +482,11 @@ int launch_fast_full(svo_ctx* c, const SlotMap& map, int n_img, int threshold) {
     FullSmem L{};
     for (const FastTile& ft : c->ftiles) {
         const int xa = (ft.x0 - 3) & ~15;
-        L.PW = std::max(L.PW, (int)svo_align(ft.x1 + 3 - xa, 16));
+        L.PW = std::max(L.PW, (int)svo_align(ft.x1 + 3 - xa + 4, 16));
         L.PH = std::max(L.PH, ft.y1 - ft.y0 + 8);
         L.SW = std::max(L.SW, (int)svo_align(ft.x1 - ft.x0 + 2, 16));
         L.SH = std::max(L.SH, ft.y1 - ft.y0 + 2);
+        L.NWB = std::max(L.NWB, (ft.x1 - ft.x0 + 31) / 32 + 3);
         L.NI = std::max(L.NI, (ft.y1 - ft.y0) * ((ft.x1 - ft.x0 + 31) / 32));
     }
     const size_t smem = L.total();
@@ -462,13 +512,13 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
             FastSmem L{};
             for (const FastTile& ft : c->tiles) {
                 const int xa = (ft.x0 - 3) & ~15;
-                L.PW = std::max(L.PW, (int)svo_align(ft.x1 + 3 - xa, 16));
+                L.PW = std::max(L.PW, (int)svo_align(ft.x1 + 3 - xa + 4, 16));
                 L.PH = std::max(L.PH, ft.y1 - ft.y0 + 6);
                 L.SW = std::max(L.SW, (int)svo_align(ft.x1 - ft.x0 + 2, 16));
                 L.SH = std::max(L.SH, ft.y1 - ft.y0 + 2);
-                L.MC = std::max(L.MC, (int)ft.ncells);
+                L.NWB = std::max(L.NWB, (ft.x1 - ft.x0 + 31) / 32 + 3);
                 L.CH = std::max(L.CH, ft.y1 - ft.y0);
-                L.CK = std::max(L.CK, (g.lvl[ft.level].wCell + 31) / 32);
+                if (g.lvl[ft.level].wCell > 64) return c->fail(SVO_ERR_INVALID, "FAST cells wider than 64 px are not supported");
             }
             L.MC = 32;  // the cell scan is one warp wide
             const size_t smem = L.total();

@@ -82,9 +82,10 @@ __device__ __forceinline__ void weights(float a, float b, int& w00, int& w01, in
 template <int N>
 __device__ __forceinline__ void load_column(const uint8_t* __restrict__ img, const LkLevelGeom& G, int x, int y0, bool interior, int (&out)[N]) {
     if (interior) {
-        const uint8_t* __restrict__ p = img + (size_t)y0 * G.pitch + x;
+        // 32-bit offsets from the (warp-uniform) image base: one integer add per row instead of 64-bit pointer arithmetic
+        const unsigned o0 = (unsigned)y0 * (unsigned)G.pitch + (unsigned)x, pitch = (unsigned)G.pitch;
 #pragma unroll
-        for (int r = 0; r < N; ++r) out[r] = __ldg(p + (size_t)r * G.pitch);
+        for (int r = 0; r < N; ++r) out[r] = __ldg(img + (o0 + (unsigned)r * pitch));
     } else {
         const uint8_t* __restrict__ col = img + reflect101(x, G.w);
 #pragma unroll
@@ -155,7 +156,8 @@ __global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keyp
         weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
 
         // ---- previous image: column X = ipx - 1 + lane, rows ipy - 1 .. ipy + 22 (REFLECT_101 outside the image)
-        short Iw[WIN], Ixw[WIN], Iyw[WIN];
+        short Iw[WIN];
+        int Ixw[WIN], Iyw[WIN];
         int a11 = 0, a12 = 0, a22 = 0;
         {
             const int X = ipx - 1 + min(lane, 23);
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keyp
                     const int ixv = descale(tgx * iw00 + tgxn * iw01 + gx * iw10 + gxn * iw11, 14);
                     const int iyv = descale(tgy * iw00 + tgyn * iw01 + gy * iw10 + gyn * iw11, 14);
                     Iw[r - 1] = (short)ival;
-                    Ixw[r - 1] = (short)ixv;
-                    Iyw[r - 1] = (short)iyv;
+                    Ixw[r - 1] = ixv;
+                    Iyw[r - 1] = iyv;
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
