@@ -31,7 +31,7 @@ namespace {
 
 constexpr int FT = 256;  // threads per CTA
 constexpr int FW = FT / 32;
-constexpr int QCAP = 192;  // per-warp queue: up to 31 left over + 128 new entries per pre-test iteration
+constexpr int QCAP = 64;   // per-warp queue of 4-pixel words: up to 31 left over + 32 new entries per pre-test iteration
 
 // FAST-9 corner score of the pixel at p (shared memory, row pitch `pw`): max over the 16 arcs of 9 contiguous ring
 // pixels of min(v - ring) [dark arc] and of min(ring - v) [bright arc], minus 1 (== cv cornerScore<16>).
@@ -71,13 +71,20 @@ __device__ __forceinline__ void load_window(const uint8_t* __restrict__ img, int
     }
 }
 
-__device__ __forceinline__ void score_one(const uint8_t* pix, int PW, int sx0, int sy0, uint32_t e, int thr, uint8_t* sc, int SW,
-                                          uint32_t* nz, int NWB) {
-    const int ey = (int)(e >> 16), ex = (int)(e & 0xFFFF);
-    const int s = fast9_score(pix + (size_t)(sy0 + ey) * PW + sx0 + ex, PW);
-    if (s >= thr && s > 0) {
-        sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
-        atomicOr(nz + (ey + 1) * NWB + (ex >> 5), 1u << (ex & 31));
+// exact scores of the flagged pixels of one queued 4-pixel word
+__device__ __forceinline__ void score_word(const uint8_t* pix, int PW, int sx0, int sy0, uint32_t e, int thr, uint8_t* sc, int SW,
+                                           uint32_t* nz, int NWB) {
+    const int ey = (int)(e >> 20), wi = (int)((e >> 4) & 0xFFFF);
+    uint32_t bits = e & 15u;
+    while (bits) {
+        const int b = __ffs((int)bits) - 1;
+        bits &= bits - 1;
+        const int ex = 4 * wi + b - sx0;
+        const int s = fast9_score(pix + (size_t)(sy0 + ey) * PW + 4 * wi + b, PW);
+        if (s >= thr && s > 0) {
+            sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
+            atomicOr(nz + (ey + 1) * NWB + (ex >> 5), 1u << (ex & 31));
+        }
     }
 }
 
@@ -110,22 +117,20 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
                 if (lo > 0) pass &= 0x80808080u << (8 * lo);
                 if (hi < 4) pass &= 0x80808080u >> (8 * (4 - hi));
             }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const bool p = (pass >> (8 * b + 7)) & 1u;
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, p);
-                if (p) wq[qn + __popc(m & lt_mask)] = ((uint32_t)yy << 16) | (uint32_t)(4 * wi + b - sx0);
-                qn += __popc(m);
-            }
+            // queue entry = one 4-pixel word with its pass bits: row << 20 | word << 4 | bits
+            const uint32_t bits = ((pass >> 7) & 1u) | ((pass >> 14) & 2u) | ((pass >> 21) & 4u) | ((pass >> 28) & 8u);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, bits != 0);
+            if (bits) wq[qn + __popc(m & lt_mask)] = ((uint32_t)yy << 20) | ((uint32_t)wi << 4) | bits;
+            qn += __popc(m);
             __syncwarp();
             while (qn >= 32) {
                 qn -= 32;
-                score_one(pix, PW, sx0, sy0, wq[qn + lane], thr, sc, SW, nz, NWB);
+                score_word(pix, PW, sx0, sy0, wq[qn + lane], thr, sc, SW, nz, NWB);
                 __syncwarp();
             }
         }
     }
-    if (lane < qn) score_one(pix, PW, sx0, sy0, wq[lane], thr, sc, SW, nz, NWB);
+    if (lane < qn) score_word(pix, PW, sx0, sy0, wq[lane], thr, sc, SW, nz, NWB);
 }
 
 // bits [x0, x0 + n) (n <= 64) of a bitmap row
@@ -142,12 +147,13 @@ struct FastSmem {
     int SW, SH;  // score map pitch / rows (1-px zero frame)
     int NWB;     // bitmap words per row (+3 slack words so that row_bits may read past the end)
     int MC, CH;  // max cells per tile, max rows per cell
-    __host__ __device__ size_t sc_off() const { return (size_t)PW * PH; }
+    // the per-(cell,row) keep masks alias the pixel window, which is dead once the scores exist
+    __host__ __device__ size_t mask_bytes() const { return (size_t)MC * CH * 2 * sizeof(unsigned long long); }
+    __host__ __device__ size_t pix_bytes() const { return ((size_t)PW * PH > mask_bytes() ? (size_t)PW * PH : mask_bytes() + 15) & ~(size_t)15; }
+    __host__ __device__ size_t sc_off() const { return pix_bytes(); }
     __host__ __device__ size_t nz_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
-    __host__ __device__ size_t mask_off() const { return nz_off() + (((size_t)NWB * SH * 4 + 15) & ~(size_t)15); }
-    __host__ __device__ size_t rowbase_off() const { return mask_off() + (size_t)MC * CH * 2 * sizeof(unsigned long long); }
-    __host__ __device__ size_t cell_off() const { return rowbase_off() + (size_t)MC * CH * sizeof(int); }
-    __host__ __device__ size_t queue_off() const { return cell_off() + (size_t)(4 * MC + 4) * sizeof(int); }
+    __host__ __device__ size_t cell_off() const { return nz_off() + (((size_t)NWB * SH * 4 + 15) & ~(size_t)15); }
+    __host__ __device__ size_t queue_off() const { return cell_off() + (size_t)(3 * MC + 4) * sizeof(int); }
     __host__ __device__ size_t total() const { return queue_off() + (size_t)FW * QCAP * sizeof(uint32_t); }
 };
 
@@ -161,12 +167,10 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
     uint8_t* pix = smem;
     uint8_t* sc = smem + L.sc_off();
     uint32_t* nz = reinterpret_cast<uint32_t*>(smem + L.nz_off());
-    unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + L.mask_off());  // [cell][row][all, strong]
-    int* rowbase = reinterpret_cast<int*>(smem + L.rowbase_off());
+    unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem);  // [cell][row][all, strong]; aliases pix after the score stage
     int* cellflag = reinterpret_cast<int*>(smem + L.cell_off());
     int* cntAll = cellflag + L.MC;
     int* cntStr = cntAll + L.MC;
-    int* cellbase = cntStr + L.MC;  // MC + 1 entries
     uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L.queue_off());
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -176,9 +180,9 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
     load_window(G.base + (size_t)slot * G.plane, G.pitch, xa, t.y0 - 3, th + 6, nchunk, pix, L.PW);
     {  // zero the score map, the bitmap and the per-cell counters (contiguous regions up to mask_off, then the cell block)
         uint4* z = reinterpret_cast<uint4*>(sc);
-        const int nz16 = (int)((L.mask_off() - L.sc_off()) >> 4);
+        const int nz16 = (int)((L.cell_off() - L.sc_off()) >> 4);
         for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < 4 * L.MC + 4; i += FT) cellflag[i] = 0;
+        for (int i = threadIdx.x; i < 3 * L.MC + 4; i += FT) cellflag[i] = 0;
     }
     __syncthreads();
 
@@ -215,7 +219,11 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
         }
     }
     __syncthreads();
-    if (warp == 0) {  // exclusive scan over <= 32 cells of the selected counts
+    // ---- every warp scans the (<= 32) per-cell counts, then owns whole cells: lanes = rows, warp scan of the row counts,
+    //      and each lane writes the survivors of its row at their final position (cell-major, row-major inside the cell)
+    int total;
+    int mybase;
+    {
         const int v = lane < t.ncells ? (cellflag[lane] ? cntStr[lane] : cntAll[lane]) : 0;
         int incl = v;
 #pragma unroll
@@ -223,32 +231,31 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
             const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= o) incl += n;
         }
-        cellbase[lane] = incl - v;
-        if (lane == 31) cellbase[32] = incl;
-        // row offsets inside each cell (one lane per cell walks its rows)
-        if (lane < t.ncells) {
-            const int which = cellflag[lane];
-            int run = incl - v;
-            for (int ly = 0; ly < th; ++ly) {
-                rowbase[lane * th + ly] = run;
-                run += __popcll(masks[2 * (lane * th + ly) + which]);
-            }
-        }
+        total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        mybase = incl - v;  // lane c holds the base of cell c
     }
-    __syncthreads();
-    const int total = cellbase[32];
     uint32_t* out = tile_buf + (size_t)slot * tile_buf_per_slot + t.out_off;
-    for (int it = threadIdx.x; it < nitems; it += FT) {
-        const int cidx = it / th, ly = it - cidx * th;
-        unsigned long long m = masks[2 * it + cellflag[cidx]];
-        if (!m) continue;
-        const int cx0 = cidx * wCell;
-        int o = rowbase[it];
-        while (m) {
-            const int lx = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            if (o < t.out_cap) out[o] = pack_cand(t.x0 + cx0 + lx - SVO_MINB, t.y0 + ly - SVO_MINB, sc[(size_t)(ly + 1) * L.SW + cx0 + lx + 1]);
-            ++o;
+    for (int cidx = warp; cidx < t.ncells; cidx += FW) {
+        const int which = cellflag[cidx], cx0 = cidx * wCell;
+        int run = __shfl_sync(0xFFFFFFFFu, mybase, cidx);
+        for (int r0 = 0; r0 < th; r0 += 32) {
+            const int ly = r0 + lane;
+            unsigned long long m = ly < th ? masks[2 * (cidx * th + ly) + which] : 0ull;
+            const int c = __popcll(m);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            int o = run + incl - c;
+            run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            while (m) {
+                const int lx = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                if (o < t.out_cap) out[o] = pack_cand(t.x0 + cx0 + lx - SVO_MINB, t.y0 + ly - SVO_MINB, sc[(size_t)(ly + 1) * L.SW + cx0 + lx + 1]);
+                ++o;
+            }
         }
     }
     if (threadIdx.x == 0) {
