@@ -17,10 +17,10 @@ namespace {
 constexpr int DW = 4;            // warps (keypoints) per CTA
 constexpr int PR = 21;           // source patch radius: 18 (max rotated tap) + 3 (blur)
 constexpr int PS = 2 * PR + 1;   // 43
-constexpr int PP = 44;           // patch pitch
+constexpr int PP = 48;           // patch pitch in bytes (12 words; the horizontal pass reads words 0..11)
 constexpr int BR = 18;           // blurred patch radius
-constexpr int BS = 2 * BR + 1;   // 37
-constexpr int BP = 40;           // blurred patch pitch
+constexpr int HC = 40;           // columns of the horizontal pass (37 needed, 10 words x 4)
+constexpr int HP = 46;           // pitch (u16 units, even) of the TRANSPOSED horizontal-pass array hT[col][row]
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -53,13 +53,16 @@ struct UmaxTable {
     int v[16];
 };
 
+// Blur: out = (sum_i sum_j k_i k_j I(y+i-3, x+j-3) + 32768) >> 16 with k = [18,34,48,56,48,34,18] (exact integers).
+//   horizontal pass for the whole 43 x 40 neighbourhood with IDP.4A on 32-bit words of the patch (4 outputs per step),
+//   stored TRANSPOSED as u16 so that the 7 vertical taps of a sample are contiguous;
+//   vertical pass ON DEMAND at the 512 rotated sample positions with IDP.2A (u16 x u8), 4 per sample.
 __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, UmaxTable umax, const int8_t* __restrict__ pattern,
                                                       const uint32_t* __restrict__ lkp_all, const int* __restrict__ nlkp,
                                                       svo_keypoint* __restrict__ kps_all, uint8_t* __restrict__ desc_all,
                                                       int* __restrict__ nkp, uint32_t lkp_per_slot, int kp_cap) {
-    __shared__ uint8_t s_patch[DW][PS * PP];
-    __shared__ uint16_t s_h[DW][PS * BP];   // horizontal pass: 43 rows x 37 cols
-    __shared__ uint8_t s_blur[DW][BS * BP];
+    __shared__ __align__(16) uint8_t s_patch[DW][PS * PP];
+    __shared__ __align__(16) uint16_t s_hT[DW][HC * HP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = map.slot(blockIdx.y);
     const int kidx = blockIdx.x * DW + warp;
@@ -85,14 +88,35 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
     const int kx = cand_x(c) + SVO_MINB, ky = cand_y(c) + SVO_MINB;  // level pixel coordinates (:797-798)
     const uint8_t* __restrict__ img = G.base + (size_t)slot * G.plane;
 
+    // ---- 43 x 43 patch -> shared memory (REFLECT_101 at the level's own edges; interior keypoints skip the reflection)
     uint8_t* patch = s_patch[warp];
-    for (int i = lane; i < PS * PS; i += 32) {
-        const int py = i / PS, px = i - py * PS;
-        patch[py * PP + px] = __ldg(img + (size_t)reflect101(ky - PR + py, G.h) * G.pitch + reflect101(kx - PR + px, G.w));
+    {
+        const int x0 = kx - PR, y0 = ky - PR;
+        const bool interior = x0 >= 0 && y0 >= 0 && x0 + PS <= G.w && y0 + PS <= G.h;  // warp-uniform
+        const int c1 = lane + 32;                                                        // second column of this lane (< 43 for lanes < 11)
+        if (interior) {
+            const uint8_t* p = img + (size_t)y0 * G.pitch + x0;
+#pragma unroll 4
+            for (int r = 0; r < PS; ++r) {
+                patch[r * PP + lane] = __ldg(p + lane);
+                if (c1 < PS) patch[r * PP + c1] = __ldg(p + c1);
+                p += G.pitch;
+            }
+        } else {
+            const int xa = reflect101(x0 + lane, G.w), xb = reflect101(x0 + min(c1, PS - 1), G.w);
+            for (int r = 0; r < PS; ++r) {
+                const uint8_t* p = img + (size_t)reflect101(y0 + r, G.h) * G.pitch;
+                patch[r * PP + lane] = __ldg(p + xa);
+                if (c1 < PS) patch[r * PP + c1] = __ldg(p + xb);
+            }
+        }
+        if (lane < PP - PS) {  // zero the 5 padding columns the word-wise horizontal pass touches
+            for (int r = 0; r < PS; ++r) patch[r * PP + PS + lane] = 0;
+        }
     }
     __syncwarp();
 
-    // ---- K4: intensity centroid.  lane u-15 handles column u (31 columns), rows limited by umax.
+    // ---- K4: intensity centroid.  lane u+15 handles column u (31 columns), rows limited by umax.
     int m10 = 0, m01 = 0;
     if (lane < 31) {
         const int u = lane - 15;
@@ -110,45 +134,56 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
         }
         m01 = vs;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, o);
-        m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, o);
-    }
+    m10 = __reduce_add_sync(0xFFFFFFFFu, m10);
+    m01 = __reduce_add_sync(0xFFFFFFFFu, m01);
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // ---- K5: separable exact-integer blur of the 37x37 neighbourhood
-    uint16_t* hb = s_h[warp];
-    for (int i = lane; i < PS * BS; i += 32) {
-        const int r = i / BS, x = i - r * BS;
-        const uint8_t* p = patch + r * PP + x;  // taps x .. x+6 of the 43-wide row
-        hb[r * BP + x] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncwarp();
-    uint8_t* bl = s_blur[warp];
-    for (int i = lane; i < BS * BS; i += 32) {
-        const int y = i / BS, x = i - y * BS;
-        const uint16_t* p = hb + y * BP + x;
-        const uint32_t acc = 18u * (p[0] + p[6 * BP]) + 34u * (p[BP] + p[5 * BP]) + 48u * (p[2 * BP] + p[4 * BP]) + 56u * p[3 * BP];
-        bl[y * BP + x] = (uint8_t)((acc + 32768u) >> 16);
+    // ---- K5a: horizontal 7-tap pass, 4 outputs per item: item = (row r, word j), outputs columns 4j .. 4j+3
+    uint16_t* hT = s_hT[warp];
+    {
+        const uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
+        for (int it = lane; it < PS * (HC / 4); it += 32) {
+            const int r = it / (HC / 4), j = it - r * (HC / 4);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(patch + r * PP) + j;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            uint16_t* o = hT + (4 * j) * HP + r;
+            o[0] = (uint16_t)(__dp4a(w0, K0, 0u) + __dp4a(w1, K1, 0u));
+            o[HP] = (uint16_t)(__dp4a(__funnelshift_r(w0, w1, 8), K0, 0u) + __dp4a(__funnelshift_r(w1, w2, 8), K1, 0u));
+            o[2 * HP] = (uint16_t)(__dp4a(__funnelshift_r(w0, w1, 16), K0, 0u) + __dp4a(__funnelshift_r(w1, w2, 16), K1, 0u));
+            o[3 * HP] = (uint16_t)(__dp4a(__funnelshift_r(w0, w1, 24), K0, 0u) + __dp4a(__funnelshift_r(w1, w2, 24), K1, 0u));
+        }
     }
     __syncwarp();
 
-    // ---- steered BRIEF: lane i computes descriptor byte i (pairs 8i .. 8i+7)
+    // ---- steered BRIEF: lane i computes descriptor byte i (pairs 8i .. 8i+7), blurring its 16 samples on demand
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float ang = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);
+    const float a = (float)cd, b = (float)sd;
     const int8_t* pat = pattern + lane * 32;
-    const uint8_t* ctr = bl + BR * BP + BR;
+    // vertical taps as packed u8 weights for even / odd first rows
+    const uint32_t E0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), E1 = 48u | (34u << 8) | (18u << 16);
+    const uint32_t O0 = (18u << 8) | (34u << 16) | (48u << 24), O1 = 56u | (48u << 8) | (34u << 16) | (18u << 24);
+    auto sample = [&](float px, float py) -> int {
+        const int row = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+        const int col = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+        // blurred(row, col) = sum_i k_i h(row + 18 + i, col + 18) over source rows row+18 .. row+24 of column col+18
+        const int r0 = row + BR, e = r0 & ~1;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(hT + (col + BR) * HP + e);
+        const bool odd = r0 & 1;
+        const uint32_t B0 = odd ? O0 : E0, B1 = odd ? O1 : E1;
+        uint32_t acc = __dp2a_lo(w[0], B0, 32768u);
+        acc = __dp2a_hi(w[1], B0, acc);
+        acc = __dp2a_lo(w[2], B1, acc);
+        acc = __dp2a_hi(w[3], B1, acc);
+        return (int)(acc >> 16);
+    };
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = ctr[r0 * BP + c0], t1 = ctr[r1 * BP + c1];
+        const int t0 = sample((float)pat[4 * k], (float)pat[4 * k + 1]);
+        const int t1 = sample((float)pat[4 * k + 2], (float)pat[4 * k + 3]);
         val |= (t0 < t1) << k;
     }
     desc_all[((size_t)slot * kp_cap + kidx) * 32 + lane] = (uint8_t)val;

@@ -12,37 +12,74 @@
 
 namespace {
 
-// Each thread produces 4 horizontally adjacent pixels of one row; a CTA covers 256 x 4 destination pixels.
+// Each thread produces a 4 x 4 block of destination pixels; a CTA covers 256 x 16.  Per source row the horizontal pass of a
+// pixel is ONE IDP.2A: the two source bytes S[sx], S[sx+1] are cut out of an aligned word pair with a funnel shift and
+// multiplied with the packed (a0, a1) u16 coefficients.  Consecutive destination rows usually share a source row
+// (sy(dy+1) == sy(dy)+1 for scale 1.2 in 5 of 6 rows); its horizontal results are reused from registers.
+constexpr int RY = 4;
+
+__device__ __forceinline__ void hpass4(const uint8_t* __restrict__ row, const unsigned (&woff)[4], const unsigned (&sh)[4], const uint32_t (&al)[4],
+                                       int (&T)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t wa = __ldg(reinterpret_cast<const uint32_t*>(row + woff[i]));
+        const uint32_t wb = __ldg(reinterpret_cast<const uint32_t*>(row + woff[i] + 4));
+        T[i] = (int)__dp2a_lo(al[i], __funnelshift_r(wa, wb, sh[i]), 0u);  // S[sx]*a0 + S[sx+1]*a1
+    }
+}
+
 __global__ void __launch_bounds__(256) k_resize_level(LevelGeom S, LevelGeom D, SlotMap map) {
     const int slot = map.slot(blockIdx.z);
     const int dx0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
-    const int dy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (dx0 >= D.w || dy >= D.h) return;
+    const int dy0 = (blockIdx.y * 4 + (threadIdx.x >> 6)) * RY;
+    if (dx0 >= D.w || dy0 >= D.h) return;
     const uint8_t* __restrict__ src = S.base + (size_t)slot * S.plane;
-    uint8_t* __restrict__ dst = D.base + (size_t)slot * D.plane;
+    uint8_t* __restrict__ dst = D.base + (size_t)slot * D.plane + (size_t)dy0 * D.pitch + dx0;
 
     const int4 xo = *reinterpret_cast<const int4*>(D.xofs + dx0);
-    const int4 al = *reinterpret_cast<const int4*>(D.alpha + 2 * dx0);  // 8 shorts
-    const int2 yo = *reinterpret_cast<const int2*>(D.yofs + 2 * dy);
-    const int bt = *reinterpret_cast<const int*>(D.beta + 2 * dy);
-    const int b0 = (short)(bt & 0xFFFF), b1 = (short)(bt >> 16);
-    const uint8_t* r0 = src + (size_t)yo.x * S.pitch;
-    const uint8_t* r1 = src + (size_t)yo.y * S.pitch;
+    const int4 alv = *reinterpret_cast<const int4*>(D.alpha + 2 * dx0);  // 4 x (a0 | a1 << 16)
+    const uint32_t al[4] = {(uint32_t)alv.x, (uint32_t)alv.y, (uint32_t)alv.z, (uint32_t)alv.w};
     const int sx[4] = {xo.x, xo.y, xo.z, xo.w};
-    const int aw[4] = {al.x, al.y, al.z, al.w};
-    uint32_t out = 0;
+    unsigned woff[4], sh[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int a0 = (short)(aw[i] & 0xFFFF), a1 = (short)(aw[i] >> 16);
-        // a1 == 0 whenever sx is the last column, so the +1 read never contributes past the row
-        const int t0 = __ldg(r0 + sx[i]) * a0 + __ldg(r0 + sx[i] + 1) * a1;
-        const int t1 = __ldg(r1 + sx[i]) * a0 + __ldg(r1 + sx[i] + 1) * a1;
-        int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
-        v = min(255, max(0, v));
-        out |= (uint32_t)v << (8 * i);
+        woff[i] = (unsigned)sx[i] & ~3u;  // a1 == 0 whenever sx is the last column, so the byte after the row never contributes
+        sh[i] = ((unsigned)sx[i] & 3u) * 8u;
     }
-    // pitch is a multiple of 64, so the 4-byte store stays inside the row even when dx0+3 >= w
-    *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch + dx0) = out;
+    int cached_row = -1;
+    int Tc[4] = {0, 0, 0, 0};  // horizontal pass of source row `cached_row`
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+        const int dy = dy0 + r;
+        if (dy >= D.h) break;
+        const int2 yo = *reinterpret_cast<const int2*>(D.yofs + 2 * dy);
+        const int bt = *reinterpret_cast<const int*>(D.beta + 2 * dy);
+        const int b0 = (short)(bt & 0xFFFF), b1 = (short)(bt >> 16);
+        int T0[4], T1[4];
+        if (yo.x == cached_row) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) T0[i] = Tc[i];
+        } else {
+            hpass4(src + (size_t)yo.x * S.pitch, woff, sh, al, T0);
+        }
+        if (yo.y == yo.x) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) T1[i] = T0[i];
+        } else {
+            hpass4(src + (size_t)yo.y * S.pitch, woff, sh, al, T1);
+        }
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int v = (((b0 * (T0[i] >> 4)) >> 16) + ((b1 * (T1[i] >> 4)) >> 16) + 2) >> 2;
+            v = min(255, max(0, v));
+            out |= (uint32_t)v << (8 * i);
+            Tc[i] = T1[i];
+        }
+        cached_row = yo.y;
+        // pitch is a multiple of 64, so the 4-byte store stays inside the row even when dx0+3 >= w
+        *reinterpret_cast<uint32_t*>(dst + (size_t)r * D.pitch) = out;
+    }
 }
 
 // exact 2x decimation: cv::resize silently uses INTER_AREA (2x2 mean, round half up)
@@ -92,7 +129,7 @@ int launch_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
             dim3 grid((D.w + 63) / 64, (D.h + 3) / 4, n_img);
             k_resize_half<<<grid, 256, 0, c->stream>>>(S, D, map);
         } else {
-            dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, n_img);
+            dim3 grid((D.w + 255) / 256, (D.h + 4 * RY - 1) / (4 * RY), n_img);
             k_resize_level<<<grid, 256, 0, c->stream>>>(S, D, map);
         }
         ++c->launches;
