@@ -31,7 +31,7 @@ namespace {
 
 constexpr int FT = 256;  // threads per CTA
 constexpr int FW = FT / 32;
-constexpr int QCAP = 64;   // per-warp queue of 4-pixel words: up to 31 left over + 32 new entries per pre-test iteration
+constexpr int QCAP = 160;  // per-warp queue of pre-test survivors: up to 31 left over + 128 new per pre-test iteration
 
 // FAST-9 corner score of the pixel at p (shared memory, row pitch `pw`): max over the 16 arcs of 9 contiguous ring
 // pixels of min(v - ring) [dark arc] and of min(ring - v) [bright arc], minus 1 (== cv cornerScore<16>).
@@ -71,32 +71,29 @@ __device__ __forceinline__ void load_window(const uint8_t* __restrict__ img, int
     }
 }
 
-// exact scores of the flagged pixels of one queued 4-pixel word
-__device__ __forceinline__ void score_word(const uint8_t* pix, int PW, int sx0, int sy0, uint32_t e, int thr, uint8_t* sc, int SW,
-                                           uint32_t* nz, int NWB) {
-    const int ey = (int)(e >> 20), wi = (int)((e >> 4) & 0xFFFF);
-    uint32_t bits = e & 15u;
-    while (bits) {
-        const int b = __ffs((int)bits) - 1;
-        bits &= bits - 1;
-        const int ex = 4 * wi + b - sx0;
-        const int s = fast9_score(pix + (size_t)(sy0 + ey) * PW + 4 * wi + b, PW);
-        if (s >= thr && s > 0) {
-            sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
-            atomicOr(nz + (ey + 1) * NWB + (ex >> 5), 1u << (ex & 31));
-        }
+__device__ __forceinline__ void score_pixel(const uint8_t* pix, int PW, int sx0, int sy0, uint32_t e, int thr, uint8_t* sc, int SW,
+                                            uint32_t* nz, int NWB) {
+    const int ey = (int)(e >> 16), ex = (int)(e & 0xFFFF);
+    const int s = fast9_score(pix + (size_t)(sy0 + ey) * PW + sx0 + ex, PW);
+    if (s >= thr && s > 0) {
+        sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
+        atomicOr(nz + (ey + 1) * NWB + (ex >> 5), 1u << (ex & 31));
     }
 }
 
 // Score stage: scores >= thr of the pixels [sx0, sx0+sw) x [sy0, sy0+sh) (window coordinates; sx0 >= 3, PW % 4 == 0) are
-// written to sc at (+1,+1) and flagged in the row bitmap nz at row +1; sc and nz must be zero-initialised.
+// written to sc at (+1,+1) and flagged in the row bitmap nz at row +1; sc and nz must be zero-initialised.  Each warp owns
+// rows warp, warp+8, ...; pre-test survivors are appended to the warp's queue (slot = prefix over lanes from 3 ballots of
+// the per-lane survivor count) and scored 32 at a time, so the exact score always runs on (almost) full warps.
 __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0, int sy0, int sw, int sh, int thr, uint8_t* sc,
                                              int SW, uint32_t* nz, int NWB, uint32_t* wq) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t8 = (thr + 1) >> 1;
     const uint32_t K = (uint32_t)(0x80 - t8) * 0x01010101u;
     const int w0 = sx0 >> 2, w1 = (sx0 + sw - 1) >> 2;  // first / last 4-pixel word of the region
-    const uint32_t lt_mask = (1u << lane) - 1;
+    const uint32_t m_first = 0x80808080u << (8 * (sx0 & 3));                  // bytes >= sx0 of word w0
+    const uint32_t m_last = 0x80808080u >> (8 * (3 - ((sx0 + sw - 1) & 3)));  // bytes <= last column of word w1
+    const uint32_t lt = (1u << lane) - 1;
     int qn = 0;
     for (int yy = warp; yy < sh; yy += FW) {
         const uint32_t* row = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy) * PW);
@@ -107,30 +104,36 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
             uint32_t pass = 0;
             if (wi <= w1) {
                 const uint32_t c0 = row[wi], cm = row[wi - 1], cp = row[wi + 1];
-                const uint32_t dl = __vabsdiffu4(c0, __funnelshift_r(cm, c0, 8));    // pixels x - 3
-                const uint32_t dr = __vabsdiffu4(c0, __funnelshift_r(c0, cp, 24));   // pixels x + 3
+                const uint32_t dl = __vabsdiffu4(c0, __funnelshift_r(cm, c0, 8));   // pixels x - 3
+                const uint32_t dr = __vabsdiffu4(c0, __funnelshift_r(c0, cp, 24));  // pixels x + 3
                 const uint32_t du = __vabsdiffu4(c0, rup[wi]), dd = __vabsdiffu4(c0, rdn[wi]);
                 const uint32_t ml = ((dl >> 1) & 0x7F7F7F7Fu) + K, mr = ((dr >> 1) & 0x7F7F7F7Fu) + K;
                 const uint32_t mu = ((du >> 1) & 0x7F7F7F7Fu) + K, md = ((dd >> 1) & 0x7F7F7F7Fu) + K;
                 pass = (ml | mr) & (mu | md) & 0x80808080u;
-                const int lo = sx0 - 4 * wi, hi = sx0 + sw - 4 * wi;  // valid bytes: lo <= b < hi
-                if (lo > 0) pass &= 0x80808080u << (8 * lo);
-                if (hi < 4) pass &= 0x80808080u >> (8 * (4 - hi));
+                if (wi == w0) pass &= m_first;
+                if (wi == w1) pass &= m_last;
             }
-            // queue entry = one 4-pixel word with its pass bits: row << 20 | word << 4 | bits
-            const uint32_t bits = ((pass >> 7) & 1u) | ((pass >> 14) & 2u) | ((pass >> 21) & 4u) | ((pass >> 28) & 8u);
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, bits != 0);
-            if (bits) wq[qn + __popc(m & lt_mask)] = ((uint32_t)yy << 20) | ((uint32_t)wi << 4) | bits;
-            qn += __popc(m);
-            __syncwarp();
-            while (qn >= 32) {
-                qn -= 32;
-                score_word(pix, PW, sx0, sy0, wq[qn + lane], thr, sc, SW, nz, NWB);
+            const int n = __popc(pass);  // 0..4 survivors in this lane
+            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, n & 1), b1 = __ballot_sync(0xFFFFFFFFu, n & 2), b2 = __ballot_sync(0xFFFFFFFFu, n & 4);
+            if (b0 | b1 | b2) {
+                if (pass) {
+                    int pos = qn + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+                    const uint32_t e0 = ((uint32_t)yy << 16) + (uint32_t)(4 * wi - sx0);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (pass & (0x80u << (8 * b))) wq[pos++] = e0 + b;
+                }
+                qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
                 __syncwarp();
+                while (qn >= 32) {
+                    qn -= 32;
+                    score_pixel(pix, PW, sx0, sy0, wq[qn + lane], thr, sc, SW, nz, NWB);
+                    __syncwarp();
+                }
             }
         }
     }
-    if (lane < qn) score_word(pix, PW, sx0, sy0, wq[lane], thr, sc, SW, nz, NWB);
+    if (lane < qn) score_pixel(pix, PW, sx0, sy0, wq[lane], thr, sc, SW, nz, NWB);
 }
 
 // bits [x0, x0 + n) (n <= 64) of a bitmap row
