@@ -145,7 +145,9 @@ def run_b200(a):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    t_wait = time.time()
+    while not sampler.rows and time.time() - t_wait < 3.0:  # nvidia-smi takes a moment to produce its first sample
+        time.sleep(0.05)
     ctx.enable_stage_timing(True)
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -85,3 +85,31 @@ def test_frontend_reset_and_partial_outputs(pkg):
     ctx.frontend_batch(np.ascontiguousarray(left[:2]), np.ascontiguousarray(right[:2]), b)
     assert np.array_equal(a.n_left, b.n_left) and np.array_equal(a.n_query, b.n_query) and np.array_equal(a.stereo_idx, b.stereo_idx)
     ctx.close()
+
+
+def test_frontend_full_hd_orb_with_matches(pkg, orc):
+    """BASELINE.json configs[2]/[3] shape: ORB 2000 features at 1920x1080 plus both brute-force matches, batched."""
+    w, h, nfeat = 1920, 1080, 2000
+    left, right = pkg.synth_sequence(2000, 0, 3, w, h)
+    ctx = pkg.Context(0, w, h, 6)
+    ctx.orb_configure(nfeat, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB, 2)
+    kp_cap = ctx.orb_capacity(w, h)
+    oracle = orc.OrbOracle(nfeat, 1.2, 8, 20, 7)
+    prev = None
+    for f0, n in ((0, 2), (2, 1)):
+        out = pkg.FrontendBuffers(n, kp_cap, 1)
+        ctx.frontend_batch(np.ascontiguousarray(left[f0:f0 + n]), np.ascontiguousarray(right[f0:f0 + n]), out)
+        for i in range(n):
+            ok, od = oracle.extract(left[f0 + i])
+            nl, nr = out.n_left[i], out.n_right[i]
+            assert nl == len(ok) and np.array_equal(out.kps_left[i, :nl], ok)
+            assert np.unpackbits(out.desc_left[i, :nl] ^ od).sum() <= 2
+            if prev is not None:
+                nq = out.n_query[i]
+                si, sd = orc.match_hamming(prev[0], prev[1])
+                ti, td = orc.match_hamming(prev[0], out.desc_left[i, :nl])
+                assert np.array_equal(out.stereo_idx[i, :nq], si) and np.array_equal(out.stereo_dist[i, :nq], sd)
+                assert np.array_equal(out.temporal_idx[i, :nq], ti) and np.array_equal(out.temporal_dist[i, :nq], td)
+            prev = (out.desc_left[i, :nl].copy(), out.desc_right[i, :nr].copy())
+    ctx.close()

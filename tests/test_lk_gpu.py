@@ -38,7 +38,7 @@ def _check_lk(g, o, n_min_ok):
     return float(d.max())
 
 
-@pytest.mark.parametrize("w,h,seed", [(1241, 376, 1000), (640, 200, 7), (333, 257, 11)])
+@pytest.mark.parametrize("w,h,seed", [(1241, 376, 1000), (640, 200, 7), (333, 257, 11), (1920, 1080, 2000)])
 def test_lk_stereo_and_temporal(pkg, orc, w, h, seed):
     l0, r0 = pkg.synth_stereo_frame(seed, 3, w, h)
     l1, r1 = pkg.synth_stereo_frame(seed, 4, w, h)

@@ -9,7 +9,8 @@ CONFIGS = [
     (1241, 376, 1000, 1000),
     (640, 200, 500, 7),
     (333, 257, 300, 11),
-    (1920, 1080, 2000, 2000),
+    (1920, 1080, 2000, 2000),   # BASELINE.json configs[2]
+    (3840, 2160, 4000, 3000),   # BASELINE.json configs[3]
 ]
 
 
@@ -50,6 +51,8 @@ def test_pyramid_candidates_keypoints(pkg, orc, w, h, nfeat, seed):
         bits = int(np.unpackbits(desc[slot] ^ od).sum())
         total_bits += bits
         assert bits <= max(2, len(k) * 256 // 100000), f"descriptor bit mismatches {bits} of {len(k) * 256}"
+        if w * h > 4_000_000 and slot == 0:
+            break  # one 4K image is enough for the oracle's run time
     print(f"{w}x{h}: descriptor bit mismatch rate {total_bits}/{sum(len(k) for k in kps) * 256}")
     ctx.close()
 
