@@ -97,7 +97,7 @@ __device__ __forceinline__ void load_column(const uint8_t* __restrict__ img, con
 // lane x + 1.  Everything is register-resident: the lane walks down its column (sliding 3-row window for the Scharr
 // gradient), horizontal neighbours come from warp shuffles, and the interpolated window (I, Ix, Iy of 21 rows) stays in
 // registers for the Gauss-Newton iterations.  No shared memory, no derivative image.
-__global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
+__global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
                                                       float* __restrict__ lk_pts, uint8_t* __restrict__ lk_status, float* __restrict__ lk_err) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
@@ -159,11 +159,43 @@ __global__ void __launch_bounds__(LW * 32) k_lk_track(LkParams P, const svo_keyp
         short Iw[WIN];
         int Ixw[WIN], Iyw[WIN];
         int a11 = 0, a12 = 0, a22 = 0;
-        {
+        const bool inside = ipx - 1 >= 0 && ipx + 22 < G.w && ipy - 1 >= 0 && ipy + 22 < G.h;  // warp-uniform
+        if (inside) {
+            // Whole neighbourhood inside the image: no reflection, no zeroed gradients.  The Scharr operator and the bilinear
+            // interpolation are both linear with integer weights, so they commute exactly: interpolate the IMAGE once
+            // (Ib, un-descaled) and apply Scharr to Ib -- 4 multiplies per position instead of 12.
+            //   sum_ij w_ij Ix(x+i, y+j) = Vb(x+1, y) - Vb(x-1, y),          Vb = 3 Ib(y-1) + 10 Ib(y) + 3 Ib(y+1)
+            //   sum_ij w_ij Iy(x+i, y+j) = 3 (Db(x-1, y) + Db(x+1, y)) + 10 Db(x, y),   Db = Ib(y+1) - Ib(y-1)
+            int pix[24];
+            load_column<24>(I, G, ipx - 1 + min(lane, 23), ipy - 1, true, pix);
+            int pn0 = __shfl_down_sync(0xFFFFFFFFu, pix[0], 1), pn1 = __shfl_down_sync(0xFFFFFFFFu, pix[1], 1);
+            int ib0 = pix[0] * iw00 + pn0 * iw01 + pix[1] * iw10 + pn1 * iw11;  // Ib row -1 (image row ipy - 1)
+            int pn2 = __shfl_down_sync(0xFFFFFFFFu, pix[2], 1);
+            int ib1 = pix[1] * iw00 + pn1 * iw01 + pix[2] * iw10 + pn2 * iw11;  // Ib row 0
+            int pnr = pn2;
+#pragma unroll
+            for (int y = 0; y < WIN; ++y) {
+                const int pnn = __shfl_down_sync(0xFFFFFFFFu, pix[y + 3], 1);
+                const int ib2 = pix[y + 2] * iw00 + pnr * iw01 + pix[y + 3] * iw10 + pnn * iw11;  // Ib row y + 1
+                pnr = pnn;
+                const int Vb = 3 * (ib0 + ib2) + 10 * ib1, Db = ib2 - ib0;
+                const int ixn = __shfl_down_sync(0xFFFFFFFFu, Vb, 1) - __shfl_up_sync(0xFFFFFFFFu, Vb, 1);
+                const int iyn = 3 * (__shfl_up_sync(0xFFFFFFFFu, Db, 1) + __shfl_down_sync(0xFFFFFFFFu, Db, 1)) + 10 * Db;
+                const int ixv = descale(ixn, 14), iyv = descale(iyn, 14);
+                Iw[y] = (short)descale(ib1, 9);
+                Ixw[y] = ixv;
+                Iyw[y] = iyv;
+                a11 += ixv * ixv;
+                a12 += ixv * iyv;
+                a22 += iyv * iyv;
+                ib0 = ib1;
+                ib1 = ib2;
+            }
+        } else {
             const int X = ipx - 1 + min(lane, 23);
             const bool xin = X >= 0 && X < G.w;
             int pix[24];
-            load_column<24>(I, G, X, ipy - 1, ipx - 1 >= 0 && ipx + 22 < G.w && ipy - 1 >= 0 && ipy + 22 < G.h, pix);
+            load_column<24>(I, G, X, ipy - 1, false, pix);
             int tp = 0, tpn = 0, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;  // the row above (top taps of the bilinear stencil)
 #pragma unroll
             for (int r = 0; r < 22; ++r) {
