@@ -28,23 +28,53 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
+// horizontal [1 4 6 4 1] pass of one source row for 4 adjacent destination pixels x0..x0+3 (x0 % 4 == 0):
+// taps of pixel i start at source byte 2*x0 - 2 + 2*i.  Interior: 4 aligned words + IDP.4A; border: per byte with REFLECT_101.
+__device__ __forceinline__ void pyr_hpass4(const uint8_t* __restrict__ row, int x0, int sw, bool interior, int (&h)[4]) {
+    if (interior) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(row + 2 * x0 - 4);
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+        const uint32_t K = 1u | (4u << 8) | (6u << 16) | (4u << 24);
+        h[0] = (int)__dp4a(__funnelshift_r(w0, w1, 16), K, (w1 >> 16) & 0xFFu);
+        h[1] = (int)__dp4a(w1, K, w2 & 0xFFu);
+        h[2] = (int)__dp4a(__funnelshift_r(w1, w2, 16), K, (w2 >> 16) & 0xFFu);
+        h[3] = (int)__dp4a(w2, K, w3 & 0xFFu);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = 2 * (x0 + i);
+            h[i] = __ldg(row + reflect101(c - 2, sw)) + 4 * __ldg(row + reflect101(c - 1, sw)) + 6 * __ldg(row + reflect101(c, sw)) +
+                   4 * __ldg(row + reflect101(c + 1, sw)) + __ldg(row + reflect101(c + 2, sw));
+        }
+    }
+}
+
+// cv::pyrDown: each thread produces 4 x 2 destination pixels (7 source rows, the middle 3 shared by both output rows)
 __global__ void __launch_bounds__(256) k_pyr_down(LkLevelGeom S, LkLevelGeom D, SlotMap map) {
     const int slot = map.slot(blockIdx.z);
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= D.w || y >= D.h) return;
+    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y0 = (blockIdx.y * 4 + (threadIdx.x >> 6)) * 2;
+    if (x0 >= D.w || y0 >= D.h) return;
     const uint8_t* __restrict__ src = S.base + (size_t)slot * S.plane;
-    int cx[5];
+    // all 4 pixels' taps inside the row and the 4 aligned words inside the pitch
+    const bool interior = 2 * x0 - 4 >= 0 && 2 * x0 + 12 <= S.w;
+    int hr[7][4];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) cx[j] = reflect101(2 * x + j - 2, S.w);
-    int acc = 0;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const uint8_t* r = src + (size_t)reflect101(2 * y + i - 2, S.h) * S.pitch;
-        const int row = __ldg(r + cx[0]) + 4 * __ldg(r + cx[1]) + 6 * __ldg(r + cx[2]) + 4 * __ldg(r + cx[3]) + __ldg(r + cx[4]);
-        const int kw = (i == 0 || i == 4) ? 1 : (i == 2 ? 6 : 4);
-        acc += kw * row;
+    for (int i = 0; i < 7; ++i) {
+        const int sy = reflect101(min(2 * y0 + i - 2, S.h + 1), S.h);  // rows beyond the second output row's taps are unused
+        pyr_hpass4(src + (size_t)sy * S.pitch, x0, S.w, interior, hr[i]);
     }
-    D.base[(size_t)slot * D.plane + (size_t)y * D.pitch + x] = (uint8_t)((acc + 128) >> 8);
+    uint8_t* dst = D.base + (size_t)slot * D.plane + (size_t)y0 * D.pitch + x0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (y0 + r >= D.h) break;
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int acc = hr[2 * r][i] + hr[2 * r + 4][i] + 4 * (hr[2 * r + 1][i] + hr[2 * r + 3][i]) + 6 * hr[2 * r + 2][i];
+            out |= (uint32_t)((acc + 128) >> 8) << (8 * i);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (size_t)r * D.pitch) = out;  // pitch % 64 == 0: the store stays inside the row
+    }
 }
 
 struct LkParams {
@@ -316,7 +346,7 @@ int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
     for (int l = 1; l < c->lk_levels; ++l) {
         const LkLevelGeom& S = c->lk[l - 1];
         const LkLevelGeom& D = c->lk[l];
-        dim3 grid((D.w + 63) / 64, (D.h + 3) / 4, n_img);
+        dim3 grid((D.w + 255) / 256, (D.h + 7) / 8, n_img);
         k_pyr_down<<<grid, 256, 0, c->stream>>>(S, D, map);
         ++c->launches;
     }
