@@ -158,7 +158,9 @@ int svo_frontend_upload(svo_ctx* ctx, const uint8_t* left, const uint8_t* right,
 int svo_frontend_upload_dev(svo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, int n_frames, size_t stride);
 /* all kernels for the uploaded frames; inputs and outputs stay in HBM */
 int svo_frontend_run(svo_ctx* ctx);
-/* device -> host for every non-NULL field of out */
+/* device -> host for every non-NULL field of out, for the OLDEST run not yet delivered (runs are delivered in order; with
+ * max_images >= 2 * (2 * max_frames + 1) one more run may be in flight while this one is downloaded on its own stream).
+ * out == NULL retires the run without copying anything. */
 int svo_frontend_download(svo_ctx* ctx, svo_frontend_out* out);
 /* upload + run + download */
 int svo_frontend_batch(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride,

@@ -263,7 +263,7 @@ class Context:
         self._check(self._L.svo_frontend_run(self._h))
 
     def frontend_download(self, out):
-        self._check(self._L.svo_frontend_download(self._h, C.byref(out.struct)))
+        self._check(self._L.svo_frontend_download(self._h, C.byref(out.struct) if out is not None else None))
 
     def frontend_batch(self, left, right, out):
         assert left.shape == right.shape and left.dtype == np.uint8 and left.flags.c_contiguous and right.flags.c_contiguous

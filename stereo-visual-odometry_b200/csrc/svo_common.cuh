@@ -156,7 +156,13 @@ struct svo_ctx {
 
     // ---- frontend state
     int fe_mode = 0, fe_max_frames = 0, fe_ring = 0, fe_head = -1, fe_pending = 0, fe_first = 0;
-    int fe_done_first = 0, fe_done_n = 0, fe_done_skip = 0;  // the last completed run (what download reads)
+    struct DoneRun {
+        int first, n, skip, ev;
+    };
+    DoneRun fe_q[2] = {};  // completed, not yet downloaded runs (oldest at fe_qhead)
+    int fe_qhead = 0, fe_nq = 0, fe_depth = 1;
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t ev_done[2] = {};
     bool fe_has_last = false;
     bool fe_configured = false;
     // upload staging: linear H2D copies on a copy stream, double-buffered; rows are re-pitched into the ring by a kernel

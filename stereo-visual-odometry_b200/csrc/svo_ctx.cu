@@ -68,6 +68,11 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
     if (c->d_pattern) cudaFree(c->d_pattern);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->d2h_stream) {
+        cudaStreamSynchronize(c->d2h_stream);
+        cudaStreamDestroy(c->d2h_stream);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(c->ev_done[i]);
+    }
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (int i = 0; i < 2; ++i) {
@@ -422,6 +427,11 @@ int svo_layout(svo_ctx* c, int w, int h) {
 int svo_ensure_pinned(svo_ctx* c, size_t bytes) {
     if (c->pinned_bytes >= bytes) return SVO_OK;
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->d2h_stream) {
+        cudaStreamSynchronize(c->d2h_stream);
+        cudaStreamDestroy(c->d2h_stream);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(c->ev_done[i]);
+    }
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (int i = 0; i < 2; ++i) {

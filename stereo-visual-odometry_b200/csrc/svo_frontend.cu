@@ -150,6 +150,7 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     if (!(mode & (SVO_MODE_ORB | SVO_MODE_LK)) || (mode & ~(SVO_MODE_ORB | SVO_MODE_LK)) || w <= 0 || h <= 0 || max_frames < 1)
         return c->fail(SVO_ERR_INVALID, "svo_frontend_configure: bad mode / size / max_frames");
     if (2 * (max_frames + 1) > c->max_images) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure: need max_images >= 2 * (max_frames + 1)");
+    if (c->fe_configured) cudaStreamSynchronize(c->stream);
     if ((mode & SVO_MODE_ORB) && !c->user_configured) return c->fail(SVO_ERR_NOT_CONFIGURED, "svo_orb_configure() first");
     cudaSetDevice(c->device);
     int rc;
@@ -157,7 +158,10 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     if ((rc = svo_layout(c, w, h)) != SVO_OK) return rc;
     if (mode & SVO_MODE_LK)
         if ((rc = layout_aux(c, std::max(1024, w * h / 64))) != SVO_OK) return rc;
-    c->fe_ring = max_frames + 1;
+    // ring of frame slots: previous frame + one batch, or + two batches when the context has room -- then the results of
+    // batch k can be downloaded (own stream) while batch k+1 is already running
+    c->fe_depth = (2 * (2 * max_frames + 1) <= c->max_images) ? 2 : 1;
+    c->fe_ring = c->fe_depth * max_frames + 1;
     if (mode & SVO_MODE_ORB) {
         if (c->d_match) cudaFree(c->d_match);
         c->d_match = nullptr;
@@ -181,10 +185,14 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     c->stage_idx = 0;
     c->fe_mode = mode;
     c->fe_max_frames = max_frames;
+    if (!c->d2h_stream) {
+        SVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) SVO_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
     c->fe_head = c->fe_ring - 1;
     c->fe_has_last = false;
     c->fe_pending = 0;
-    c->fe_done_n = 0;
+    c->fe_nq = 0;
     c->fe_configured = true;
     return SVO_OK;
 }
@@ -192,9 +200,11 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
 extern "C" int svo_frontend_reset(svo_ctx* c) {
     if (!c) return SVO_ERR_INVALID;
     if (!c->fe_configured) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure() first");
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+    cudaStreamSynchronize(c->stream);
     c->fe_has_last = false;
     c->fe_pending = 0;
-    c->fe_done_n = 0;
+    c->fe_nq = 0;
     return SVO_OK;
 }
 
@@ -246,6 +256,7 @@ static int frontend_upload_impl(svo_ctx* c, const uint8_t* left, const uint8_t* 
 extern "C" int svo_frontend_run(svo_ctx* c) {
     if (!c) return SVO_ERR_INVALID;
     if (!c->fe_configured || c->fe_pending < 1) return c->fail(SVO_ERR_INVALID, "svo_frontend_run: nothing uploaded");
+    if (c->fe_nq >= c->fe_depth) return c->fail(SVO_ERR_INVALID, "svo_frontend_run: download the previous results first (ring depth reached)");
     cudaSetDevice(c->device);
     const int ring = c->fe_ring, first = (c->fe_head + 1) % ring, n = c->fe_pending, skip_first = c->fe_has_last ? 0 : 1;
     int rc;
@@ -268,9 +279,15 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
         for (int k = 0; k < 4; ++k)
             if ((rc = launch_lk_track(c, first, ring, n, skip_first, calls[k], 30, 0.01, 0.001)) != SVO_OK) return rc;
     }
-    c->fe_done_first = first;
-    c->fe_done_n = n;
-    c->fe_done_skip = skip_first;
+    {  // completed-run queue (depth <= 2): what svo_frontend_download delivers, oldest first
+        svo_ctx::DoneRun& d = c->fe_q[(c->fe_qhead + c->fe_nq) % 2];
+        d.first = first;
+        d.n = n;
+        d.skip = skip_first;
+        d.ev = (c->fe_qhead + c->fe_nq) % 2;
+        SVO_CUDA_TRY(c, cudaEventRecord(c->ev_done[d.ev], c->stream));
+        ++c->fe_nq;
+    }
     c->fe_head = (first + n - 1) % ring;
     c->fe_has_last = true;
     c->fe_pending = 0;
@@ -299,9 +316,22 @@ struct RingCopy {
 
 extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
     if (!c) return SVO_ERR_INVALID;
-    if (!c->fe_configured || c->fe_done_n < 1 || !out) return c->fail(SVO_ERR_INVALID, "svo_frontend_download: nothing to download");
+    if (!c->fe_configured || c->fe_nq < 1) return c->fail(SVO_ERR_INVALID, "svo_frontend_download: nothing to download");
     cudaSetDevice(c->device);
-    const int ring = c->fe_ring, first = c->fe_done_first, n = c->fe_done_n, skip = c->fe_done_skip;
+    const svo_ctx::DoneRun done = c->fe_q[c->fe_qhead];
+    c->fe_qhead = (c->fe_qhead + 1) % 2;
+    --c->fe_nq;
+    if (!out) return SVO_OK;  // results stay on the device (device-resident pipelines): just retire the run
+    const int ring = c->fe_ring, first = done.first, n = done.n, skip = done.skip;
+    // all copies go on the download stream, behind the event that marks the end of that run's kernels
+    cudaStream_t const compute_stream = c->stream;
+    SVO_CUDA_TRY(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_done[done.ev], 0));
+    struct StreamSwap {
+        svo_ctx* c;
+        cudaStream_t saved;
+        ~StreamSwap() { c->stream = saved; }
+    } swap{c, compute_stream};
+    c->stream = c->d2h_stream;
     const int S = c->max_images;
     int rc;
     // ---- counts first (one small copy + sync), then exact-width 2-D copies

@@ -113,3 +113,51 @@ def test_frontend_full_hd_orb_with_matches(pkg, orc):
                 assert np.array_equal(out.temporal_idx[i, :nq], ti) and np.array_equal(out.temporal_dist[i, :nq], td)
             prev = (out.desc_left[i, :nl].copy(), out.desc_right[i, :nr].copy())
     ctx.close()
+
+
+def test_frontend_pipelined_equals_sequential(pkg):
+    """Depth-2 ring: run(k+1) is issued before download(k); results must equal the synchronous svo_frontend_batch path."""
+    w, h, B, nb = 640, 200, 3, 4
+    left, right = pkg.synth_sequence(9, 0, B * nb, w, h)
+    fields = ("kps_left", "desc_left", "n_left", "n_query", "stereo_idx", "temporal_idx", "fast_kps", "n_fast", "n_seed", "lk_p3", "lk_status")
+
+    def make(max_images):
+        ctx = pkg.Context(0, w, h, max_images)
+        ctx.orb_configure(300, 1.2, 8, 20, 7)
+        ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+        return ctx, ctx.orb_capacity(w, h), max(1024, w * h // 64)
+
+    def views(k):
+        return np.ascontiguousarray(left[k * B:(k + 1) * B]), np.ascontiguousarray(right[k * B:(k + 1) * B])
+
+    seq, kc, pc = make(2 * (B + 1))
+    ref = []
+    for k in range(nb):
+        o = pkg.FrontendBuffers(B, kc, pc, fields=fields)
+        seq.frontend_batch(*views(k), o)
+        ref.append(o)
+    seq.close()
+
+    pipe, kc, pc = make(2 * (2 * B + 1))
+    got = [pkg.FrontendBuffers(B, kc, pc, fields=fields) for _ in range(nb)]
+    pipe.frontend_upload(*views(0))
+    pipe.frontend_run()
+    for k in range(nb):
+        if k + 1 < nb:
+            pipe.frontend_upload(*views(k + 1))
+            pipe.frontend_run()
+        pipe.frontend_download(got[k])
+    with pytest.raises(pkg.SvoError):
+        pipe.frontend_download(got[0])  # nothing left to deliver
+    pipe.close()
+    for k in range(nb):
+        for f in fields:
+            a, b = getattr(ref[k], f), getattr(got[k], f)
+            if f in ("n_left", "n_query", "n_fast", "n_seed"):
+                assert np.array_equal(a, b), (k, f)
+        for i in range(B):
+            nl, nq, nf, ns = ref[k].n_left[i], ref[k].n_query[i], ref[k].n_fast[i], ref[k].n_seed[i]
+            assert np.array_equal(ref[k].kps_left[i, :nl], got[k].kps_left[i, :nl]) and np.array_equal(ref[k].desc_left[i, :nl], got[k].desc_left[i, :nl])
+            assert np.array_equal(ref[k].stereo_idx[i, :nq], got[k].stereo_idx[i, :nq]) and np.array_equal(ref[k].temporal_idx[i, :nq], got[k].temporal_idx[i, :nq])
+            assert np.array_equal(ref[k].fast_kps[i, :nf], got[k].fast_kps[i, :nf])
+            assert np.array_equal(ref[k].lk_p3[i, :ns], got[k].lk_p3[i, :ns]) and np.array_equal(ref[k].lk_status[i, :, :ns], got[k].lk_status[i, :, :ns])
