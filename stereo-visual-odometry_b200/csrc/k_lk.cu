@@ -132,13 +132,14 @@ __global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_k
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     if (f == 0 && P.skip_first) return;
-    const int cur = (P.first + f) % P.ring;
-    const int pfs = (P.first + f - P.call.prev_back + P.ring) % P.ring, nfs = (P.first + f - P.call.next_back + P.ring) % P.ring;
-    const int prev_slot = P.call.prev_side * P.ring + pfs, next_slot = P.call.next_side * P.ring + nfs;
-    const int seed_fs = (P.first + f - 1 + P.ring) % P.ring;  // seeds: FAST corners of the previous left image
+    // ring arithmetic without division: first, f < ring, so every index below is in [0, 2 * ring)
+    const int cur_u = P.first + f, cur = cur_u >= P.ring ? cur_u - P.ring : cur_u;
+    const int seed_fs = cur == 0 ? P.ring - 1 : cur - 1;  // seeds: FAST corners of the previous left image
     const int n = P.standalone ? P.n_fixed : nfast[seed_fs];
     const int pt = blockIdx.x * LW + warp;
-    if (pt >= n) return;  // warp-uniform
+    if (pt >= n) return;  // warp-uniform; most warps of the fixed-size grid leave here
+    const int pfs = P.call.prev_back ? seed_fs : cur, nfs = P.call.next_back ? seed_fs : cur;  // back is 0 or 1
+    const int prev_slot = P.call.prev_side * P.ring + pfs, next_slot = P.call.next_side * P.ring + nfs;
 
     float px, py;
     if (!P.standalone && P.call.src_list == 0) {
