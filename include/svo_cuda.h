@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SVO_ABI_VERSION 1
+#define SVO_ABI_VERSION 2
 
 typedef enum svo_status {
     SVO_OK = 0,
@@ -148,10 +148,22 @@ typedef struct svo_frontend_out {
     float* lk_p3;           /* t   left   (call 3) */
     float* lk_p0r;          /* t-1 left, returned (call 4) */
     uint8_t* lk_status;     /* 4 x pt_cap per frame: status1..status4 */
+    /* device-side post-filters: what the reference hands to triangulation / PnP */
+    float* orb_t2_left;     /* ORB_Robust_Find_MuliImage_MatchedFeatures outputs (tracking.cpp:534-581), kp_cap*2 floats per frame */
+    float* orb_t1_left;
+    float* orb_t1_right;
+    int32_t* n_orb_matched; /* per frame: number of accepted matches */
+    float* lkf_t1_left;     /* LK_Robust_Find_MuliImage_MatchedFeatures outputs after deleteBadmatchFeatures (tracking.cpp:583-660) */
+    float* lkf_t1_right;
+    float* lkf_t2_right;
+    float* lkf_t2_left;
+    int32_t* n_lk_matched;  /* per frame: number of surviving tracks */
 } svo_frontend_out;
 
 int svo_frontend_configure(svo_ctx* ctx, int w, int h, int mode, int max_frames);
 int svo_frontend_reset(svo_ctx* ctx);
+/* Tracking::feature_match_error_ (parameter.cpp:53, config/default.yaml:66; default 3) used by the device-side post-filters */
+int svo_frontend_set_match_error(svo_ctx* ctx, double feature_match_error);
 /* host images -> device (left/right: n_frames contiguous images of h rows, `stride` bytes per row) */
 int svo_frontend_upload(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride);
 /* same, but left/right are DEVICE pointers (images already resident in HBM, e.g. written by a decoder or a torch tensor) */

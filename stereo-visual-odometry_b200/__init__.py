@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "svo_ctx_launch_count", "svo_ctx_enable_stage_timing", "svo_ctx_set_timing_slot", "svo_ctx_stage_ms", "svo_orb_configure", "svo_orb_tables",
     "svo_orb_capacity", "svo_orb_level_size", "svo_orb_extract", "svo_orb_extract_batch", "svo_orb_read_level",
     "svo_orb_read_candidates", "svo_fast_detect", "svo_match_hamming", "svo_lk_track", "svo_frontend_configure",
-    "svo_frontend_reset", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
+    "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
     "svo_synth_stereo_frame",
 ]
 
@@ -46,7 +46,9 @@ class SvoError(RuntimeError):
 class FrontendOut(C.Structure):
     _fields_ = [("kp_cap", C.c_int32), ("pt_cap", C.c_int32)] + [(n, C.c_void_p) for n in (
         "kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
-        "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status")]
+        "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status",
+        "orb_t2_left", "orb_t1_left", "orb_t1_right", "n_orb_matched", "lkf_t1_left", "lkf_t1_right", "lkf_t2_right", "lkf_t2_left",
+        "n_lk_matched")]
 
 
 _lib = None
@@ -242,6 +244,9 @@ class Context:
         self._check(self._L.svo_frontend_configure(self._h, w, h, mode, max_frames))
         self.fe = dict(w=w, h=h, mode=mode, max_frames=max_frames, kp_cap=self.orb_capacity(w, h) if mode & MODE_ORB else 0)
 
+    def frontend_set_match_error(self, fme):
+        self._check(self._L.svo_frontend_set_match_error(self._h, C.c_double(fme)))
+
     def frontend_reset(self):
         self._check(self._L.svo_frontend_reset(self._h))
 
@@ -274,7 +279,9 @@ class FrontendBuffers:
     """Host-side output arrays of svo_frontend_download / svo_frontend_batch (numpy-owned; `fields` selects what is copied)."""
 
     ALL = ("kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
-           "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status")
+           "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status",
+           "orb_t2_left", "orb_t1_left", "orb_t1_right", "n_orb_matched", "lkf_t1_left", "lkf_t1_right", "lkf_t2_right", "lkf_t2_left",
+           "n_lk_matched")
 
     def __init__(self, n_frames, kp_cap, pt_cap, fields=None, alloc=None):
         fields = self.ALL if fields is None else fields
@@ -286,7 +293,10 @@ class FrontendBuffers:
                       temporal_idx=((F, K), np.int32), temporal_dist=((F, K), np.int32),
                       fast_kps=((F, P), KP_DTYPE), n_fast=((F,), np.int32), n_seed=((F,), np.int32),
                       lk_p1=((F, P, 2), np.float32), lk_p2=((F, P, 2), np.float32), lk_p3=((F, P, 2), np.float32),
-                      lk_p0r=((F, P, 2), np.float32), lk_status=((F, 4, P), np.uint8))
+                      lk_p0r=((F, P, 2), np.float32), lk_status=((F, 4, P), np.uint8),
+                      orb_t2_left=((F, K, 2), np.float32), orb_t1_left=((F, K, 2), np.float32), orb_t1_right=((F, K, 2), np.float32),
+                      n_orb_matched=((F,), np.int32), lkf_t1_left=((F, P, 2), np.float32), lkf_t1_right=((F, P, 2), np.float32),
+                      lkf_t2_right=((F, P, 2), np.float32), lkf_t2_left=((F, P, 2), np.float32), n_lk_matched=((F,), np.int32))
         self.struct = FrontendOut()
         self.struct.kp_cap = kp_cap
         self.struct.pt_cap = pt_cap
@@ -310,10 +320,12 @@ class FrontendBuffers:
         def mx(a):
             return int(a.max()) if a is not None and len(a) else 0
         ml, mr, mq, mf, ms = mx(self.n_left), mx(self.n_right), mx(self.n_query), mx(self.n_fast), mx(self.n_seed)
+        mo, mk = mx(self.n_orb_matched), mx(self.n_lk_matched)
         for name, width in (("kps_left", ml * 28), ("desc_left", ml * 32), ("kps_right", mr * 28), ("desc_right", mr * 32),
                             ("stereo_idx", mq * 4), ("stereo_dist", mq * 4), ("temporal_idx", mq * 4), ("temporal_dist", mq * 4),
                             ("fast_kps", mf * 28), ("lk_p1", ms * 8), ("lk_p2", ms * 8), ("lk_p3", ms * 8), ("lk_p0r", ms * 8),
-                            ("lk_status", ms * 4)):
+                            ("lk_status", ms * 4), ("orb_t2_left", mo * 8), ("orb_t1_left", mo * 8), ("orb_t1_right", mo * 8),
+                            ("lkf_t1_left", mk * 8), ("lkf_t1_right", mk * 8), ("lkf_t2_right", mk * 8), ("lkf_t2_left", mk * 8)):
             if getattr(self, name) is not None:
                 total += width * F
         return total + 3 * 4 * 2 * (F + 1)  # the count / flag arrays

@@ -151,6 +151,13 @@ struct svo_ctx {
     uint8_t* d_lk_status = nullptr;  // per frame slot: 4 x pt_cap
     float* d_lk_err = nullptr;
 
+    // ---- device-side post-filters (K10 / K11): per frame slot
+    float* d_orb_pts = nullptr;  // [frame slot][3: t2_left, t1_left, t1_right][kp_cap][2]
+    int* d_norb = nullptr;
+    float* d_lkf_pts = nullptr;  // [frame slot][5: t1_left, t1_right, t2_right, t2_left, t1_left_returned][pt_cap][2]
+    int* d_nlkf = nullptr;
+    double fe_match_error = 3.0;  // feature_match_error (config/default.yaml:66)
+
     // ---- matches (frontend): per frame slot, kp_cap each
     int* d_match = nullptr;  // [frame slot][4][kp_cap]: stereo idx, stereo dist, temporal idx, temporal dist
 
@@ -214,6 +221,8 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img);               
 int launch_octree(svo_ctx* c, const SlotMap& map, int n_img);                        // K3
 int launch_describe(svo_ctx* c, const SlotMap& map, int n_img);                      // K4 + K5
 int launch_match_frontend(svo_ctx* c, int first, int ring, int n_frames, int skip_first);  // K6
+int launch_orb_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_first);      // K10
+int launch_lk_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_first);       // K11
 int launch_fast_full(svo_ctx* c, const SlotMap& map, int n_img, int threshold);      // K9 (+ ordered compaction)
 int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img);                    // K7
 // one call of the 4-call LK chain for n_frames unit frames (K8); see k_lk.cu

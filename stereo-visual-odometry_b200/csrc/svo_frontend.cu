@@ -183,6 +183,23 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     c->stage_bytes = 2 * svo_align((size_t)max_frames * h * (2 * (size_t)w), 256);  // 2 sides, stride up to 2 x width
     for (int i = 0; i < 2; ++i) SVO_CUDA_TRY(c, cudaMalloc(&c->d_stage[i], c->stage_bytes));
     c->stage_idx = 0;
+    {
+        void** ptrs[] = {(void**)&c->d_orb_pts, (void**)&c->d_norb, (void**)&c->d_lkf_pts, (void**)&c->d_nlkf};
+        for (void** p : ptrs) {
+            if (*p) cudaFree(*p);
+            *p = nullptr;
+        }
+    }
+    if (mode & SVO_MODE_ORB) {
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_orb_pts, sizeof(float) * 2 * 3 * (size_t)c->kp_cap * c->fe_ring));
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_norb, sizeof(int) * c->fe_ring));
+        SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_norb, 0, sizeof(int) * c->fe_ring, c->stream));
+    }
+    if (mode & SVO_MODE_LK) {
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkf_pts, sizeof(float) * 2 * 5 * (size_t)c->pt_cap * c->fe_ring));
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_nlkf, sizeof(int) * c->fe_ring));
+        SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nlkf, 0, sizeof(int) * c->fe_ring, c->stream));
+    }
     c->fe_mode = mode;
     c->fe_max_frames = max_frames;
     if (!c->d2h_stream) {
@@ -194,6 +211,12 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     c->fe_pending = 0;
     c->fe_nq = 0;
     c->fe_configured = true;
+    return SVO_OK;
+}
+
+extern "C" int svo_frontend_set_match_error(svo_ctx* c, double fme) {
+    if (!c) return SVO_ERR_INVALID;
+    c->fe_match_error = fme;
     return SVO_OK;
 }
 
@@ -270,6 +293,7 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
     if (c->fe_mode & SVO_MODE_ORB) {
         if ((rc = svo_orb_run(c, both, 2 * n)) != SVO_OK) return rc;
         if ((rc = launch_match_frontend(c, first, ring, n, skip_first)) != SVO_OK) return rc;
+        if ((rc = launch_orb_filter(c, first, ring, n, skip_first)) != SVO_OK) return rc;
     }
     if (c->fe_mode & SVO_MODE_LK) {
         if ((rc = launch_fast_full(c, leftonly, n, 20)) != SVO_OK) return rc;  // int fast_threshold = 20 (tracking.cpp:99)
@@ -278,6 +302,7 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
         const LkCall calls[4] = {{0, 1, 1, 1, 0, 1, 0}, {1, 1, 1, 0, 1, 2, 1}, {1, 0, 0, 0, 2, 3, 2}, {0, 0, 0, 1, 3, 4, 3}};
         for (int k = 0; k < 4; ++k)
             if ((rc = launch_lk_track(c, first, ring, n, skip_first, calls[k], 30, 0.01, 0.001)) != SVO_OK) return rc;
+        if ((rc = launch_lk_filter(c, first, ring, n, skip_first)) != SVO_OK) return rc;
     }
     {  // completed-run queue (depth <= 2): what svo_frontend_download delivers, oldest first
         svo_ctx::DoneRun& d = c->fe_q[(c->fe_qhead + c->fe_nq) % 2];
@@ -335,7 +360,9 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
     const int S = c->max_images;
     int rc;
     // ---- counts first (one small copy + sync), then exact-width 2-D copies
-    std::vector<int> nkp(S, 0), nfast(S, 0), flags(S, 0);
+    std::vector<int> nkp(S, 0), nfast(S, 0), flags(S, 0), norb(ring, 0), nlkf(ring, 0);
+    if (c->fe_mode & SVO_MODE_ORB) SVO_CUDA_TRY(c, cudaMemcpyAsync(norb.data(), c->d_norb, sizeof(int) * ring, cudaMemcpyDeviceToHost, c->stream));
+    if (c->fe_mode & SVO_MODE_LK) SVO_CUDA_TRY(c, cudaMemcpyAsync(nlkf.data(), c->d_nlkf, sizeof(int) * ring, cudaMemcpyDeviceToHost, c->stream));
     if (c->fe_mode & SVO_MODE_ORB) SVO_CUDA_TRY(c, cudaMemcpyAsync(nkp.data(), c->d_nkp, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
     if (c->fe_mode & SVO_MODE_LK) SVO_CUDA_TRY(c, cudaMemcpyAsync(nfast.data(), c->d_nfast, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
     SVO_CUDA_TRY(c, cudaMemcpyAsync(flags.data(), c->d_flags, sizeof(int) * S, cudaMemcpyDeviceToHost, c->stream));
@@ -369,6 +396,15 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
         if (out->desc_left && (rc = rcpy.copy(out->desc_left, hk * 32, c->d_desc, (size_t)K * 32, (size_t)maxL * 32))) return rc;
         if (out->kps_right && (rc = rcpy.copy(out->kps_right, hk * 28, c->d_kps + (size_t)ring * K, (size_t)K * 28, (size_t)maxR * 28))) return rc;
         if (out->desc_right && (rc = rcpy.copy(out->desc_right, hk * 32, c->d_desc + (size_t)ring * K * 32, (size_t)K * 32, (size_t)maxR * 32))) return rc;
+        int maxM = 0;
+        for (int f = 0; f < n; ++f) {
+            const int fs = (first + f) % ring;
+            maxM = std::max(maxM, norb[fs]);
+            if (out->n_orb_matched) out->n_orb_matched[f] = norb[fs];
+        }
+        float* oh[3] = {out->orb_t2_left, out->orb_t1_left, out->orb_t1_right};
+        for (int r = 0; r < 3; ++r)
+            if (oh[r] && (rc = rcpy.copy(oh[r], hk * 8, c->d_orb_pts + (size_t)r * K * 2, (size_t)3 * K * 8, (size_t)maxM * 8))) return rc;
         int32_t* mh[4] = {out->stereo_idx, out->stereo_dist, out->temporal_idx, out->temporal_dist};
         for (int r = 0; r < 4; ++r)
             if (mh[r] && (rc = rcpy.copy(mh[r], hk * 4, c->d_match + (size_t)r * K, (size_t)4 * K * 4, (size_t)maxQ * 4))) return rc;
@@ -391,6 +427,15 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
         float* ph[4] = {out->lk_p1, out->lk_p2, out->lk_p3, out->lk_p0r};
         for (int r = 0; r < 4; ++r)
             if (ph[r] && (rc = rcpy.copy(ph[r], hp * 8, c->d_lk_pts + (size_t)(r + 1) * P * 2, (size_t)5 * P * 8, (size_t)maxS * 8))) return rc;
+        int maxK = 0;
+        for (int f = 0; f < n; ++f) {
+            const int fs = (first + f) % ring;
+            maxK = std::max(maxK, nlkf[fs]);
+            if (out->n_lk_matched) out->n_lk_matched[f] = nlkf[fs];
+        }
+        float* fh[4] = {out->lkf_t1_left, out->lkf_t1_right, out->lkf_t2_right, out->lkf_t2_left};
+        for (int r = 0; r < 4; ++r)
+            if (fh[r] && (rc = rcpy.copy(fh[r], hp * 8, c->d_lkf_pts + (size_t)r * P * 2, (size_t)5 * P * 8, (size_t)maxK * 8))) return rc;
         if (out->lk_status)
             for (int r = 0; r < 4; ++r)
                 if ((rc = rcpy.copy(out->lk_status + (size_t)r * hp, 4 * hp, c->d_lk_status + (size_t)r * P, (size_t)4 * P, (size_t)maxS))) return rc;

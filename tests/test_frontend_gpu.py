@@ -65,7 +65,22 @@ def test_frontend_sequence(pkg, orc, w, h, nfeat, max_frames, n_total):
                                              *[out.lk_status[i, k, :ns] for k in range(4)])
                 keep_o = orc.lk_chain_filter(seeds, p1, p2, p3, p0r, *sts)
                 assert np.array_equal(keep_g, keep_o)
-            prev = dict(l=left[f], r=right[f], dl=out.desc_left[i, :nl].copy(), dr=out.desc_right[i, :nr].copy(), fast=ofast)
+                # K11: deleteBadmatchFeatures on the device == the oracle filter applied to the device's own chain outputs
+                nk = out.n_lk_matched[i]
+                assert nk == keep_g.sum()
+                assert np.array_equal(out.lkf_t1_left[i, :nk], seeds[keep_g]) and np.array_equal(out.lkf_t1_right[i, :nk], out.lk_p1[i, :ns][keep_g])
+                assert np.array_equal(out.lkf_t2_right[i, :nk], out.lk_p2[i, :ns][keep_g]) and np.array_equal(out.lkf_t2_left[i, :nk], out.lk_p3[i, :ns][keep_g])
+                # K10: the ORB association filter (tracking.cpp:546-577)
+                acc = orc.orb_match_filter(si, sd, ti, td, len(prev["dr"]), nl, prev["kl"], prev["kr"], 3.0)
+                nm = out.n_orb_matched[i]
+                assert nm == len(acc) and nm > 20
+                cur_xy = np.stack([out.kps_left[i, :nl]["x"], out.kps_left[i, :nl]["y"]], 1)
+                pl_xy = np.stack([prev["kl"]["x"], prev["kl"]["y"]], 1)
+                pr_xy = np.stack([prev["kr"]["x"], prev["kr"]["y"]], 1)
+                assert np.array_equal(out.orb_t1_left[i, :nm], pl_xy[acc[:, 0]]) and np.array_equal(out.orb_t1_right[i, :nm], pr_xy[acc[:, 1]])
+                assert np.array_equal(out.orb_t2_left[i, :nm], cur_xy[acc[:, 2]])
+            prev = dict(l=left[f], r=right[f], dl=out.desc_left[i, :nl].copy(), dr=out.desc_right[i, :nr].copy(), fast=ofast,
+                        kl=out.kps_left[i, :nl].copy(), kr=out.kps_right[i, :nr].copy())
         f0 += n
     ctx.close()
 
