@@ -1,0 +1,114 @@
+"""GPU: size-independent properties and edge cases -- random geometries vs the oracle, shard equivalence (the multi-GPU
+rule of SURVEY.md 8e checked on one device), error paths of the C ABI."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_random_geometries_match_oracle(pkg, orc):
+    """Odd widths/heights, different level counts and scale factors exercise the cell grid, tile split and octree roots."""
+    rng = np.random.default_rng(12345)
+    cases = [(int(rng.integers(120, 900)), int(rng.integers(100, 500)), int(rng.integers(100, 1500)), int(rng.integers(1, 9)),
+              float(rng.choice([1.2, 1.1, 1.5, 1.33]))) for _ in range(8)]
+    cases += [(97, 97, 50, 2, 1.2), (1241, 376, 1000, 8, 2.0), (640, 480, 700, 5, 1.2), (400, 1000, 300, 4, 1.2)]
+    for w, h, nfeat, nlev, sf in cases:
+        if w < h / 2 + 1:  # nIni == 0 is undefined in the reference
+            continue
+        left, _ = pkg.synth_stereo_frame(w * 7 + h, 1, w, h)
+        ctx = pkg.Context(0, w, h, 1)
+        ctx.orb_configure(nfeat, sf, nlev, 20, 7)
+        try:
+            k, d = ctx.orb_extract(left)
+        except pkg.SvoError as e:  # levels too small for a cell grid are rejected loudly, never mis-computed
+            assert e.code == pkg.SVO_ERR_INVALID, (w, h, nlev, sf, str(e))
+            ctx.close()
+            continue
+        o = orc.OrbOracle(nfeat, sf, nlev, 20, 7)
+        ok, od = o.extract(left)
+        assert len(k) == len(ok), (w, h, nfeat, nlev, sf, len(k), len(ok))
+        assert np.array_equal(k, ok), (w, h, nfeat, nlev, sf)
+        assert np.unpackbits(d ^ od).sum() <= 2
+        for l in range(nlev):
+            assert np.array_equal(ctx.orb_read_level(0, l), o.level(l)), (w, h, l, sf)
+        ctx.close()
+
+
+def test_shard_equivalence(pkg):
+    """Frames split over 2 'ranks' with a one-frame overlap give exactly the units of the unsharded run (no collective)."""
+    sh = importlib.import_module("svo_b200.sharding")
+    w, h, F, B = 640, 200, 9, 4
+    left, right = pkg.synth_sequence(77, 0, F, w, h)
+    fields = ("kps_left", "n_left", "n_query", "stereo_idx", "temporal_idx", "temporal_dist", "n_seed", "lk_p3", "lk_status",
+              "n_orb_matched", "orb_t2_left", "n_lk_matched", "lkf_t2_left")
+
+    def run(f0, n):
+        ctx = pkg.Context(0, w, h, 2 * (B + 1))
+        ctx.orb_configure(400, 1.2, 8, 20, 7)
+        ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+        kc, pc = ctx.orb_capacity(w, h), max(1024, w * h // 64)
+        units = {}
+        for b0, bn in sh.batches(f0, n, B):
+            out = pkg.FrontendBuffers(bn, kc, pc, fields=fields)
+            ctx.frontend_batch(np.ascontiguousarray(left[b0:b0 + bn]), np.ascontiguousarray(right[b0:b0 + bn]), out)
+            for i in range(bn):
+                if b0 + i == f0:
+                    continue  # the overlap frame only warms up "last_frame_"
+                nq, ns, nm, nk = out.n_query[i], out.n_seed[i], out.n_orb_matched[i], out.n_lk_matched[i]
+                units[b0 + i - 1] = (out.kps_left[i, :out.n_left[i]].copy(), out.stereo_idx[i, :nq].copy(), out.temporal_idx[i, :nq].copy(),
+                                     out.temporal_dist[i, :nq].copy(), out.lk_p3[i, :ns].copy(), out.lk_status[i, :, :ns].copy(),
+                                     out.orb_t2_left[i, :nm].copy(), out.lkf_t2_left[i, :nk].copy())
+        ctx.close()
+        return units
+
+    whole = run(0, F)
+    assert sorted(whole) == list(range(F - 1))
+    merged = {}
+    for r in range(2):
+        f0, n = sh.shard_units(F, 2, r)
+        merged.update(run(f0, n))
+    assert sorted(merged) == sorted(whole)
+    for u in whole:
+        for a, b in zip(whole[u], merged[u]):
+            assert np.array_equal(a, b), u
+
+
+def test_error_paths(pkg):
+    L = pkg.lib()
+    ctx = pkg.Context(0, 640, 480, 2)
+    img = np.zeros((480, 640), np.uint8)
+    with pytest.raises(pkg.SvoError) as e:  # not configured
+        ctx.orb_extract(img)
+    assert e.value.code == pkg.SVO_ERR_NOT_CONFIGURED
+    ctx.orb_configure(500, 1.2, 8, 20, 7)
+    with pytest.raises(pkg.SvoError) as e:  # image larger than the context
+        ctx.orb_extract(np.zeros((481, 640), np.uint8))
+    assert e.value.code == pkg.SVO_ERR_INVALID
+    kps = np.zeros(10, pkg.KP_DTYPE)
+    desc = np.zeros((10, 32), np.uint8)
+    n = C.c_int()
+    left, _ = pkg.synth_stereo_frame(1, 0, 640, 480)
+    rc = L.svo_orb_extract(ctx._h, left.ctypes.data_as(C.c_void_p), 640, 480, C.c_size_t(640), kps.ctypes.data_as(C.c_void_p),
+                           desc.ctypes.data_as(C.c_void_p), 10, C.byref(n))
+    assert rc == pkg.SVO_ERR_CAPACITY  # never silently truncated
+    with pytest.raises(pkg.SvoError):
+        ctx.orb_configure(500, 1.0, 8, 20, 7)  # scaleFactor must be > 1
+    with pytest.raises(pkg.SvoError):
+        ctx.lk_track(left, left, np.zeros((4, 2), np.float32), win=15)
+    with pytest.raises(pkg.SvoError):
+        ctx.fast_detect(left, 20, nms=False)
+    with pytest.raises(pkg.SvoError):
+        ctx.frontend_configure(640, 480, pkg.MODE_ORB, 4)  # needs max_images >= 2 * (4 + 1)
+    ctx.frontend_configure(320, 240, pkg.MODE_LK, 0 + 1) if False else None
+    small = pkg.Context(0, 640, 480, 4)
+    small.orb_configure(300, 1.2, 8, 20, 7)
+    small.frontend_configure(640, 480, pkg.MODE_ORB, 1)
+    with pytest.raises(pkg.SvoError):
+        small.frontend_run()  # nothing uploaded
+    with pytest.raises(pkg.SvoError):
+        small.frontend_download(None)  # nothing to deliver
+    small.close()
+    ctx.close()
