@@ -86,7 +86,7 @@ __device__ __forceinline__ void score_pixel(const uint8_t* pix, int PW, int sx0,
 // rows warp, warp+8, ...; pre-test survivors are appended to the warp's queue (slot = prefix over lanes from 3 ballots of
 // the per-lane survivor count) and scored 32 at a time, so the exact score always runs on (almost) full warps.
 __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0, int sy0, int sw, int sh, int thr, uint8_t* sc,
-                                             int SW, uint32_t* nz, int NWB, uint32_t* wq) {
+                                             int SW, uint32_t* nz, int NWB, uint32_t* wq, uint32_t* tail_q) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t8 = (thr + 1) >> 1;
     const uint32_t K = (uint32_t)(0x80 - t8) * 0x01010101u;
@@ -133,7 +133,18 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
             }
         }
     }
-    if (lane < qn) score_pixel(pix, PW, sx0, sy0, wq[lane], thr, sc, SW, nz, NWB);
+    // leftovers (< 32 per warp) are pooled in the first warp's queue area and scored by full warps after a barrier
+    int* tail_n = reinterpret_cast<int*>(tail_q);
+    uint32_t* tail = tail_q + 4;
+    if (qn) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(tail_n, qn);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (lane < qn) tail[base + lane] = wq[lane];
+    }
+    __syncthreads();
+    const int tn = *tail_n;
+    for (int i = threadIdx.x; i < tn; i += FT) score_pixel(pix, PW, sx0, sy0, tail[i], thr, sc, SW, nz, NWB);
 }
 
 // bits [x0, x0 + n) (n <= 64) of a bitmap row
@@ -157,7 +168,7 @@ struct FastSmem {
     __host__ __device__ size_t nz_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
     __host__ __device__ size_t cell_off() const { return nz_off() + (((size_t)NWB * SH * 4 + 15) & ~(size_t)15); }
     __host__ __device__ size_t queue_off() const { return cell_off() + (size_t)(3 * MC + 4) * sizeof(int); }
-    __host__ __device__ size_t total() const { return queue_off() + (size_t)FW * QCAP * sizeof(uint32_t); }
+    __host__ __device__ size_t total() const { return queue_off() + (size_t)(FW * QCAP + 4 + FW * 32) * sizeof(uint32_t); }
 };
 
 __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const FastTile* __restrict__ tiles, FastSmem L,
@@ -186,10 +197,11 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
         const int nz16 = (int)((L.cell_off() - L.sc_off()) >> 4);
         for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
         for (int i = threadIdx.x; i < 3 * L.MC + 4; i += FT) cellflag[i] = 0;
+        if (threadIdx.x == 0) queues[FW * QCAP] = 0;
     }
     __syncthreads();
 
-    score_region(pix, L.PW, t.x0 - xa, 3, tw, th, g.minTh, sc, L.SW, nz, L.NWB, queues + warp * QCAP);
+    score_region(pix, L.PW, t.x0 - xa, 3, tw, th, g.minTh, sc, L.SW, nz, L.NWB, queues + warp * QCAP, queues + FW * QCAP);
     __syncthreads();
 
     // ---- one thread per (cell, row): non-maximum suppression clipped to the cell, per-cell threshold statistics
@@ -328,7 +340,7 @@ struct FullSmem {
     __host__ __device__ size_t nz_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
     __host__ __device__ size_t item_off() const { return nz_off() + (((size_t)NWB * SH * 4 + 15) & ~(size_t)15); }
     __host__ __device__ size_t queue_off() const { return item_off() + (size_t)(2 * NI + 16) * sizeof(int); }
-    __host__ __device__ size_t total() const { return queue_off() + (size_t)FW * QCAP * sizeof(uint32_t); }
+    __host__ __device__ size_t total() const { return queue_off() + (size_t)(FW * QCAP + 4 + FW * 32) * sizeof(uint32_t); }
 };
 
 __device__ int block_scan_excl_ft(int* a, int n, int* wtmp) {  // in-place exclusive scan, all FT threads call
@@ -385,11 +397,12 @@ __global__ void __launch_bounds__(FT) k_fast_full(LevelGeom G, SlotMap map, cons
         uint4* z = reinterpret_cast<uint4*>(sc);
         const int nz16 = (int)((L.item_off() - L.sc_off()) >> 4);
         for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) queues[FW * QCAP] = 0;
     }
     __syncthreads();
     // map row of image row y is y - (t.y0 - 1); the score stage writes row (y - ys0) + 1, hence the shift
     const int shift = ys0 - t.y0;
-    score_region(pix, L.PW, t.x0 - xa, 3, tw, nsr, thr, sc + shift * L.SW, L.SW, nz + shift * L.NWB, L.NWB, queues + warp * QCAP);
+    score_region(pix, L.PW, t.x0 - xa, 3, tw, nsr, thr, sc + shift * L.SW, L.SW, nz + shift * L.NWB, L.NWB, queues + warp * QCAP, queues + FW * QCAP);
     __syncthreads();
     // ---- one thread per bitmap word of the strip's own rows: 3x3 non-maximum suppression
     const int nck = (tw + 31) >> 5, ni = th * nck;

@@ -280,17 +280,24 @@ __global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_k
             weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
             int jp[22];
             load_column<22>(J, G, inx - 1 + min(lane, 23), iny, inx - 1 >= 0 && inx + 22 < G.w && iny >= 0 && iny + 21 < G.h, jp);
-            int b1 = 0, b2 = 0;
-            int top = jp[0], topn = __shfl_down_sync(0xFFFFFFFFu, top, 1);
+            // neighbour column of every row first (22 independent shuffles), then two accumulator pairs: short dependency chains
+            int jn[22];
+#pragma unroll
+            for (int r = 0; r < 22; ++r) jn[r] = __shfl_down_sync(0xFFFFFFFFu, jp[r], 1);
+            int b1 = 0, b2 = 0, b1o = 0, b2o = 0;
 #pragma unroll
             for (int y = 0; y < WIN; ++y) {
-                const int bot = jp[y + 1], botn = __shfl_down_sync(0xFFFFFFFFu, bot, 1);
-                const int diff = descale(top * iw00 + topn * iw01 + bot * iw10 + botn * iw11, 9) - Iw[y];
-                b1 += diff * Ixw[y];
-                b2 += diff * Iyw[y];
-                top = bot;
-                topn = botn;
+                const int diff = descale(jp[y] * iw00 + jn[y] * iw01 + jp[y + 1] * iw10 + jn[y + 1] * iw11, 9) - Iw[y];
+                if (y & 1) {
+                    b1o += diff * Ixw[y];
+                    b2o += diff * Iyw[y];
+                } else {
+                    b1 += diff * Ixw[y];
+                    b2 += diff * Iyw[y];
+                }
             }
+            b1 += b1o;
+            b2 += b2o;
             const long long sb1 = warp_sum64(wlane ? b1 : 0), sb2 = warp_sum64(wlane ? b2 : 0);
             const float b1f = __fmul_rn((float)sb1, FLT_SCALE), b2f = __fmul_rn((float)sb2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2f), __fmul_rn(A22, b1f)), D);
