@@ -8,6 +8,8 @@
 // never read on this path and is not materialised (it is produced on the host only when mvImagePyramid is asked for).
 //
 // Roofline: HBM-bound streaming.  Algorithmic bytes per image = read L(l-1) + write L(l) summed over l = 1..7.
+#include <cuda.h>
+
 #include "svo_common.cuh"
 
 namespace {
@@ -108,6 +110,114 @@ __global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ lef
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K1 fused: all pyramid levels of one tile in ONE pass.  The level-0 region of the tile is staged in shared
+// memory by TMA (one cp.async.bulk.tensor.2d per CTA, completion on an mbarrier); level l is then computed from level l-1
+// entirely in shared memory (ping-pong between two buffers) and only the pixels the tile owns are written to HBM, so level
+// 0 is read once and levels 1..7 are written once.  Arithmetic is identical to k_resize_level (IDP.2A horizontal pass).
+// Thread layout per level: thread = (4-pixel group g, row lane), groups aligned to 4 in the level's x coordinate so that
+// shared-memory and HBM stores are aligned words; a thread keeps its column coefficients in registers and walks the rows.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ CUtensorMap tmap, PyrGeom g, SlotMap map,
+                                                       const PyrTile* __restrict__ tiles, int bufB_off) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int slot = map.slot(blockIdx.y);
+    const PyrTile& T = tiles[blockIdx.x];
+    uint8_t* bufA = smem;             // level-0 box (SVO_PYR_BOX_H x SVO_PYR_BOX_W), later the even levels
+    uint8_t* bufB = smem + bufB_off;  // odd levels
+    const PyrRect r0 = T.lv[0];
+    if (r0.x1n <= r0.x0) return;  // empty tile (CTA-uniform)
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(SVO_PYR_BOX_W * SVO_PYR_BOX_H) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(bufA)),
+                     "l"(&tmap), "r"((int)r0.x0 & ~15), "r"(slot * g.lvl[0].h + (int)r0.y0), "r"(smem_u32(&mbar))
+                     : "memory");
+    }
+    {  // every thread waits for the TMA bytes (phase 0)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+        }
+    }
+
+    const uint8_t* src = bufA;
+    int s_orgx = r0.x0 & ~15, s_orgy = r0.y0, s_pitch = SVO_PYR_BOX_W;  // the box starts at a 16-byte aligned column
+    for (int l = 1; l < g.nlevels; ++l) {
+        const LevelGeom& D = g.lvl[l];
+        const PyrRect r = T.lv[l];
+        const int nw = r.x1n - r.x0, nh = r.y1n - r.y0;
+        if (nw <= 0 || nh <= 0) break;  // deeper levels of this tile are empty too (CTA-uniform)
+        uint8_t* dbuf = (l & 1) ? bufB : bufA;
+        const int d_orgx = r.x0 & ~3;
+        const int ng = (r.x1n - d_orgx + 3) >> 2;             // 4-pixel groups
+        const int d_pitch = ng * 4 + 8;
+        const int nrl = 256 / ng;                             // row lanes
+        const int gi = threadIdx.x % ng, rl = threadIdx.x / ng;
+        if (rl < nrl) {
+            const int gx = d_orgx + 4 * gi;                   // level x of the group's first pixel
+            // column coefficients of the 4 pixels (tables are padded to a multiple of 4 entries)
+            const int4 xo = *reinterpret_cast<const int4*>(D.xofs + gx);
+            const int4 alv = *reinterpret_cast<const int4*>(D.alpha + 2 * gx);
+            const uint32_t al[4] = {(uint32_t)alv.x, (uint32_t)alv.y, (uint32_t)alv.z, (uint32_t)alv.w};
+            const int sxs[4] = {xo.x, xo.y, xo.z, xo.w};
+            unsigned woff[4], sh[4];
+            bool valid[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                valid[i] = gx + i >= r.x0 && gx + i < r.x1n;
+                const int rel = valid[i] ? sxs[i] - s_orgx : 0;
+                woff[i] = (unsigned)rel & ~3u;
+                sh[i] = ((unsigned)rel & 3u) * 8u;
+            }
+            const bool own_full = gx >= r.x0 && gx + 4 <= r.x1o;
+            uint8_t* gdst = D.base + (size_t)slot * D.plane + gx;
+            for (int y = r.y0 + rl; y < r.y1n; y += nrl) {
+                const int2 yo = *reinterpret_cast<const int2*>(D.yofs + 2 * y);
+                const int bt = *reinterpret_cast<const int*>(D.beta + 2 * y);
+                const int b0 = (short)(bt & 0xFFFF), b1 = (short)(bt >> 16);
+                const uint8_t* row0 = src + (yo.x - s_orgy) * s_pitch;
+                const uint8_t* row1 = src + (yo.y - s_orgy) * s_pitch;
+                uint32_t out = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!valid[i]) continue;
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(row0 + woff[i]), a1 = *reinterpret_cast<const uint32_t*>(row0 + woff[i] + 4);
+                    const uint32_t c0 = *reinterpret_cast<const uint32_t*>(row1 + woff[i]), c1 = *reinterpret_cast<const uint32_t*>(row1 + woff[i] + 4);
+                    const int t0 = (int)__dp2a_lo(al[i], __funnelshift_r(a0, a1, sh[i]), 0u);
+                    const int t1 = (int)__dp2a_lo(al[i], __funnelshift_r(c0, c1, sh[i]), 0u);
+                    const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;  // always in [0, 255]
+                    out |= (uint32_t)v << (8 * i);
+                }
+                *reinterpret_cast<uint32_t*>(dbuf + (y - r.y0) * d_pitch + 4 * gi) = out;
+                if (y < r.y1o) {
+                    uint8_t* p = gdst + (size_t)y * D.pitch;
+                    if (own_full) {
+                        *reinterpret_cast<uint32_t*>(p) = out;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (gx + i >= r.x0 && gx + i < r.x1o) p[i] = (uint8_t)(out >> (8 * i));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        src = dbuf;
+        s_orgx = d_orgx;
+        s_orgy = r.y0;
+        s_pitch = d_pitch;
+    }
+}
+
 }  // namespace
 
 int launch_repitch(svo_ctx* c, const uint8_t* left, const uint8_t* right, size_t stride, int first, int ring, int n_frames) {
@@ -122,6 +232,16 @@ int launch_repitch(svo_ctx* c, const uint8_t* left, const uint8_t* right, size_t
 int launch_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
     StageTimer t(c, 0);
     const PyrGeom& g = c->geom;
+    if (c->fused_pyr) {
+        const int bufA = SVO_PYR_BOX_W * SVO_PYR_BOX_H;
+        const size_t smem = (size_t)bufA + c->pyr_bufB_bytes;
+        SVO_CUDA_TRY(c, cudaFuncSetAttribute(k_pyramid_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(c->n_ptiles, n_img);
+        k_pyramid_fused<<<grid, 256, smem, c->stream>>>(*reinterpret_cast<const CUtensorMap*>(c->tmap_l0), g, map, c->d_ptiles, bufA);
+        ++c->launches;
+        SVO_CUDA_TRY(c, cudaGetLastError());
+        return SVO_OK;
+    }
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& S = g.lvl[l - 1];
         const LevelGeom& D = g.lvl[l];

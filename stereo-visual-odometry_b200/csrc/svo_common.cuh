@@ -52,6 +52,18 @@ struct PyrGeom {
     LevelGeom lvl[SVO_MAX_LEVELS];
 };
 
+// One tile of the one-pass pyramid (K1 fused): for every level the pixels this CTA OWNS (writes to HBM) and the slightly
+// larger region it NEEDS in shared memory as the source of the next level.  lv[0] is the level-0 region to stage (TMA box).
+struct PyrRect {
+    short x0, x1o, x1n;  // owned [x0, x1o), needed [x0, x1n)
+    short y0, y1o, y1n;
+};
+struct PyrTile {
+    PyrRect lv[SVO_MAX_LEVELS];
+};
+#define SVO_PYR_BOX_W 256  // TMA box of the staged level-0 region (bytes x rows); boxDim <= 256 per dimension
+#define SVO_PYR_BOX_H 96
+
 // One FAST tile = one cell row x a run of cells of one level (K2), or a full-width strip of rows (K9).
 struct FastTile {
     short level, cell_i;
@@ -110,6 +122,14 @@ struct svo_ctx {
     uint32_t tile_buf_per_slot = 0, cand_per_slot = 0, lkp_per_slot = 0;
     int kp_cap = 0;
     int octree_ncap = 0;
+
+    // ---- one-pass pyramid (K1 fused): tiles, TMA descriptor of level 0, shared-memory budget
+    bool fused_pyr = false;
+    std::vector<PyrTile> ptiles;
+    PyrTile* d_ptiles = nullptr;
+    int n_ptiles = 0;
+    int pyr_bufB_bytes = 0;
+    alignas(64) unsigned char tmap_l0[128] = {};  // CUtensorMap
 
     // ---- device memory
     uint8_t* d_pyr = nullptr;  // all levels, all slots

@@ -7,7 +7,10 @@
 //                         coefficient tables cv::resize builds once per call
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+
+#include <cuda.h>
 
 #include "svo_common.cuh"
 
@@ -51,7 +54,8 @@ static void free_layout(svo_ctx* c) {
                      (void**)&c->d_flags,    (void**)&c->d_tiles,    (void**)&c->d_lkpyr,    (void**)&c->d_ftiles,
                      (void**)&c->d_ftile_buf, (void**)&c->d_ftile_cnt, (void**)&c->d_fast_kps, (void**)&c->d_nfast,
                      (void**)&c->d_lk_pts,   (void**)&c->d_lk_status, (void**)&c->d_lk_err,   (void**)&c->d_match,
-                     (void**)&c->d_orb_pts,  (void**)&c->d_norb,      (void**)&c->d_lkf_pts,  (void**)&c->d_nlkf};
+                     (void**)&c->d_orb_pts,  (void**)&c->d_norb,      (void**)&c->d_lkf_pts,  (void**)&c->d_nlkf,
+                     (void**)&c->d_ptiles};
     for (void** p : ptrs) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -333,6 +337,113 @@ int svo_layout(svo_ctx* c, int w, int h) {
             g.lvl[l].alpha = (const short*)((uint8_t*)c->d_tables + off_a[l]);
             g.lvl[l].yofs = (const int*)((uint8_t*)c->d_tables + off_y[l]);
             g.lvl[l].beta = (const short*)((uint8_t*)c->d_tables + off_b[l]);
+        }
+    }
+
+    // ---- one-pass pyramid tiling (K1 fused).  Ownership: a level-l pixel belongs to the tile that owns its top-left source
+    // tap at level l-1, so only the +1 taps (right / bottom) fall outside the owned source region; the region a tile NEEDS at
+    // level l-1 is its owned region plus that small right/bottom fringe, computed redundantly by the neighbours.
+    c->fused_pyr = false;
+    c->ptiles.clear();
+    if (L >= 2 && !getenv("SVO_PYRAMID_PER_LEVEL")) {
+        std::vector<std::vector<int>> hx(L), hy(L);  // host copies of the left / top tap index per destination pixel
+        bool ok = true;
+        for (int l = 1; l < L && ok; ++l) {
+            const int sw = g.lvl[l - 1].w, sh = g.lvl[l - 1].h, dw = g.lvl[l].w, dh = g.lvl[l].h;
+            if (sw == 2 * dw && sh == 2 * dh) ok = false;  // INTER_AREA case: per-level kernels only
+            const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+            hx[l].resize(dw);
+            hy[l].resize(dh);
+            for (int dx = 0; dx < dw; ++dx) {
+                int sx = (int)std::floor((float)((dx + 0.5) * scale_x - 0.5));
+                hx[l][dx] = std::min(std::max(sx, 0), sw - 1);
+            }
+            for (int dy = 0; dy < dh; ++dy) {
+                int sy = (int)std::floor((float)((dy + 0.5) * scale_y - 0.5));
+                hy[l][dy] = std::min(std::max(sy, 0), sh - 1);
+            }
+            // the scheme needs monotone taps that start at 0 (down-scaling)
+            if (hx[l][0] != 0 || hy[l][0] != 0) ok = false;
+        }
+        auto first_ge = [](const std::vector<int>& v, int val) { return (int)(std::lower_bound(v.begin(), v.end(), val) - v.begin()); };
+        for (int TW = 192, TH = 64; ok && c->ptiles.empty(); ) {
+            std::vector<PyrTile> tiles;
+            bool fits = true;
+            int maxB = 0;
+            const int w1 = g.lvl[1].w, h1 = g.lvl[1].h;
+            for (int ty = 0; ty * TH < h1 && fits; ++ty)
+                for (int tx = 0; tx * TW < w1 && fits; ++tx) {
+                    PyrTile t;
+                    std::memset(&t, 0, sizeof(t));
+                    int ox0 = tx * TW, ox1 = std::min(ox0 + TW, w1), oy0 = ty * TH, oy1 = std::min(oy0 + TH, h1);
+                    t.lv[1] = PyrRect{(short)ox0, (short)ox1, (short)ox1, (short)oy0, (short)oy1, (short)oy1};
+                    for (int l = 2; l < L; ++l) {
+                        const PyrRect& p = t.lv[l - 1];
+                        const int x0 = first_ge(hx[l], p.x0), x1 = first_ge(hx[l], p.x1o), y0 = first_ge(hy[l], p.y0), y1 = first_ge(hy[l], p.y1o);
+                        t.lv[l] = PyrRect{(short)x0, (short)x1, (short)x1, (short)y0, (short)y1, (short)y1};
+                    }
+                    for (int l = L - 1; l >= 1; --l) {  // needed regions, deepest level first
+                        const PyrRect& d = t.lv[l];
+                        const bool empty = d.x1n <= d.x0 || d.y1n <= d.y0;
+                        if (l == 1) {
+                            PyrRect& s0 = t.lv[0];
+                            if (empty) { s0 = PyrRect{0, 0, 0, 0, 0, 0}; break; }
+                            s0.x0 = (short)hx[1][d.x0];
+                            s0.y0 = (short)hy[1][d.y0];
+                            s0.x1o = s0.x1n = (short)std::min(hx[1][d.x1n - 1] + 2, g.lvl[0].w);
+                            s0.y1o = s0.y1n = (short)std::min(hy[1][d.y1n - 1] + 2, g.lvl[0].h);
+                            // the TMA box starts at a 16-byte aligned column (hardware requirement for 1-byte elements)
+                            if (s0.x1n - (s0.x0 & ~15) > SVO_PYR_BOX_W || s0.y1n - s0.y0 > SVO_PYR_BOX_H) fits = false;
+                        } else if (!empty) {
+                            PyrRect& sr = t.lv[l - 1];
+                            sr.x1n = (short)std::max<int>(sr.x1n, std::min(hx[l][d.x1n - 1] + 2, g.lvl[l - 1].w));
+                            sr.y1n = (short)std::max<int>(sr.y1n, std::min(hy[l][d.y1n - 1] + 2, g.lvl[l - 1].h));
+                            if (hx[l][d.x0] < sr.x0 || hy[l][d.y0] < sr.y0) fits = false;  // cannot happen by construction
+                        }
+                    }
+                    for (int l = 1; l < L; l += 2) {  // odd levels live in buffer B
+                        const PyrRect& r = t.lv[l];
+                        const int pw = (int)svo_align(r.x1n - (r.x0 & ~3), 4) + 8;
+                        maxB = std::max(maxB, pw * std::max(0, r.y1n - r.y0));
+                    }
+                    for (int l = 2; l < L; l += 2) {  // even levels reuse buffer A (the level-0 box)
+                        const PyrRect& r = t.lv[l];
+                        const int pw = (int)svo_align(r.x1n - (r.x0 & ~3), 4) + 8;
+                        if (pw * std::max(0, r.y1n - r.y0) > SVO_PYR_BOX_W * SVO_PYR_BOX_H) fits = false;
+                    }
+                    tiles.push_back(t);
+                }
+            if (fits) {
+                c->ptiles = tiles;
+                c->pyr_bufB_bytes = (int)svo_align(maxB + 16, 128);
+            } else if (TW > 64) {
+                TW -= 32;
+                TH = std::max(32, TH - 8);
+            } else {
+                ok = false;
+            }
+        }
+        if (ok && !c->ptiles.empty()) {
+            // TMA descriptor: level 0 of all slots as one 2-D u8 tensor [max_images * h0 rows][pitch0 cols]
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) {
+                const cuuint64_t dims[2] = {(cuuint64_t)g.lvl[0].pitch, (cuuint64_t)g.lvl[0].h * (cuuint64_t)S};
+                const cuuint64_t strides[1] = {(cuuint64_t)g.lvl[0].pitch};
+                const cuuint32_t box[2] = {SVO_PYR_BOX_W, SVO_PYR_BOX_H};
+                const cuuint32_t estr[2] = {1, 1};
+                const CUresult r = ((EncodeFn)fn)(reinterpret_cast<CUtensorMap*>(c->tmap_l0), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, g.lvl[0].base, dims, strides,
+                                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r == CUDA_SUCCESS) {
+                    c->n_ptiles = (int)c->ptiles.size();
+                    SVO_CUDA_TRY(c, cudaMalloc(&c->d_ptiles, sizeof(PyrTile) * c->n_ptiles));
+                    SVO_CUDA_TRY(c, cudaMemcpy(c->d_ptiles, c->ptiles.data(), sizeof(PyrTile) * c->n_ptiles, cudaMemcpyHostToDevice));
+                    c->fused_pyr = true;
+                }
+            }
         }
     }
 
