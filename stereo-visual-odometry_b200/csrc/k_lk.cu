@@ -127,8 +127,10 @@ __device__ __forceinline__ void load_column(const uint8_t* __restrict__ img, con
 // lane x + 1.  Everything is register-resident: the lane walks down its column (sliding 3-row window for the Scharr
 // gradient), horizontal neighbours come from warp shuffles, and the interpolated window (I, Ix, Iy of 21 rows) stays in
 // registers for the Gauss-Newton iterations.  No shared memory, no derivative image.
-__global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
+__global__ void __launch_bounds__(LW * 32, 3) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
                                                       float* __restrict__ lk_pts, uint8_t* __restrict__ lk_status, float* __restrict__ lk_err) {
+    __shared__ short s_Iw[LW][WIN * 32];
+    __shared__ uint32_t s_G[LW][WIN * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     if (f == 0 && P.skip_first) return;
@@ -187,8 +189,9 @@ __global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_k
         weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
 
         // ---- previous image: column X = ipx - 1 + lane, rows ipy - 1 .. ipy + 22 (REFLECT_101 outside the image)
-        short Iw[WIN];
-        int Ixw[WIN], Iyw[WIN];
+        // the interpolated window lives in shared memory (lane-major, conflict-free): keeps the kernel at 3 CTAs / SM
+        short* Iw = s_Iw[warp] + lane;      // Iw[y * 32]
+        uint32_t* Gw = s_G[warp] + lane;    // (Ix, Iy) int16 pair at Gw[y * 32]
         int a11 = 0, a12 = 0, a22 = 0;
         const bool inside = ipx - 1 >= 0 && ipx + 22 < G.w && ipy - 1 >= 0 && ipy + 22 < G.h;  // warp-uniform
         if (inside) {
@@ -213,9 +216,8 @@ __global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_k
                 const int ixn = __shfl_down_sync(0xFFFFFFFFu, Vb, 1) - __shfl_up_sync(0xFFFFFFFFu, Vb, 1);
                 const int iyn = 3 * (__shfl_up_sync(0xFFFFFFFFu, Db, 1) + __shfl_down_sync(0xFFFFFFFFu, Db, 1)) + 10 * Db;
                 const int ixv = descale(ixn, 14), iyv = descale(iyn, 14);
-                Iw[y] = (short)descale(ib1, 9);
-                Ixw[y] = ixv;
-                Iyw[y] = iyv;
+                Iw[y * 32] = (short)descale(ib1, 9);
+                Gw[y * 32] = ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16);
                 a11 += ixv * ixv;
                 a12 += ixv * iyv;
                 a22 += iyv * iyv;
@@ -245,9 +247,8 @@ __global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_k
                     const int ival = descale(tp * iw00 + tpn * iw01 + p * iw10 + pn * iw11, 9);
                     const int ixv = descale(tgx * iw00 + tgxn * iw01 + gx * iw10 + gxn * iw11, 14);
                     const int iyv = descale(tgy * iw00 + tgyn * iw01 + gy * iw10 + gyn * iw11, 14);
-                    Iw[r - 1] = (short)ival;
-                    Ixw[r - 1] = ixv;
-                    Iyw[r - 1] = iyv;
+                    Iw[(r - 1) * 32] = (short)ival;
+                    Gw[(r - 1) * 32] = ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16);
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
@@ -287,13 +288,15 @@ __global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_k
             int b1 = 0, b2 = 0, b1o = 0, b2o = 0;
 #pragma unroll
             for (int y = 0; y < WIN; ++y) {
-                const int diff = descale(jp[y] * iw00 + jn[y] * iw01 + jp[y + 1] * iw10 + jn[y + 1] * iw11, 9) - Iw[y];
+                const int diff = descale(jp[y] * iw00 + jn[y] * iw01 + jp[y + 1] * iw10 + jn[y + 1] * iw11, 9) - Iw[y * 32];
+                const uint32_t gw = Gw[y * 32];
+                const int gxv = (int)(short)(gw & 0xFFFFu), gyv = (int)gw >> 16;
                 if (y & 1) {
-                    b1o += diff * Ixw[y];
-                    b2o += diff * Iyw[y];
+                    b1o += diff * gxv;
+                    b2o += diff * gyv;
                 } else {
-                    b1 += diff * Ixw[y];
-                    b2 += diff * Iyw[y];
+                    b1 += diff * gxv;
+                    b2 += diff * gyv;
                 }
             }
             b1 += b1o;
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(LW * 32, 2) k_lk_track(LkParams P, const svo_k
 #pragma unroll
                 for (int y = 0; y < WIN; ++y) {
                     const int bot = __ldg(col + (size_t)reflect101(iny + y + 1, G.h) * G.pitch), botn = __shfl_down_sync(0xFFFFFFFFu, bot, 1);
-                    e += abs(descale(top * iw00 + topn * iw01 + bot * iw10 + botn * iw11, 9) - Iw[y]);
+                    e += abs(descale(top * iw00 + topn * iw01 + bot * iw10 + botn * iw11, 9) - Iw[y * 32]);
                     top = bot;
                     topn = botn;
                 }
