@@ -95,12 +95,13 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
         const bool interior = x0 >= 0 && y0 >= 0 && x0 + PS <= G.w && y0 + PS <= G.h;  // warp-uniform
         const int c1 = lane + 32;                                                        // second column of this lane (< 43 for lanes < 11)
         if (interior) {
-            const uint8_t* p = img + (size_t)y0 * G.pitch + x0;
-#pragma unroll 4
-            for (int r = 0; r < PS; ++r) {
-                patch[r * PP + lane] = __ldg(p + lane);
-                if (c1 < PS) patch[r * PP + c1] = __ldg(p + c1);
-                p += G.pitch;
+            // word-wise: smem word j of row r = image bytes x0 + 4j .. x0 + 4j + 3, cut out of two aligned global words
+            const uint8_t* p = img + (size_t)y0 * G.pitch + (x0 & ~3);
+            const unsigned sh = (unsigned)(x0 & 3) * 8u;
+            for (int it = lane; it < PS * 11; it += 32) {
+                const int r = it / 11, j = it - r * 11;
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(p + (size_t)r * G.pitch) + j;
+                reinterpret_cast<uint32_t*>(patch + r * PP)[j] = __funnelshift_r(__ldg(w), __ldg(w + 1), sh);
             }
         } else {
             const int xa = reflect101(x0 + lane, G.w), xb = reflect101(x0 + min(c1, PS - 1), G.w);
@@ -110,9 +111,7 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
                 if (c1 < PS) patch[r * PP + c1] = __ldg(p + xb);
             }
         }
-        if (lane < PP - PS) {  // zero the 5 padding columns the word-wise horizontal pass touches
-            for (int r = 0; r < PS; ++r) patch[r * PP + PS + lane] = 0;
-        }
+        // columns 43..47 of the patch are never initialised: they only feed horizontal outputs 37..39, which nothing samples
     }
     __syncwarp();
 
