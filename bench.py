@@ -216,7 +216,8 @@ def run_b200(a):
         achieved = bpi * 2 * B / (t_pf * 1e-3) / 1e9 if t_pf > 0 else None
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pyramid_fast_dram_bytes_per_step")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get("pyramid_fast_dram_bytes_per_step") * (2 * B) / tj.get("images_per_step", 128)  # measured per image, scaled to this launch
         except Exception:
             pass
         line = {
@@ -229,7 +230,7 @@ def run_b200(a):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                          "traffic": traffic, "peak_source": peak_src + " (of measured)" if "hbm_gbs" in peaks else peak_src,
-                         "kernels": "K1 k_resize_level x7 + K2 k_fast_cells + K2b k_compact (pyramid + FAST stages)",
+                         "kernels": "K1 k_pyramid_fused (one-pass, TMA-staged) + K2 k_fast_cells + K2b k_compact (pyramid + FAST stages)",
                          "algorithmic_bytes_per_launch": bpi * 2 * B, "ms_per_launch": t_pf},
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage.items()},
             "cpu_baseline": cpu_baseline,
