@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SVO_ABI_VERSION 2
+#define SVO_ABI_VERSION 3
 
 typedef enum svo_status {
     SVO_OK = 0,
@@ -112,6 +112,14 @@ int svo_lk_track(svo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, 
                  const float* prev_xy, int n, float* next_xy, uint8_t* status, float* err, int win, int max_level,
                  int max_iter, double eps, double min_eig);
 
+/* ---- triangulation ------------------------------------------------------------------------------------------- */
+/* Replaces cv::triangulatePoints(P1, P2, pts1, pts2, points4D) + cv::convertPointsFromHomogeneous (tracking.cpp:190-192,
+ * 292-294).  proj1/proj2: 3x4 row-major doubles; pts: n x 2 floats; points4d (may be NULL): n x 4 floats (column i of
+ * OpenCV's 4 x n result); points3d: n x 3 floats.  Agreement with OpenCV: sign of the 4-vector is arbitrary, 3-D points
+ * match to float rounding. */
+int svo_triangulate_points(svo_ctx* ctx, const double* proj1, const double* proj2, const float* pts1, const float* pts2,
+                           int n, float* points4d, float* points3d);
+
 /* ---- throughput mode: batches of consecutive stereo frames ------------------------------------------------------ */
 /* One unit of work = one new stereo frame t:
  *   SVO_MODE_ORB: operator() on left_t and right_t (Detect_MyORBFeatures, tracking.cpp:502-532), then
@@ -158,12 +166,19 @@ typedef struct svo_frontend_out {
     float* lkf_t2_right;
     float* lkf_t2_left;
     int32_t* n_lk_matched;  /* per frame: number of surviving tracks */
+    /* cv::triangulatePoints + convertPointsFromHomogeneous of (t1_left, t1_right) (tracking.cpp:190-192, 292-294); filled only
+     * after svo_frontend_set_projection(); 3 floats per point */
+    float* orb_points3d;    /* kp_cap*3 floats per frame, n_orb_matched valid */
+    float* lk_points3d;     /* pt_cap*3 floats per frame, n_lk_matched valid */
 } svo_frontend_out;
 
 int svo_frontend_configure(svo_ctx* ctx, int w, int h, int mode, int max_frames);
 int svo_frontend_reset(svo_ctx* ctx);
 /* Tracking::feature_match_error_ (parameter.cpp:53, config/default.yaml:66; default 3) used by the device-side post-filters */
 int svo_frontend_set_match_error(svo_ctx* ctx, double feature_match_error);
+/* Sensors::projMatr1_ / projMatr2_ (3x4, row-major doubles; sensors.cpp:8-24): enables the device-side triangulation of
+ * the filtered lists.  Call after svo_frontend_configure(). */
+int svo_frontend_set_projection(svo_ctx* ctx, const double* proj_left, const double* proj_right);
 /* host images -> device (left/right: n_frames contiguous images of h rows, `stride` bytes per row) */
 int svo_frontend_upload(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride);
 /* same, but left/right are DEVICE pointers (images already resident in HBM, e.g. written by a decoder or a torch tensor) */

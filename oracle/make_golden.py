@@ -58,6 +58,19 @@ def main():
     for name, (a, b) in {"lk_stereo": (l0, r0), "lk_temporal": (l0, l1)}.items():
         p, st, err = cv2.calcOpticalFlowPyrLK(a, b, pts.reshape(-1, 1, 2), None, **lk)
         out[name + "_pts"], out[name + "_status"], out[name + "_err"] = p.reshape(-1, 2), st.ravel(), err.ravel()
+    # cv::triangulatePoints + convertPointsFromHomogeneous with KITTI-00-like projection matrices (sensors.cpp:8-24)
+    P1 = np.array([[718.856, 0, 607.1928, 0], [0, 718.856, 185.2157, 0], [0, 0, 1, 0]], np.float64)
+    P2 = P1.copy()
+    P2[0, 3] = -386.1448
+    xl = rng.uniform(20, 1220, 400).astype(np.float32)
+    yl = rng.uniform(20, 356, 400).astype(np.float32)
+    disp = rng.uniform(1.5, 90, 400).astype(np.float32)
+    t1 = np.stack([xl, yl], 1)
+    t2 = np.stack([xl - disp, yl + rng.uniform(-1.5, 1.5, 400).astype(np.float32)], 1)
+    p4 = cv2.triangulatePoints(P1, P2, t1.T.copy(), t2.T.copy())
+    p3 = cv2.convertPointsFromHomogeneous(p4.T.copy()).reshape(-1, 3)
+    out["tri_P1"], out["tri_P2"], out["tri_pts1"], out["tri_pts2"] = P1, P2, t1, t2
+    out["tri_points4d"], out["tri_points3d"] = p4.T.astype(np.float32).copy(), p3.astype(np.float32)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     path = os.path.join(ROOT, "tests", "golden", "cv2_primitives.npz")
     np.savez_compressed(path, **out)

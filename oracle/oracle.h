@@ -102,4 +102,8 @@ int lk_chain_filter(int n, const float* p0, const float* p1, const float* p2, co
                     const uint8_t* s0, const uint8_t* s1, const uint8_t* s2, const uint8_t* s3, double feature_match_error,
                     uint8_t* keep);
 
+// cv::triangulatePoints + cv::convertPointsFromHomogeneous (tracking.cpp:190-192, 292-294).  P1, P2: 3x4 row-major; out4: n x 4
+// (unit right singular vector of the smallest singular value, sign arbitrary), out3: n x 3 (float division like OpenCV).
+void triangulate_points(const double* P1, const double* P2, const float* pts1, const float* pts2, int n, float* out4, float* out3);
+
 }  // namespace orc

@@ -142,6 +142,10 @@ int orc_lk_chain_filter(int n, const float* p0, const float* p1, const float* p2
     return lk_chain_filter(n, p0, p1, p2, p3, p0r, s0, s1, s2, s3, fme, keep);
 }
 
+void orc_triangulate_points(const double* P1, const double* P2, const float* pts1, const float* pts2, int n, float* out4, float* out3) {
+    triangulate_points(P1, P2, pts1, pts2, n, out4, out3);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Whole front-end over a sequence, for the CPU baseline ("port"): per frame t: ORB on L_t and R_t, match(L_{t-1},R_{t-1}),
 // match(L_{t-1},L_t); FAST on L_t and the 4-call LK chain over (t-1, t).  Frames are split over `threads` workers in

@@ -430,4 +430,64 @@ void calc_optical_flow_pyr_lk(const Image& prev, const Image& next, const float*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cv::triangulatePoints (calib3d): per point, SVD of the 4x4 matrix with rows x*P[2]-P[0], y*P[2]-P[1] for both views, take
+// the right singular vector of the smallest singular value (double), store as float; convertPointsFromHomogeneous then
+// scales X, Y, Z by 1.f / W in float.  One-sided (Hestenes) Jacobi like OpenCV's JacobiSVD.
+// ---------------------------------------------------------------------------------------------------------------
+void triangulate_points(const double* P1, const double* P2, const float* pts1, const float* pts2, int n, float* out4, float* out3) {
+    for (int i = 0; i < n; ++i) {
+        double a[4][4], v[4][4];  // columns
+        const double x1 = pts1[2 * i], y1 = pts1[2 * i + 1], x2 = pts2[2 * i], y2 = pts2[2 * i + 1];
+        for (int k = 0; k < 4; ++k) {
+            a[k][0] = x1 * P1[8 + k] - P1[k];
+            a[k][1] = y1 * P1[8 + k] - P1[4 + k];
+            a[k][2] = x2 * P2[8 + k] - P2[k];
+            a[k][3] = y2 * P2[8 + k] - P2[4 + k];
+            for (int r = 0; r < 4; ++r) v[k][r] = k == r ? 1.0 : 0.0;
+        }
+        const double eps = DBL_EPSILON * 2;
+        for (int sweep = 0; sweep < 30; ++sweep) {
+            bool changed = false;
+            for (int p = 0; p < 3; ++p)
+                for (int q = p + 1; q < 4; ++q) {
+                    double alpha = 0, beta = 0, gamma = 0;
+                    for (int r = 0; r < 4; ++r) {
+                        alpha += a[p][r] * a[p][r];
+                        beta += a[q][r] * a[q][r];
+                        gamma += a[p][r] * a[q][r];
+                    }
+                    if (std::fabs(gamma) <= eps * std::sqrt(alpha * beta)) continue;
+                    changed = true;
+                    const double zeta = (beta - alpha) / (2.0 * gamma);
+                    const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+                    for (int r = 0; r < 4; ++r) {
+                        const double ap = a[p][r], aq = a[q][r];
+                        a[p][r] = c * ap - s * aq;
+                        a[q][r] = s * ap + c * aq;
+                        const double vp = v[p][r], vq = v[q][r];
+                        v[p][r] = c * vp - s * vq;
+                        v[q][r] = s * vp + c * vq;
+                    }
+                }
+            if (!changed) break;
+        }
+        int jmin = 0;
+        double wmin = 1e300;
+        for (int k = 0; k < 4; ++k) {
+            double w = 0;
+            for (int r = 0; r < 4; ++r) w += a[k][r] * a[k][r];
+            if (w < wmin) { wmin = w; jmin = k; }
+        }
+        float h[4];
+        for (int r = 0; r < 4; ++r) h[r] = (float)v[jmin][r];
+        if (out4) for (int r = 0; r < 4; ++r) out4[4 * i + r] = h[r];
+        const float scale = h[3] != 0.f ? 1.f / h[3] : 1.f;
+        out3[3 * i] = h[0] * scale;
+        out3[3 * i + 1] = h[1] * scale;
+        out3[3 * i + 2] = h[2] * scale;
+    }
+}
+
 }  // namespace orc

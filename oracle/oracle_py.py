@@ -215,6 +215,18 @@ def lk_chain_filter(p0, p1, p2, p3, p0r, s0, s1, s2, s3, fme=3.0):
     return keep[:n].astype(bool)
 
 
+def triangulate_points(p1, p2, pts1, pts2):
+    p1 = np.ascontiguousarray(p1, np.float64).reshape(12)
+    p2 = np.ascontiguousarray(p2, np.float64).reshape(12)
+    pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+    pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+    n = len(pts1)
+    o4 = np.zeros((n, 4), np.float32)
+    o3 = np.zeros((n, 3), np.float32)
+    lib().orc_triangulate_points(_p(p1), _p(p2), _p(pts1), _p(pts2), C.c_int(n), _p(o4), _p(o3))
+    return o4, o3
+
+
 def frontend_sequence(left, right, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, mode=3, threads=1):
     left = np.ascontiguousarray(left, np.uint8)
     right = np.ascontiguousarray(right, np.uint8)

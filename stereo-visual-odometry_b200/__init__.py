@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "svo_ctx_launch_count", "svo_ctx_enable_stage_timing", "svo_ctx_set_timing_slot", "svo_ctx_stage_ms", "svo_orb_configure", "svo_orb_tables",
     "svo_orb_capacity", "svo_orb_level_size", "svo_orb_extract", "svo_orb_extract_batch", "svo_orb_read_level",
     "svo_orb_read_candidates", "svo_fast_detect", "svo_match_hamming", "svo_lk_track", "svo_frontend_configure",
-    "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
+    "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_projection", "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
     "svo_synth_stereo_frame",
 ]
 
@@ -48,7 +48,7 @@ class FrontendOut(C.Structure):
         "kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
         "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status",
         "orb_t2_left", "orb_t1_left", "orb_t1_right", "n_orb_matched", "lkf_t1_left", "lkf_t1_right", "lkf_t2_right", "lkf_t2_left",
-        "n_lk_matched")]
+        "n_lk_matched", "orb_points3d", "lk_points3d")]
 
 
 _lib = None
@@ -247,6 +247,23 @@ class Context:
     def frontend_set_match_error(self, fme):
         self._check(self._L.svo_frontend_set_match_error(self._h, C.c_double(fme)))
 
+    def frontend_set_projection(self, p1, p2):
+        p1 = np.ascontiguousarray(p1, np.float64).reshape(12)
+        p2 = np.ascontiguousarray(p2, np.float64).reshape(12)
+        self._check(self._L.svo_frontend_set_projection(self._h, _p(p1), _p(p2)))
+
+    def triangulate_points(self, p1, p2, pts1, pts2):
+        """cv::triangulatePoints + convertPointsFromHomogeneous -> (points4d [n,4], points3d [n,3])"""
+        p1 = np.ascontiguousarray(p1, np.float64).reshape(12)
+        p2 = np.ascontiguousarray(p2, np.float64).reshape(12)
+        pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+        n = len(pts1)
+        o4 = np.zeros((n, 4), np.float32)
+        o3 = np.zeros((n, 3), np.float32)
+        self._check(self._L.svo_triangulate_points(self._h, _p(p1), _p(p2), _p(pts1), _p(pts2), n, _p(o4), _p(o3)))
+        return o4, o3
+
     def frontend_reset(self):
         self._check(self._L.svo_frontend_reset(self._h))
 
@@ -281,7 +298,7 @@ class FrontendBuffers:
     ALL = ("kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
            "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status",
            "orb_t2_left", "orb_t1_left", "orb_t1_right", "n_orb_matched", "lkf_t1_left", "lkf_t1_right", "lkf_t2_right", "lkf_t2_left",
-           "n_lk_matched")
+           "n_lk_matched", "orb_points3d", "lk_points3d")
 
     def __init__(self, n_frames, kp_cap, pt_cap, fields=None, alloc=None):
         fields = self.ALL if fields is None else fields
@@ -296,7 +313,8 @@ class FrontendBuffers:
                       lk_p0r=((F, P, 2), np.float32), lk_status=((F, 4, P), np.uint8),
                       orb_t2_left=((F, K, 2), np.float32), orb_t1_left=((F, K, 2), np.float32), orb_t1_right=((F, K, 2), np.float32),
                       n_orb_matched=((F,), np.int32), lkf_t1_left=((F, P, 2), np.float32), lkf_t1_right=((F, P, 2), np.float32),
-                      lkf_t2_right=((F, P, 2), np.float32), lkf_t2_left=((F, P, 2), np.float32), n_lk_matched=((F,), np.int32))
+                      lkf_t2_right=((F, P, 2), np.float32), lkf_t2_left=((F, P, 2), np.float32), n_lk_matched=((F,), np.int32),
+                      orb_points3d=((F, K, 3), np.float32), lk_points3d=((F, P, 3), np.float32))
         self.struct = FrontendOut()
         self.struct.kp_cap = kp_cap
         self.struct.pt_cap = pt_cap
@@ -325,7 +343,8 @@ class FrontendBuffers:
                             ("stereo_idx", mq * 4), ("stereo_dist", mq * 4), ("temporal_idx", mq * 4), ("temporal_dist", mq * 4),
                             ("fast_kps", mf * 28), ("lk_p1", ms * 8), ("lk_p2", ms * 8), ("lk_p3", ms * 8), ("lk_p0r", ms * 8),
                             ("lk_status", ms * 4), ("orb_t2_left", mo * 8), ("orb_t1_left", mo * 8), ("orb_t1_right", mo * 8),
-                            ("lkf_t1_left", mk * 8), ("lkf_t1_right", mk * 8), ("lkf_t2_right", mk * 8), ("lkf_t2_left", mk * 8)):
+                            ("lkf_t1_left", mk * 8), ("lkf_t1_right", mk * 8), ("lkf_t2_right", mk * 8), ("lkf_t2_left", mk * 8),
+                            ("orb_points3d", mo * 12), ("lk_points3d", mk * 12)):
             if getattr(self, name) is not None:
                 total += width * F
         return total + 3 * 4 * 2 * (F + 1)  # the count / flag arrays

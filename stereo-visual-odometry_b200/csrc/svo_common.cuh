@@ -177,6 +177,11 @@ struct svo_ctx {
     float* d_lkf_pts = nullptr;  // [frame slot][5: t1_left, t1_right, t2_right, t2_left, t1_left_returned][pt_cap][2]
     int* d_nlkf = nullptr;
     double fe_match_error = 3.0;  // feature_match_error (config/default.yaml:66)
+    // K12: triangulated points of the filtered lists (sensors_->projMatr1_/2_, sensors.cpp:8-24)
+    bool have_proj = false;
+    double proj1[12] = {}, proj2[12] = {};
+    float* d_orb_xyz = nullptr;  // [frame slot][kp_cap][3]
+    float* d_lkf_xyz = nullptr;  // [frame slot][pt_cap][3]
 
     // ---- matches (frontend): per frame slot, kp_cap each
     int* d_match = nullptr;  // [frame slot][4][kp_cap]: stereo idx, stereo dist, temporal idx, temporal dist
@@ -243,6 +248,7 @@ int launch_describe(svo_ctx* c, const SlotMap& map, int n_img);                 
 int launch_match_frontend(svo_ctx* c, int first, int ring, int n_frames, int skip_first);  // K6
 int launch_orb_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_first);      // K10
 int launch_lk_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_first);       // K11
+int launch_triangulate_frontend(svo_ctx* c, int first, int ring, int n_frames);            // K12
 int launch_fast_full(svo_ctx* c, const SlotMap& map, int n_img, int threshold);      // K9 (+ ordered compaction)
 int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img);                    // K7
 // one call of the 4-call LK chain for n_frames unit frames (K8); see k_lk.cu

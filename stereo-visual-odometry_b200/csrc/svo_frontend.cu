@@ -184,7 +184,7 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     for (int i = 0; i < 2; ++i) SVO_CUDA_TRY(c, cudaMalloc(&c->d_stage[i], c->stage_bytes));
     c->stage_idx = 0;
     {
-        void** ptrs[] = {(void**)&c->d_orb_pts, (void**)&c->d_norb, (void**)&c->d_lkf_pts, (void**)&c->d_nlkf};
+        void** ptrs[] = {(void**)&c->d_orb_pts, (void**)&c->d_norb, (void**)&c->d_lkf_pts, (void**)&c->d_nlkf, (void**)&c->d_orb_xyz, (void**)&c->d_lkf_xyz};
         for (void** p : ptrs) {
             if (*p) cudaFree(*p);
             *p = nullptr;
@@ -194,11 +194,13 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
         SVO_CUDA_TRY(c, cudaMalloc(&c->d_orb_pts, sizeof(float) * 2 * 3 * (size_t)c->kp_cap * c->fe_ring));
         SVO_CUDA_TRY(c, cudaMalloc(&c->d_norb, sizeof(int) * c->fe_ring));
         SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_norb, 0, sizeof(int) * c->fe_ring, c->stream));
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_orb_xyz, sizeof(float) * 3 * (size_t)c->kp_cap * c->fe_ring));
     }
     if (mode & SVO_MODE_LK) {
         SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkf_pts, sizeof(float) * 2 * 5 * (size_t)c->pt_cap * c->fe_ring));
         SVO_CUDA_TRY(c, cudaMalloc(&c->d_nlkf, sizeof(int) * c->fe_ring));
         SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nlkf, 0, sizeof(int) * c->fe_ring, c->stream));
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkf_xyz, sizeof(float) * 3 * (size_t)c->pt_cap * c->fe_ring));
     }
     c->fe_mode = mode;
     c->fe_max_frames = max_frames;
@@ -217,6 +219,16 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
 extern "C" int svo_frontend_set_match_error(svo_ctx* c, double fme) {
     if (!c) return SVO_ERR_INVALID;
     c->fe_match_error = fme;
+    return SVO_OK;
+}
+
+extern "C" int svo_frontend_set_projection(svo_ctx* c, const double* p1, const double* p2) {
+    if (!c || !p1 || !p2) return SVO_ERR_INVALID;
+    for (int i = 0; i < 12; ++i) {
+        c->proj1[i] = p1[i];
+        c->proj2[i] = p2[i];
+    }
+    c->have_proj = true;
     return SVO_OK;
 }
 
@@ -304,6 +316,7 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
             if ((rc = launch_lk_track(c, first, ring, n, skip_first, calls[k], 30, 0.01, 0.001)) != SVO_OK) return rc;
         if ((rc = launch_lk_filter(c, first, ring, n, skip_first)) != SVO_OK) return rc;
     }
+    if (c->have_proj && (rc = launch_triangulate_frontend(c, first, ring, n)) != SVO_OK) return rc;
     {  // completed-run queue (depth <= 2): what svo_frontend_download delivers, oldest first
         svo_ctx::DoneRun& d = c->fe_q[(c->fe_qhead + c->fe_nq) % 2];
         d.first = first;
@@ -405,6 +418,7 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
         float* oh[3] = {out->orb_t2_left, out->orb_t1_left, out->orb_t1_right};
         for (int r = 0; r < 3; ++r)
             if (oh[r] && (rc = rcpy.copy(oh[r], hk * 8, c->d_orb_pts + (size_t)r * K * 2, (size_t)3 * K * 8, (size_t)maxM * 8))) return rc;
+        if (out->orb_points3d && c->have_proj && (rc = rcpy.copy(out->orb_points3d, hk * 12, c->d_orb_xyz, (size_t)K * 12, (size_t)maxM * 12))) return rc;
         int32_t* mh[4] = {out->stereo_idx, out->stereo_dist, out->temporal_idx, out->temporal_dist};
         for (int r = 0; r < 4; ++r)
             if (mh[r] && (rc = rcpy.copy(mh[r], hk * 4, c->d_match + (size_t)r * K, (size_t)4 * K * 4, (size_t)maxQ * 4))) return rc;
@@ -436,6 +450,7 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
         float* fh[4] = {out->lkf_t1_left, out->lkf_t1_right, out->lkf_t2_right, out->lkf_t2_left};
         for (int r = 0; r < 4; ++r)
             if (fh[r] && (rc = rcpy.copy(fh[r], hp * 8, c->d_lkf_pts + (size_t)r * P * 2, (size_t)5 * P * 8, (size_t)maxK * 8))) return rc;
+        if (out->lk_points3d && c->have_proj && (rc = rcpy.copy(out->lk_points3d, hp * 12, c->d_lkf_xyz, (size_t)P * 12, (size_t)maxK * 12))) return rc;
         if (out->lk_status)
             for (int r = 0; r < 4; ++r)
                 if ((rc = rcpy.copy(out->lk_status + (size_t)r * hp, 4 * hp, c->d_lk_status + (size_t)r * P, (size_t)4 * P, (size_t)maxS))) return rc;

@@ -23,7 +23,7 @@ def test_exports_every_declared_symbol(pkg):
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
     assert sorted(pkg.ABI_SYMBOLS) == declared
-    assert L.svo_abi_version() == 2
+    assert L.svo_abi_version() == 3
 
 
 def test_keypoint_layout(pkg):

@@ -176,3 +176,43 @@ def test_frontend_pipelined_equals_sequential(pkg):
             assert np.array_equal(ref[k].stereo_idx[i, :nq], got[k].stereo_idx[i, :nq]) and np.array_equal(ref[k].temporal_idx[i, :nq], got[k].temporal_idx[i, :nq])
             assert np.array_equal(ref[k].fast_kps[i, :nf], got[k].fast_kps[i, :nf])
             assert np.array_equal(ref[k].lk_p3[i, :ns], got[k].lk_p3[i, :ns]) and np.array_equal(ref[k].lk_status[i, :, :ns], got[k].lk_status[i, :, :ns])
+
+
+KITTI_P1 = np.array([[718.856, 0, 607.1928, 0], [0, 718.856, 185.2157, 0], [0, 0, 1, 0]], np.float64)
+KITTI_P2 = KITTI_P1.copy()
+KITTI_P2[0, 3] = -386.1448
+
+
+def test_triangulate_points(pkg, orc):
+    gold = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "cv2_primitives.npz"))
+    ctx = pkg.Context(0, 64, 64, 2)
+    g4, g3 = ctx.triangulate_points(gold["tri_P1"], gold["tri_P2"], gold["tri_pts1"], gold["tri_pts2"])
+    o4, o3 = orc.triangulate_points(gold["tri_P1"], gold["tri_P2"], gold["tri_pts1"], gold["tri_pts2"])
+    ref3 = gold["tri_points3d"]  # cv2.triangulatePoints + convertPointsFromHomogeneous
+    assert (np.abs(g3 - ref3) <= 2e-5 * np.abs(ref3) + 1e-6).all()
+    assert (np.abs(g3 - o3) <= 2e-5 * np.abs(o3) + 1e-6).all()
+    print("triangulation: bit-identical to cv2 on", int((g3 == ref3).all(1).sum()), "of", len(ref3), "points")
+    assert ctx.triangulate_points(KITTI_P1, KITTI_P2, np.zeros((0, 2)), np.zeros((0, 2)))[1].shape == (0, 3)
+    ctx.close()
+
+
+def test_frontend_triangulated_lists(pkg, orc):
+    """K12 inside the batch: 3-D points of the filtered ORB and LK lists == oracle triangulation of those lists."""
+    w, h, B = 1241, 376, 3
+    left, right = pkg.synth_sequence(1000, 2, B, w, h)
+    ctx = pkg.Context(0, w, h, 2 * (B + 1))
+    ctx.orb_configure(1000, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    ctx.frontend_set_projection(KITTI_P1, KITTI_P2)
+    out = pkg.FrontendBuffers(B, ctx.orb_capacity(w, h), max(1024, w * h // 64))
+    ctx.frontend_batch(left, right, out)
+    for i in range(1, B):
+        for n, a, b, xyz in ((out.n_orb_matched[i], out.orb_t1_left[i], out.orb_t1_right[i], out.orb_points3d[i]),
+                             (out.n_lk_matched[i], out.lkf_t1_left[i], out.lkf_t1_right[i], out.lk_points3d[i])):
+            assert n > 50
+            _, o3 = orc.triangulate_points(KITTI_P1, KITTI_P2, a[:n], b[:n])
+            assert (np.abs(xyz[:n] - o3) <= 2e-5 * np.abs(o3) + 1e-6).all()
+        # synthetic disparity is 8 px: depth = fx * baseline / 8 for the bulk of the LK tracks
+        z = out.lk_points3d[i, :out.n_lk_matched[i], 2]
+        assert abs(np.median(z) - 386.1448 / 8) < 1.0
+    ctx.close()

@@ -53,6 +53,14 @@ def test_golden_lk(orc, gold):
         assert np.abs(err - gold[name + "_err"])[ok].max() <= 1e-2
 
 
+def test_golden_triangulation(orc, gold):
+    o4, o3 = orc.triangulate_points(gold["tri_P1"], gold["tri_P2"], gold["tri_pts1"], gold["tri_pts2"])
+    ref3 = gold["tri_points3d"]
+    assert (np.abs(o3 - ref3) <= 2e-5 * np.abs(ref3) + 1e-6).all()  # observed: bit-identical to cv2 4.13
+    sgn = np.sign((o4 * gold["tri_points4d"]).sum(1))[:, None]  # the singular vector's sign is arbitrary
+    assert np.abs(o4 * sgn - gold["tri_points4d"]).max() <= 1e-6
+
+
 def test_tables(orc):
     scale, inv, fpl, umax = orc.orb_tables(1000, 1.2, 8)
     assert list(fpl) == [217, 181, 151, 126, 105, 87, 73, 60]
