@@ -3,13 +3,15 @@
 //
 //  K7  k_pyr_down   cv::pyrDown: 5x5 [1 4 6 4 1]^2 / 256, BORDER_REFLECT_101, round half up; levels 1..3 of each image.
 //                   Built once per image (the reference rebuilds both pyramids inside each of its 4 calls).
-//  K8  k_lk_track   one warp per point, all pyramid levels in one launch, fully register-resident (no shared memory): lane l
-//                   owns one image column of the 24x24 neighbourhood of the previous image (REFLECT_101 outside the
-//                   image), derives the Scharr gradients on the fly with a sliding 3-row window + warp shuffles
-//                   (constant 0 outside the image, exactly like OpenCV's padded derivative buffer -- no derivative image is
-//                   ever written to HBM), keeps its column of the 21x21 interpolated window (I, Ix, Iy as int16) in
-//                   registers and iterates Gauss-Newton on 22x22 neighbourhoods of the next image read straight from
-//                   L1/L2.  All window sums are exact integers (int64 across the warp), converted to float once.
+//  K7b k_lk_pad     REFLECT_101 border (32 columns / 24 rows) around every LK plane, so that the tracker never branches on
+//                   the image border when it loads pixels.
+//  K8  k_lk_track   one warp per point, all pyramid levels in one launch.  Image neighbourhoods are staged per warp in
+//                   shared memory as (row, row shifted by one byte) word pairs, so the two horizontal taps of the bilinear
+//                   stencil are one aligned 16-bit load feeding IDP.2A.  Scharr gradients are derived on the fly (constant 0
+//                   outside the image, exactly like OpenCV's padded derivative buffer -- no derivative image is ever written
+//                   to HBM); the interpolated 21x21 template (I, Ix, Iy) lives in shared memory in flattened pixel order and
+//                   the Gauss-Newton iterations spread its 441 pixels over all 32 lanes.  All window sums are exact integers
+//                   (int64 across the warp), converted to float once.
 //
 // f32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) to follow OpenCV's scalar expressions.
 #include <cfloat>
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) k_pyr_down(LkLevelGeom S, LkLevelGeom D, 
 }
 
 struct LkParams {
-    LkLevelGeom lv[SVO_LK_LEVELS];
+    LkLevelGeom lv[SVO_LK_LEVELS];  // padded planes (REFLECT_101 border of SVO_LK_PADX / SVO_LK_PADY materialised)
     int levels;      // pyramid levels available (maxLevel + 1)
     int first, ring, skip_first;
     LkCall call;
@@ -90,6 +92,55 @@ struct LkParams {
     int want_err;
     int pt_cap;
 };
+
+// K7b: REFLECT_101 border of the LK planes (what buildOpticalFlowPyramid's copyMakeBorder produces).  Level 0 is copied
+// whole from the (unpadded) ORB level-0 plane; levels 1..3 are filled in place from their own interior.
+struct LkPadParams {
+    LkLevelGeom src0;               // unpadded level 0
+    LkLevelGeom lv[SVO_LK_LEVELS];  // padded planes (base = interior origin)
+    int row0[SVO_LK_LEVELS + 1];    // first CTA row of every level (padded rows are h + 2 * PADY)
+    int levels;
+};
+
+__device__ __forceinline__ int reflect101_any(int i, int n) {
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(128) k_lk_pad(LkPadParams P, SlotMap map) {
+    int l = 0;
+    while (l + 1 < P.levels && (int)blockIdx.x >= P.row0[l + 1]) ++l;
+    const LkLevelGeom& D = P.lv[l];
+    const int slot = map.slot(blockIdx.y);
+    const int yp = (int)blockIdx.x - P.row0[l] - SVO_LK_PADY;  // padded row, interior coordinates
+    const int ry = reflect101_any(yp, D.h);
+    uint8_t* drow = D.base + (size_t)slot * D.plane + (ptrdiff_t)yp * D.pitch;
+    const bool yin = yp >= 0 && yp < D.h;
+    if (l == 0) {
+        const uint8_t* __restrict__ srow = P.src0.base + (size_t)slot * P.src0.plane + (size_t)ry * P.src0.pitch;
+        for (int x = -SVO_LK_PADX + 4 * (int)threadIdx.x; x < D.w + SVO_LK_PADX; x += 4 * 128) {
+            uint32_t v;
+            if (x >= 0 && x + 3 < D.w) {
+                v = __ldg(reinterpret_cast<const uint32_t*>(srow + x));
+            } else {
+                v = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v |= (uint32_t)__ldg(srow + reflect101_any(x + i, D.w)) << (8 * i);
+            }
+            *reinterpret_cast<uint32_t*>(drow + x) = v;
+        }
+    } else {
+        const uint8_t* srow = D.base + (size_t)slot * D.plane + (ptrdiff_t)ry * D.pitch;
+        if (yin) {  // left / right pads only
+            for (int i = threadIdx.x; i < 2 * SVO_LK_PADX; i += 128) {
+                const int x = i < SVO_LK_PADX ? i - SVO_LK_PADX : D.w + i - SVO_LK_PADX;
+                drow[x] = srow[reflect101_any(x, D.w)];
+            }
+        } else {
+            for (int x = -SVO_LK_PADX + (int)threadIdx.x; x < D.w + SVO_LK_PADX; x += 128) drow[x] = srow[reflect101_any(x, D.w)];
+        }
+    }
+}
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
@@ -108,29 +159,57 @@ __device__ __forceinline__ void weights(float a, float b, int& w00, int& w01, in
     w11 = 16384 - w00 - w01 - w10;
 }
 
-// rows [y0, y0 + N) of image column x (REFLECT_101 outside the image); `interior` is warp-uniform: no reflection needed
-template <int N>
-__device__ __forceinline__ void load_column(const uint8_t* __restrict__ img, const LkLevelGeom& G, int x, int y0, bool interior, int (&out)[N]) {
-    if (interior) {
-        // 32-bit offsets from the (warp-uniform) image base: one integer add per row instead of 64-bit pointer arithmetic
-        const unsigned o0 = (unsigned)y0 * (unsigned)G.pitch + (unsigned)x, pitch = (unsigned)G.pitch;
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1  (a: two signed 16-bit weights, b: two unsigned pixels) -- one IDP.2A
+__device__ __forceinline__ int dp2(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// ---- per-warp shared-memory tile of an image neighbourhood ------------------------------------------------------------
+// 24 rows x 64 bytes.  A row holds 8 pairs of words (T_w, T2_w): T is the image row starting at the neighbourhood's first
+// column (the byte alignment of the global address is removed while staging), T2 the same row one byte later.  The two
+// horizontally adjacent pixels (c, c+1) of the bilinear stencil are therefore always ONE aligned 16-bit shared-memory load
+// (from T for even c, from T2 for odd c) that feeds IDP.2A directly -- no shuffles, no byte permutes, no address arithmetic
+// per row (rows are an immediate offset apart).
+constexpr int TROW = 64, TROWS = 24, TILE_BYTES = TROW * TROWS;
+constexpr int NPIX = WIN * WIN;  // 441 window pixels
+constexpr int NK = 14;           // window pixels per lane in the flattened (iteration) form: 32 * 14 = 448 >= 441
+constexpr int WARP_SMEM = TILE_BYTES + 32 * NK * 8;
+
+__device__ __forceinline__ int pair_off(int c) {  // byte offset in a tile row of the aligned u16 holding tile bytes (c, c+1)
+    const int e = c & ~1;
+    return ((e >> 2) << 3) + (e & 3) + ((c & 1) << 2);
+}
+
+__device__ __forceinline__ uint32_t lds_u16(const uint8_t* p) { return *reinterpret_cast<const unsigned short*>(p); }
+
+// rows y0 .. y0+23, columns x0 .. x0+27 of the padded plane -> tile (every lane: one aligned word per 4 rows, 6 rounds)
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restrict__ img, int pitch, int x0, int y0, int lane) {
+    const int a0 = x0 & 3, sh = 8 * a0;
+    const uint8_t* __restrict__ p = img + ((ptrdiff_t)(y0 + (lane >> 3)) * pitch + (x0 - a0) + 4 * (lane & 7));
+    uint2* dst = reinterpret_cast<uint2*>(tile + (lane >> 3) * TROW + (lane & 7) * 8);
+    const ptrdiff_t step = (ptrdiff_t)4 * pitch;
 #pragma unroll
-        for (int r = 0; r < N; ++r) out[r] = __ldg(img + (o0 + (unsigned)r * pitch));
-    } else {
-        const uint8_t* __restrict__ col = img + reflect101(x, G.w);
-#pragma unroll
-        for (int r = 0; r < N; ++r) out[r] = __ldg(col + (size_t)reflect101(y0 + r, G.h) * G.pitch);
+    for (int k = 0; k < TROWS / 4; ++k) {
+        const uint32_t W = __ldg(reinterpret_cast<const uint32_t*>(p + k * step));
+        const uint32_t Wn = __shfl_down_sync(0xFFFFFFFFu, W, 1);  // next word of the same row (lane & 7 == 7: unused word)
+        dst[k * (4 * TROW / 8)] = make_uint2(__funnelshift_r(W, Wn, sh), __funnelshift_rc(W, Wn, sh + 8));
     }
 }
 
-// One warp per point; lane l owns image column (ip.x - 1 + l) of the 24-column neighbourhood, so window column x lives in
-// lane x + 1.  Everything is register-resident: the lane walks down its column (sliding 3-row window for the Scharr
-// gradient), horizontal neighbours come from warp shuffles, and the interpolated window (I, Ix, Iy of 21 rows) stays in
-// registers for the Gauss-Newton iterations.  No shared memory, no derivative image.
-__global__ void __launch_bounds__(LW * 32, 3) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
+// One warp per point, all pyramid levels in one launch.
+//  setup (previous image): lane l owns column ipx - 1 + l of the staged 24 x 24 neighbourhood and walks down the rows; the
+//    Scharr gradient and the bilinear interpolation -- both linear with integer weights -- are commuted EXACTLY when every
+//    gradient tap lies inside the image: the image is interpolated once (Ib, un-descaled, 2 IDP.2A per row) and Scharr is
+//    applied to Ib with two shuffles per row.  Otherwise (window across the image border) the general form with OpenCV's
+//    constant-0 derivative outside the image runs.  The template (I, Ix, Iy) goes to shared memory in FLATTENED pixel order.
+//  iterations (next image): the 441 window pixels are spread over all 32 lanes (14 each): per pixel two 16-bit loads of the
+//    staged tile, one 64-bit template load, 2 IDP.2A, one shift, two sign extensions, two IMAD.
+// All window sums are exact integers; float expressions follow OpenCV's scalar order with _rn intrinsics.
+__global__ void __launch_bounds__(LW * 32, 4) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
                                                       float* __restrict__ lk_pts, uint8_t* __restrict__ lk_status, float* __restrict__ lk_err) {
-    __shared__ short s_Iw[LW][WIN * 32];
-    __shared__ uint32_t s_G[LW][WIN * 32];
+    __shared__ __align__(16) uint8_t s_mem[LW * WARP_SMEM];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;
     if (f == 0 && P.skip_first) return;
@@ -156,11 +235,25 @@ __global__ void __launch_bounds__(LW * 32, 3) k_lk_track(LkParams P, const svo_k
     float* dst = lk_pts + ((size_t)cur * 5 + P.call.dst_list) * P.pt_cap * 2;
     uint8_t* st_out = lk_status + ((size_t)cur * 4 + P.call.status_row) * P.pt_cap;
 
+    uint8_t* tile = s_mem + warp * WARP_SMEM;
+    uint2* tmpl = reinterpret_cast<uint2*>(tile + TILE_BYTES);  // [pixel y * 21 + x] = (256 - 512 * I, Ix | Iy << 16)
+    if (lane < 32 * NK - NPIX) tmpl[NPIX + lane] = make_uint2(0u, 0u);  // the 7 pad pixels: zero gradient, never rewritten
+    // flattened form: lane owns pixels lane + 32 k; offset of the (x, x+1) pair of row y in a tile whose byte 0 is column x = 0
+    int offJ[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        int idx = lane + 32 * k;
+        if (idx >= NPIX) idx = 0;
+        const int y = idx / WIN, x = idx - WIN * y;
+        offJ[k] = y * TROW + pair_off(x);
+    }
+    const int ccol = min(lane, 23);  // setup: tile column of this lane
+
     const float half = 10.f;   // (win - 1) * 0.5
     float nx = 0.f, ny = 0.f;  // nextPts[pt] carried across levels
     int status = 1;
     float err = 0.f;
-    const bool wlane = lane >= 1 && lane <= WIN;  // lanes that own a window column
+    const bool wlane = lane >= 1 && lane <= WIN;  // lanes that own a window column during the setup
 
     for (int level = P.levels - 1; level >= 0; --level) {
         const LkLevelGeom& G = P.lv[level];
@@ -187,73 +280,81 @@ __global__ void __launch_bounds__(LW * 32, 3) k_lk_track(LkParams P, const svo_k
         }
         int iw00, iw01, iw10, iw11;
         weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
+        uint32_t Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16), Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
 
-        // ---- previous image: column X = ipx - 1 + lane, rows ipy - 1 .. ipy + 22 (REFLECT_101 outside the image)
-        // the interpolated window lives in shared memory (lane-major, conflict-free): keeps the kernel at 3 CTAs / SM
-        short* Iw = s_Iw[warp] + lane;      // Iw[y * 32]
-        uint32_t* Gw = s_G[warp] + lane;    // (Ix, Iy) int16 pair at Gw[y * 32]
+        // ---- previous image: tile byte 0 = column ipx - 1, tile row 0 = image row ipy - 1
+        __syncwarp();
+        stage_tile(tile, I, G.pitch, ipx - 1, ipy - 1, lane);
+        __syncwarp();
         int a11 = 0, a12 = 0, a22 = 0;
-        const bool inside = ipx - 1 >= 0 && ipx + 22 < G.w && ipy - 1 >= 0 && ipy + 22 < G.h;  // warp-uniform
+        uint2* tw = tmpl + (lane - 1);  // window column x = lane - 1; row y at tw[y * 21]
+        // every gradient tap (columns ipx .. ipx+21, rows ipy .. ipy+21) inside the image?  (warp-uniform)
+        const bool inside = ipx >= 0 && ipx + WIN < G.w && ipy >= 0 && ipy + WIN < G.h;
         if (inside) {
-            // Whole neighbourhood inside the image: no reflection, no zeroed gradients.  The Scharr operator and the bilinear
-            // interpolation are both linear with integer weights, so they commute exactly: interpolate the IMAGE once
-            // (Ib, un-descaled) and apply Scharr to Ib -- 4 multiplies per position instead of 12.
-            //   sum_ij w_ij Ix(x+i, y+j) = Vb(x+1, y) - Vb(x-1, y),          Vb = 3 Ib(y-1) + 10 Ib(y) + 3 Ib(y+1)
-            //   sum_ij w_ij Iy(x+i, y+j) = 3 (Db(x-1, y) + Db(x+1, y)) + 10 Db(x, y),   Db = Ib(y+1) - Ib(y-1)
-            int pix[24];
-            load_column<24>(I, G, ipx - 1 + min(lane, 23), ipy - 1, true, pix);
-            int pn0 = __shfl_down_sync(0xFFFFFFFFu, pix[0], 1), pn1 = __shfl_down_sync(0xFFFFFFFFu, pix[1], 1);
-            int ib0 = pix[0] * iw00 + pn0 * iw01 + pix[1] * iw10 + pn1 * iw11;  // Ib row -1 (image row ipy - 1)
-            int pn2 = __shfl_down_sync(0xFFFFFFFFu, pix[2], 1);
-            int ib1 = pix[1] * iw00 + pn1 * iw01 + pix[2] * iw10 + pn2 * iw11;  // Ib row 0
-            int pnr = pn2;
+            //   Ib(r) = interpolated image at tile row r (rows 0..22), exact and un-descaled
+            //   Ix(y) = 3 (dH(y) + dH(y+2)) + 10 dH(y+1),  dH = Ib(x+1) - Ib(x-1)
+            //   Iy(y) = S(y+2) - S(y),                       S  = 3 (Ib(x-1) + Ib(x+1)) + 10 Ib(x)
+            const uint8_t* tp = tile + pair_off(ccol);
+            int top = dp2(Wtop, lds_u16(tp), 0);
+            int dH0 = 0, dH1 = 0, S0 = 0, S1 = 0, ibm = 0;
 #pragma unroll
-            for (int y = 0; y < WIN; ++y) {
-                const int pnn = __shfl_down_sync(0xFFFFFFFFu, pix[y + 3], 1);
-                const int ib2 = pix[y + 2] * iw00 + pnr * iw01 + pix[y + 3] * iw10 + pnn * iw11;  // Ib row y + 1
-                pnr = pnn;
-                const int Vb = 3 * (ib0 + ib2) + 10 * ib1, Db = ib2 - ib0;
-                const int ixn = __shfl_down_sync(0xFFFFFFFFu, Vb, 1) - __shfl_up_sync(0xFFFFFFFFu, Vb, 1);
-                const int iyn = 3 * (__shfl_up_sync(0xFFFFFFFFu, Db, 1) + __shfl_down_sync(0xFFFFFFFFu, Db, 1)) + 10 * Db;
-                const int ixv = descale(ixn, 14), iyv = descale(iyn, 14);
-                Iw[y * 32] = (short)descale(ib1, 9);
-                Gw[y * 32] = ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16);
-                a11 += ixv * ixv;
-                a12 += ixv * iyv;
-                a22 += iyv * iyv;
-                ib0 = ib1;
-                ib1 = ib2;
+            for (int r = 1; r < TROWS; ++r) {
+                const uint32_t pr = lds_u16(tp + r * TROW);
+                const int ib = dp2(Wbot, pr, top);  // Ib(r - 1)
+                top = dp2(Wtop, pr, 0);
+                const int ibL = __shfl_up_sync(0xFFFFFFFFu, ib, 1), ibR = __shfl_down_sync(0xFFFFFFFFu, ib, 1);
+                const int dH2 = ibR - ibL, S2 = 3 * (ibL + ibR) + 10 * ib;
+                if (r >= 3) {  // window row y = r - 3: Ib rows y, y+1, y+2 are complete
+                    const int y = r - 3;
+                    const int ixv = (3 * (dH0 + dH2) + 10 * dH1 + (1 << 13)) >> 14;
+                    const int iyv = (S2 - S0 + (1 << 13)) >> 14;
+                    const int iv = (ibm + 256) >> 9;
+                    if (wlane) tw[y * WIN] = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
+                    a11 += ixv * ixv;
+                    a12 += ixv * iyv;
+                    a22 += iyv * iyv;
+                }
+                dH0 = dH1;
+                dH1 = dH2;
+                S0 = S1;
+                S1 = S2;
+                ibm = ib;
             }
         } else {
-            const int X = ipx - 1 + min(lane, 23);
+            // general form: Scharr gradient per image position, zero outside the image (OpenCV's constant-0 padded
+            // derivative), then the bilinear interpolation of I, Ix, Iy separately
+            const int X = ipx - 1 + ccol;
             const bool xin = X >= 0 && X < G.w;
-            int pix[24];
-            load_column<24>(I, G, X, ipy - 1, false, pix);
-            int tp = 0, tpn = 0, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;  // the row above (top taps of the bilinear stencil)
+            const uint8_t* tb = tile + ((ccol >> 2) << 3) + (ccol & 3);  // T byte of this lane's column
+            const uint8_t* tp = tile + pair_off(ccol);
+            int p0 = tb[0], p1 = tb[TROW];
+            int top = 0, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;
 #pragma unroll
             for (int r = 0; r < 22; ++r) {
-                // Scharr gradient at (X, Y = ipy + r); zero outside the image like OpenCV's constant-0 padded derivative
-                const int V = 3 * (pix[r] + pix[r + 2]) + 10 * pix[r + 1], Dv = pix[r + 2] - pix[r];
+                const int p2 = tb[(r + 2) * TROW];
+                // Scharr gradient at (X, Y = ipy + r) (tile row r + 1)
+                const int V = 3 * (p0 + p2) + 10 * p1, Dv = p2 - p0;
                 const int Vl = __shfl_up_sync(0xFFFFFFFFu, V, 1), Vr = __shfl_down_sync(0xFFFFFFFFu, V, 1);
                 const int Dl = __shfl_up_sync(0xFFFFFFFFu, Dv, 1), Dr = __shfl_down_sync(0xFFFFFFFFu, Dv, 1);
                 const int Y = ipy + r;
                 const bool in = xin && Y >= 0 && Y < G.h;
                 const int gx = in ? Vr - Vl : 0;
                 const int gy = in ? 3 * (Dl + Dr) + 10 * Dv : 0;
-                const int p = pix[r + 1];
-                const int pn = __shfl_down_sync(0xFFFFFFFFu, p, 1);
                 const int gxn = __shfl_down_sync(0xFFFFFFFFu, gx, 1), gyn = __shfl_down_sync(0xFFFFFFFFu, gy, 1);
+                const uint32_t pr = lds_u16(tp + (r + 1) * TROW);
                 if (r >= 1) {
-                    const int ival = descale(tp * iw00 + tpn * iw01 + p * iw10 + pn * iw11, 9);
+                    const int iv = (dp2(Wbot, pr, top) + 256) >> 9;
                     const int ixv = descale(tgx * iw00 + tgxn * iw01 + gx * iw10 + gxn * iw11, 14);
                     const int iyv = descale(tgy * iw00 + tgyn * iw01 + gy * iw10 + gyn * iw11, 14);
-                    Iw[(r - 1) * 32] = (short)ival;
-                    Gw[(r - 1) * 32] = ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16);
+                    if (wlane) tw[(r - 1) * WIN] = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
                 }
-                tp = p; tpn = pn; tgx = gx; tgxn = gxn; tgy = gy; tgyn = gyn;
+                top = dp2(Wtop, pr, 0);
+                tgx = gx; tgxn = gxn; tgy = gy; tgyn = gyn;
+                p0 = p1;
+                p1 = p2;
             }
         }
         const long long sA11 = warp_sum64(wlane ? a11 : 0), sA12 = warp_sum64(wlane ? a12 : 0), sA22 = warp_sum64(wlane ? a22 : 0);
@@ -272,6 +373,7 @@ __global__ void __launch_bounds__(LW * 32, 3) k_lk_track(LkParams P, const svo_k
         nx = __fsub_rn(nx, half);
         ny = __fsub_rn(ny, half);
         float pdx = 0.f, pdy = 0.f;
+        const uint2* tl = tmpl + lane;
         for (int j = 0; j < P.max_iter; ++j) {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
             if (inx < -WIN || inx >= G.w || iny < -WIN || iny >= G.h) {
@@ -279,29 +381,22 @@ __global__ void __launch_bounds__(LW * 32, 3) k_lk_track(LkParams P, const svo_k
                 break;
             }
             weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
-            int jp[22];
-            load_column<22>(J, G, inx - 1 + min(lane, 23), iny, inx - 1 >= 0 && inx + 22 < G.w && iny >= 0 && iny + 21 < G.h, jp);
-            // neighbour column of every row first (22 independent shuffles), then two accumulator pairs: short dependency chains
-            int jn[22];
+            Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16);
+            Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
+            __syncwarp();  // the previous tile (and, in the first iteration, the template stores) are complete
+            stage_tile(tile, J, G.pitch, inx, iny, lane);
+            __syncwarp();
+            int b1 = 0, b2 = 0;
 #pragma unroll
-            for (int r = 0; r < 22; ++r) jn[r] = __shfl_down_sync(0xFFFFFFFFu, jp[r], 1);
-            int b1 = 0, b2 = 0, b1o = 0, b2o = 0;
-#pragma unroll
-            for (int y = 0; y < WIN; ++y) {
-                const int diff = descale(jp[y] * iw00 + jn[y] * iw01 + jp[y + 1] * iw10 + jn[y + 1] * iw11, 9) - Iw[y * 32];
-                const uint32_t gw = Gw[y * 32];
-                const int gxv = (int)(short)(gw & 0xFFFFu), gyv = (int)gw >> 16;
-                if (y & 1) {
-                    b1o += diff * gxv;
-                    b2o += diff * gyv;
-                } else {
-                    b1 += diff * gxv;
-                    b2 += diff * gyv;
-                }
+            for (int k = 0; k < NK; ++k) {
+                const uint32_t pt0 = lds_u16(tile + offJ[k]), pt1 = lds_u16(tile + offJ[k] + TROW);
+                const uint2 t = tl[32 * k];
+                const int diff = dp2(Wbot, pt1, dp2(Wtop, pt0, (int)t.x)) >> 9;  // descale(J interpolated, 9) - I
+                const int gxv = (int)(short)(t.y & 0xFFFFu), gyv = (int)t.y >> 16;
+                b1 += diff * gxv;
+                b2 += diff * gyv;
             }
-            b1 += b1o;
-            b2 += b2o;
-            const long long sb1 = warp_sum64(wlane ? b1 : 0), sb2 = warp_sum64(wlane ? b2 : 0);
+            const long long sb1 = warp_sum64(b1), sb2 = warp_sum64(b2);
             const float b1f = __fmul_rn((float)sb1, FLT_SCALE), b2f = __fmul_rn((float)sb2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2f), __fmul_rn(A22, b1f)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1f), __fmul_rn(A11, b2f)), D);
@@ -327,17 +422,19 @@ __global__ void __launch_bounds__(LW * 32, 3) k_lk_track(LkParams P, const svo_k
                 status = 0;
             } else if (P.want_err) {
                 weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), iw00, iw01, iw10, iw11);
-                const uint8_t* __restrict__ col = J + reflect101(inx - 1 + min(lane, 23), G.w);
+                Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16);
+                Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
+                __syncwarp();
+                stage_tile(tile, J, G.pitch, inx, iny, lane);
+                __syncwarp();
                 int e = 0;
-                int top = __ldg(col + (size_t)reflect101(iny, G.h) * G.pitch), topn = __shfl_down_sync(0xFFFFFFFFu, top, 1);
 #pragma unroll
-                for (int y = 0; y < WIN; ++y) {
-                    const int bot = __ldg(col + (size_t)reflect101(iny + y + 1, G.h) * G.pitch), botn = __shfl_down_sync(0xFFFFFFFFu, bot, 1);
-                    e += abs(descale(top * iw00 + topn * iw01 + bot * iw10 + botn * iw11, 9) - Iw[y * 32]);
-                    top = bot;
-                    topn = botn;
+                for (int k = 0; k < NK; ++k) {
+                    const uint32_t pt0 = lds_u16(tile + offJ[k]), pt1 = lds_u16(tile + offJ[k] + TROW);
+                    const int diff = dp2(Wbot, pt1, dp2(Wtop, pt0, (int)tl[32 * k].x)) >> 9;
+                    if (lane + 32 * k < NPIX) e += abs(diff);
                 }
-                const long long se = warp_sum64(wlane ? e : 0);
+                const long long se = warp_sum64(e);
                 err = __fdiv_rn((float)se, (float)(32 * WIN * WIN));
             }
         }
@@ -361,12 +458,24 @@ int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
         k_pyr_down<<<grid, 256, 0, c->stream>>>(S, D, map);
         ++c->launches;
     }
+    LkPadParams P{};
+    P.src0 = c->lk[0];
+    P.lv[0] = c->lkp0;
+    P.levels = c->lk_levels;
+    P.row0[0] = 0;
+    for (int l = 0; l < c->lk_levels; ++l) {
+        if (l) P.lv[l] = c->lk[l];
+        P.row0[l + 1] = P.row0[l] + P.lv[l].h + 2 * SVO_LK_PADY;
+    }
+    k_lk_pad<<<dim3(P.row0[c->lk_levels], n_img), 128, 0, c->stream>>>(P, map);
+    ++c->launches;
     SVO_CUDA_TRY(c, cudaGetLastError());
     return SVO_OK;
 }
 
 static void fill_params(svo_ctx* c, LkParams& P, int max_level, int max_iter, double eps, double min_eig) {
-    for (int l = 0; l < SVO_LK_LEVELS; ++l) P.lv[l] = c->lk[l];
+    P.lv[0] = c->lkp0;
+    for (int l = 1; l < SVO_LK_LEVELS; ++l) P.lv[l] = c->lk[l];
     P.levels = std::min(c->lk_levels, max_level + 1);
     P.max_iter = std::min(std::max(max_iter, 0), 100);
     eps = std::min(std::max(eps, 0.), 10.);

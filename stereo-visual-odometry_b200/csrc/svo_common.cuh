@@ -24,6 +24,10 @@
 #define SVO_MAX_DIM 4096   // packed candidate coordinates are 12 bits (relative to minBorder)
 #define SVO_LK_LEVELS 4    // maxLevel 3 (tracking.cpp:594)
 #define SVO_LK_WIN 21
+// REFLECT_101 border materialised around every LK plane (buildOpticalFlowPyramid pads by winSize): the tracker reads up to
+// 22 px beyond the image and stages aligned 32-byte rows, hence 32 columns; 24 rows
+#define SVO_LK_PADX 32
+#define SVO_LK_PADY 24
 
 struct LevelGeom {
     uint8_t* base;  // slot 0 of this level
@@ -155,9 +159,10 @@ struct svo_ctx {
     size_t pinned_bytes = 0;
 
     // ---- LK / full-frame FAST
-    LkLevelGeom lk[SVO_LK_LEVELS];
+    LkLevelGeom lk[SVO_LK_LEVELS];  // [0]: the ORB level-0 plane (unpadded); [1..3]: padded planes, base = interior origin
+    LkLevelGeom lkp0;               // padded copy of level 0 (written by k_lk_pad)
     int lk_levels = 0;
-    uint8_t* d_lkpyr = nullptr;  // levels 1..3 (level 0 aliases ORB level 0)
+    uint8_t* d_lkpyr = nullptr;  // padded planes: level-0 copy + levels 1..3
     std::vector<FastTile> ftiles;
     FastTile* d_ftiles = nullptr;
     int n_ftiles = 0;

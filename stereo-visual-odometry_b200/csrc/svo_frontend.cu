@@ -35,21 +35,30 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
     const LevelGeom& L0 = c->geom.lvl[0];
     c->lk[0] = LkLevelGeom{L0.base, L0.w, L0.h, L0.pitch, L0.plane};
     c->lk_levels = 1;
+    // padded planes (REFLECT_101 border of SVO_LK_PADX columns / SVO_LK_PADY rows): a copy of level 0 and levels 1..3
     size_t total = 0;
     std::vector<size_t> off(SVO_LK_LEVELS, 0);
+    auto padded = [&](int lw, int lh, size_t& o) {
+        LkLevelGeom g{};
+        g.w = lw;
+        g.h = lh;
+        g.pitch = (int)svo_align(lw + 2 * SVO_LK_PADX, 64);
+        g.plane = (uint32_t)g.pitch * (uint32_t)(lh + 2 * SVO_LK_PADY);
+        o = total;
+        total += svo_align((size_t)g.plane * S, 256);
+        return g;
+    };
+    c->lkp0 = padded(L0.w, L0.h, off[0]);
     for (int l = 1; l < SVO_LK_LEVELS; ++l) {
         const int lw = (c->lk[l - 1].w + 1) / 2, lh = (c->lk[l - 1].h + 1) / 2;
         if (lw <= SVO_LK_WIN || lh <= SVO_LK_WIN) break;  // buildOpticalFlowPyramid stops before a level <= winSize
-        c->lk[l].w = lw;
-        c->lk[l].h = lh;
-        c->lk[l].pitch = (int)svo_align(lw, 64);
-        c->lk[l].plane = (uint32_t)c->lk[l].pitch * lh;
-        off[l] = total;
-        total += svo_align((size_t)c->lk[l].plane * S, 256);
+        c->lk[l] = padded(lw, lh, off[l]);
         c->lk_levels = l + 1;
     }
     SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkpyr, total + 4096));
-    for (int l = 1; l < c->lk_levels; ++l) c->lk[l].base = c->d_lkpyr + off[l];
+    SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_lkpyr, 0, total + 4096, c->stream));
+    c->lkp0.base = c->d_lkpyr + off[0] + (size_t)SVO_LK_PADY * c->lkp0.pitch + SVO_LK_PADX;
+    for (int l = 1; l < c->lk_levels; ++l) c->lk[l].base = c->d_lkpyr + off[l] + (size_t)SVO_LK_PADY * c->lk[l].pitch + SVO_LK_PADX;
 
     // full-frame FAST strips over the inner domain [3, w-3) x [3, h-3)
     c->ftiles.clear();
