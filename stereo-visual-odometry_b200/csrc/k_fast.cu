@@ -25,41 +25,43 @@
 // Ordered output without atomics on the order: per-cell (K2) / per-word (K9) keep masks, a scan, then positional writes.
 //
 // Roofline: every level pixel is read from HBM once (window halos come from L2); the kernels are integer-ALU bound.
+#include <type_traits>
+
 #include "svo_common.cuh"
 
 namespace {
 
 constexpr int FT = 256;  // threads per CTA
 constexpr int FW = FT / 32;
-constexpr int QCAP = 160;  // per-warp queue of pre-test survivors: up to 31 left over + 128 new per pre-test iteration
+constexpr int QCAP = 288;  // per-warp queue of pre-test survivors: up to 31 left over + 256 new per pre-test step
 
 // FAST-9 corner score of the pixel at p (shared memory, row pitch `pw`): max over the 16 arcs of 9 contiguous ring
 // pixels of min(v - ring) [dark arc] and of min(ring - v) [bright arc], minus 1 (== cv cornerScore<16>).
 __device__ __forceinline__ int fast9_score(const uint8_t* p, int pw) {
     const int v = p[0];
-    const uint32_t base = ((uint32_t)v << 16) | (uint32_t)((-v) & 0xFFFF);  // hi: +v, lo: -v
+    // biased differences, two per register: hi half = v - ring + 256, lo half = ring - v + 256 (both in [1, 511], so the halves
+    // never borrow from each other and ONE 32-bit multiply-add per ring pixel builds both: ring * 0xFFFF0001 = (-ring : +ring))
+    const uint32_t base = ((uint32_t)(v + 256) << 16) | (uint32_t)(256 - v);
     uint32_t d[16];
     {
         const int r0 = p[3 * pw], r1 = p[3 * pw + 1], r2 = p[2 * pw + 2], r3 = p[pw + 3], r4 = p[3], r5 = p[-pw + 3],
                   r6 = p[-2 * pw + 2], r7 = p[-3 * pw + 1], r8 = p[-3 * pw], r9 = p[-3 * pw - 1], r10 = p[-2 * pw - 2],
                   r11 = p[-pw - 3], r12 = p[-3], r13 = p[pw - 3], r14 = p[2 * pw - 2], r15 = p[3 * pw - 1];
         const int r[16] = {r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15};
-        // r * 0xFFFF0001 = r - (r << 16): hi half = -r, lo half = +r (no borrow); + base -> hi: v - r, lo: r - v
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = __vadd2((uint32_t)r[k] * 0xFFFF0001u, base);
+        for (int k = 0; k < 16; ++k) d[k] = (uint32_t)r[k] * 0xFFFF0001u + base;
     }
     uint32_t m3[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    uint32_t best = 0x80008000u;
+    uint32_t best = 0;
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
         const uint32_t a = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
         const uint32_t b = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
         best = __vimax3_s16x2(best, a, b);
     }
-    const int lo = (short)(best & 0xFFFF), hi = (short)(best >> 16);
-    return max(lo, hi) - 1;
+    return max((int)(best & 0xFFFF), (int)(best >> 16)) - 257;  // remove the bias, then cornerScore's -1
 }
 
 __device__ __forceinline__ void load_window(const uint8_t* __restrict__ img, int pitch, int xa, int ya, int rows, int nchunk,
@@ -71,26 +73,71 @@ __device__ __forceinline__ void load_window(const uint8_t* __restrict__ img, int
     }
 }
 
+// where the score stage records the pixels with a score >= thr: a row bitmap (K9) or a compact corner list (K2)
+struct CornerSink {
+    uint32_t* nz;    // bitmap: row (ey + 1) * NWB, bit ex          (nullptr: not used)
+    int NWB;
+    uint16_t* list;  // corner list entries ey << 10 | ex             (nullptr: not used)
+    int* list_n;
+    int list_cap;
+};
+
+// queue entry of a pre-test survivor: row << 16 | x (32-bit, any strip width) or row << 10 | x (16-bit, tiles up to 1024 x 64)
+template <bool E16>
 __device__ __forceinline__ void score_pixel(const uint8_t* pix, int PW, int sx0, int sy0, uint32_t e, int thr, uint8_t* sc, int SW,
-                                            uint32_t* nz, int NWB) {
-    const int ey = (int)(e >> 16), ex = (int)(e & 0xFFFF);
+                                            const CornerSink& sink) {
+    const int ey = E16 ? (int)(e >> 10) : (int)(e >> 16), ex = E16 ? (int)(e & 1023) : (int)(e & 0xFFFF);
     const int s = fast9_score(pix + (size_t)(sy0 + ey) * PW + sx0 + ex, PW);
-    if (s >= thr && s > 0) {
-        sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
-        atomicOr(nz + (ey + 1) * NWB + (ex >> 5), 1u << (ex & 31));
+    const bool hit = s >= thr && s > 0;
+    if (hit) sc[(size_t)(ey + 1) * SW + ex + 1] = (uint8_t)s;
+    if (sink.list) {  // warp-aggregated append (order is irrelevant: the list only feeds the suppression stage)
+        const unsigned act = __activemask();
+        const unsigned bal = __ballot_sync(act, hit);
+        if (bal) {
+            const int lane = threadIdx.x & 31, leader = __ffs((int)bal) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(sink.list_n, __popc(bal));
+            base = __shfl_sync(act, base, leader);
+            const int o = base + __popc(bal & ((1u << lane) - 1));
+            if (hit && o < sink.list_cap) sink.list[o] = (uint16_t)((ey << 10) | ex);
+        }
+    } else if (hit) {
+        atomicOr(sink.nz + (ey + 1) * sink.NWB + (ex >> 5), 1u << (ex & 31));
     }
 }
 
-// Score stage: scores >= thr of the pixels [sx0, sx0+sw) x [sy0, sy0+sh) (window coordinates; sx0 >= 3, PW % 4 == 0) are
-// written to sc at (+1,+1) and flagged in the row bitmap nz at row +1; sc and nz must be zero-initialised.  Each warp owns
-// rows warp, warp+8, ...; pre-test survivors are appended to the warp's queue (slot = prefix over lanes from 3 ballots of
-// the per-lane survivor count) and scored 32 at a time, so the exact score always runs on (almost) full warps.
+// byte-SIMD necessary condition for 4 pixels (one word c of the centre row): a 9-arc holds one pixel of each opposite ring
+// pair, so a corner at threshold t needs |c - left| > t or |c - right| > t, AND the same for up / down.  MSB of each byte.
+// POW2 (t + 1 a power of two, e.g. minThFAST = 7): "d >= t + 1" depends only on the high bits of d, so the two differences
+// of a pair can be OR-ed before the comparison (exact); otherwise each difference is compared on its own.
+template <bool POW2>
+__device__ __forceinline__ uint32_t pretest4(uint32_t c, uint32_t cm, uint32_t cp, uint32_t up, uint32_t dn, uint32_t K7) {
+    const uint32_t dl = __vabsdiffu4(c, __funnelshift_r(cm, c, 8));   // pixels x - 3
+    const uint32_t dr = __vabsdiffu4(c, __funnelshift_r(c, cp, 24));  // pixels x + 3
+    const uint32_t du = __vabsdiffu4(c, up), dd = __vabsdiffu4(c, dn);
+    if (POW2) {
+        const uint32_t h = dl | dr, v = du | dd;
+        return (((h & 0x7F7F7F7Fu) + K7) | h) & (((v & 0x7F7F7F7Fu) + K7) | v) & 0x80808080u;
+    }
+    const uint32_t h = ((dl & 0x7F7F7F7Fu) + K7) | dl | ((dr & 0x7F7F7F7Fu) + K7) | dr;
+    const uint32_t v = ((du & 0x7F7F7F7Fu) + K7) | du | ((dd & 0x7F7F7F7Fu) + K7) | dd;
+    return h & v & 0x80808080u;
+}
+
+// Score stage: scores >= thr of the pixels [sx0, sx0+sw) x [sy0, sy0+sh) (window coordinates; sx0 >= 3, PW % 16 == 0, pix
+// 16-byte aligned) are written to sc at (+1,+1) and recorded in `sink`; sc (and the bitmap) must be zero-initialised.  Each
+// warp owns rows warp, warp+8, ...; a lane pre-tests 8 pixels (an aligned word pair) per step; survivors are appended to the
+// warp's queue (slot = prefix over lanes from 4 ballots of the per-lane survivor count) and scored 32 at a time, so the exact
+// score always runs on (almost) full warps.
+template <bool POW2, bool E16>
 __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0, int sy0, int sw, int sh, int thr, uint8_t* sc,
-                                             int SW, uint32_t* nz, int NWB, uint32_t* wq, uint32_t* tail_q) {
+                                             int SW, const CornerSink& sink, typename std::conditional<E16, uint16_t, uint32_t>::type* wq,
+                                             uint32_t* tail_q) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t8 = (thr + 1) >> 1;
-    const uint32_t K = (uint32_t)(0x80 - t8) * 0x01010101u;
+    const int T = min(thr + 1, 128);  // necessary: |difference| >= T
+    const uint32_t K7 = (uint32_t)(0x80 - T) * 0x01010101u;
     const int w0 = sx0 >> 2, w1 = (sx0 + sw - 1) >> 2;  // first / last 4-pixel word of the region
+    const int w0e = w0 & ~1;
     const uint32_t m_first = 0x80808080u << (8 * (sx0 & 3));                  // bytes >= sx0 of word w0
     const uint32_t m_last = 0x80808080u >> (8 * (3 - ((sx0 + sw - 1) & 3)));  // bytes <= last column of word w1
     const uint32_t lt = (1u << lane) - 1;
@@ -99,35 +146,43 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
         const uint32_t* row = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy) * PW);
         const uint32_t* rup = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy - 3) * PW);
         const uint32_t* rdn = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy + 3) * PW);
-        for (int wb = w0; wb <= w1; wb += 32) {
-            const int wi = wb + lane;
-            uint32_t pass = 0;
+        for (int wb = w0e; wb <= w1; wb += 64) {
+            const int wi = wb + 2 * lane;  // this lane: words wi, wi + 1
+            uint32_t pass0 = 0, pass1 = 0;
             if (wi <= w1) {
-                const uint32_t c0 = row[wi], cm = row[wi - 1], cp = row[wi + 1];
-                const uint32_t dl = __vabsdiffu4(c0, __funnelshift_r(cm, c0, 8));   // pixels x - 3
-                const uint32_t dr = __vabsdiffu4(c0, __funnelshift_r(c0, cp, 24));  // pixels x + 3
-                const uint32_t du = __vabsdiffu4(c0, rup[wi]), dd = __vabsdiffu4(c0, rdn[wi]);
-                const uint32_t ml = ((dl >> 1) & 0x7F7F7F7Fu) + K, mr = ((dr >> 1) & 0x7F7F7F7Fu) + K;
-                const uint32_t mu = ((du >> 1) & 0x7F7F7F7Fu) + K, md = ((dd >> 1) & 0x7F7F7F7Fu) + K;
-                pass = (ml | mr) & (mu | md) & 0x80808080u;
-                if (wi == w0) pass &= m_first;
-                if (wi == w1) pass &= m_last;
+                const uint2 c = *reinterpret_cast<const uint2*>(row + wi);
+                const uint2 u = *reinterpret_cast<const uint2*>(rup + wi), d = *reinterpret_cast<const uint2*>(rdn + wi);
+                const uint32_t cm = row[wi - 1], cp = row[wi + 2];
+                pass0 = pretest4<POW2>(c.x, cm, c.y, u.x, d.x, K7);
+                pass1 = pretest4<POW2>(c.y, c.x, cp, u.y, d.y, K7);
+                if (wi <= w0 || wi + 1 >= w1) {  // region edges (rare)
+                    if (wi < w0) pass0 = 0;
+                    if (wi == w0) pass0 &= m_first;
+                    if (wi == w1) pass0 &= m_last;
+                    if (wi + 1 == w0) pass1 &= m_first;
+                    if (wi + 1 == w1) pass1 &= m_last;
+                    if (wi + 1 > w1) pass1 = 0;
+                }
             }
-            const int n = __popc(pass);  // 0..4 survivors in this lane
-            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, n & 1), b1 = __ballot_sync(0xFFFFFFFFu, n & 2), b2 = __ballot_sync(0xFFFFFFFFu, n & 4);
-            if (b0 | b1 | b2) {
-                if (pass) {
-                    int pos = qn + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-                    const uint32_t e0 = ((uint32_t)yy << 16) + (uint32_t)(4 * wi - sx0);
+            const int n = __popc(pass0) + __popc(pass1);  // 0..8 survivors in this lane
+            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, n & 1), b1 = __ballot_sync(0xFFFFFFFFu, n & 2), b2 = __ballot_sync(0xFFFFFFFFu, n & 4),
+                           b3 = __ballot_sync(0xFFFFFFFFu, n & 8);
+            if (b0 | b1 | b2 | b3) {
+                if (n) {
+                    int pos = qn + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+                    const uint32_t e0 = ((uint32_t)yy << (E16 ? 10 : 16)) + (uint32_t)(4 * wi - sx0);
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
-                        if (pass & (0x80u << (8 * b))) wq[pos++] = e0 + b;
+                        if (pass0 & (0x80u << (8 * b))) wq[pos++] = e0 + b;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (pass1 & (0x80u << (8 * b))) wq[pos++] = e0 + 4 + b;
                 }
-                qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
                 __syncwarp();
                 while (qn >= 32) {
                     qn -= 32;
-                    score_pixel(pix, PW, sx0, sy0, wq[qn + lane], thr, sc, SW, nz, NWB);
+                    score_pixel<E16>(pix, PW, sx0, sy0, wq[qn + lane], thr, sc, SW, sink);
                     __syncwarp();
                 }
             }
@@ -144,7 +199,7 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
     }
     __syncthreads();
     const int tn = *tail_n;
-    for (int i = threadIdx.x; i < tn; i += FT) score_pixel(pix, PW, sx0, sy0, tail[i], thr, sc, SW, nz, NWB);
+    for (int i = threadIdx.x; i < tn; i += FT) score_pixel<E16>(pix, PW, sx0, sy0, tail[i], thr, sc, SW, sink);
 }
 
 // bits [x0, x0 + n) (n <= 64) of a bitmap row
@@ -160,17 +215,20 @@ struct FastSmem {
     int PW, PH;  // pixel window pitch (multiple of 16) / rows
     int SW, SH;  // score map pitch / rows (1-px zero frame)
     int NWB;     // bitmap words per row (+3 slack words so that row_bits may read past the end)
-    int MC, CH;  // max cells per tile, max rows per cell
-    // the per-(cell,row) keep masks alias the pixel window, which is dead once the scores exist
-    __host__ __device__ size_t mask_bytes() const { return (size_t)MC * CH * 2 * sizeof(unsigned long long); }
-    __host__ __device__ size_t pix_bytes() const { return ((size_t)PW * PH > mask_bytes() ? (size_t)PW * PH : mask_bytes() + 15) & ~(size_t)15; }
+    int MC;      // max cells per tile
+    int LCAP;    // corner list capacity (entries)
+    // the two keep bitmaps (all / strong survivors of the suppression) alias the pixel window, which is dead once the scores exist
+    __host__ __device__ size_t keep_bytes() const { return (size_t)2 * NWB * SH * sizeof(uint32_t); }
+    __host__ __device__ size_t pix_bytes() const { return ((size_t)PW * PH > keep_bytes() ? (size_t)PW * PH : keep_bytes() + 15) & ~(size_t)15; }
     __host__ __device__ size_t sc_off() const { return pix_bytes(); }
-    __host__ __device__ size_t nz_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
-    __host__ __device__ size_t cell_off() const { return nz_off() + (((size_t)NWB * SH * 4 + 15) & ~(size_t)15); }
-    __host__ __device__ size_t queue_off() const { return cell_off() + (size_t)(3 * MC + 4) * sizeof(int); }
-    __host__ __device__ size_t total() const { return queue_off() + (size_t)(FW * QCAP + 4 + FW * 32) * sizeof(uint32_t); }
+    __host__ __device__ size_t cell_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
+    __host__ __device__ size_t list_off() const { return cell_off() + (size_t)(3 * MC + 4) * sizeof(int); }
+    __host__ __device__ size_t queue_off() const { return list_off() + (((size_t)LCAP * 2 + 15) & ~(size_t)15); }
+    __host__ __device__ size_t tail_off() const { return queue_off() + (((size_t)FW * QCAP * 2 + 15) & ~(size_t)15); }
+    __host__ __device__ size_t total() const { return tail_off() + (size_t)(4 + FW * 32) * sizeof(uint32_t); }
 };
 
+template <bool POW2>
 __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const FastTile* __restrict__ tiles, FastSmem L,
                                                    uint32_t* __restrict__ tile_buf, int* __restrict__ tile_cnt, int* __restrict__ flags,
                                                    uint32_t tile_buf_per_slot, int n_tiles) {
@@ -180,57 +238,63 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
     const LevelGeom& G = g.lvl[t.level];
     uint8_t* pix = smem;
     uint8_t* sc = smem + L.sc_off();
-    uint32_t* nz = reinterpret_cast<uint32_t*>(smem + L.nz_off());
-    unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem);  // [cell][row][all, strong]; aliases pix after the score stage
-    int* cellflag = reinterpret_cast<int*>(smem + L.cell_off());
+    uint32_t* keepAll = reinterpret_cast<uint32_t*>(smem);  // [row + 1][NWB]; aliases pix after the score stage
+    uint32_t* keepStr = keepAll + L.NWB * L.SH;
+    int* cellflag = reinterpret_cast<int*>(smem + L.cell_off());  // [MC] flag, [MC] cntAll, [MC] cntStr, [0] list counter
     int* cntAll = cellflag + L.MC;
     int* cntStr = cntAll + L.MC;
-    uint32_t* queues = reinterpret_cast<uint32_t*>(smem + L.queue_off());
+    int* list_n = cntStr + L.MC;
+    uint16_t* list = reinterpret_cast<uint16_t*>(smem + L.list_off());
+    uint16_t* queues = reinterpret_cast<uint16_t*>(smem + L.queue_off());
+    uint32_t* tailq = reinterpret_cast<uint32_t*>(smem + L.tail_off());
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int tw = t.x1 - t.x0, th = t.y1 - t.y0;
     const int xa = (t.x0 - 3) & ~15;
     const int nchunk = (t.x1 + 3 - xa + 15) >> 4;
     load_window(G.base + (size_t)slot * G.plane, G.pitch, xa, t.y0 - 3, th + 6, nchunk, pix, L.PW);
-    {  // zero the score map, the bitmap and the per-cell counters (contiguous regions up to mask_off, then the cell block)
+    {  // zero the score map and the per-cell counters (one contiguous region)
         uint4* z = reinterpret_cast<uint4*>(sc);
-        const int nz16 = (int)((L.cell_off() - L.sc_off()) >> 4);
+        const int nz16 = (int)((L.list_off() - L.sc_off() + 15) >> 4);
         for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = threadIdx.x; i < 3 * L.MC + 4; i += FT) cellflag[i] = 0;
-        if (threadIdx.x == 0) queues[FW * QCAP] = 0;
+        if (threadIdx.x == 0) tailq[0] = 0;
     }
     __syncthreads();
 
-    score_region(pix, L.PW, t.x0 - xa, 3, tw, th, g.minTh, sc, L.SW, nz, L.NWB, queues + warp * QCAP, queues + FW * QCAP);
+    const CornerSink sink{nullptr, 0, list, list_n, L.LCAP};
+    score_region<POW2, true>(pix, L.PW, t.x0 - xa, 3, tw, th, g.minTh, sc, L.SW, sink, queues + warp * QCAP, tailq);
+    __syncthreads();
+    {  // the pixel window is dead: clear the keep bitmaps that alias it
+        uint32_t* z = keepAll;
+        const int nw = 2 * L.NWB * L.SH;
+        for (int i = threadIdx.x; i < nw; i += FT) z[i] = 0;
+    }
     __syncthreads();
 
-    // ---- one thread per (cell, row): non-maximum suppression clipped to the cell, per-cell threshold statistics
-    const int wCell = G.wCell, nitems = t.ncells * th;
-    for (int it = threadIdx.x; it < nitems; it += FT) {
-        const int cidx = it / th, ly = it - cidx * th;
-        const int cx0 = cidx * wCell, cw = min(cx0 + wCell, tw) - cx0;
-        unsigned long long m = row_bits(nz + (ly + 1) * L.NWB, cx0, cw), all = 0, strong = 0;
-        const uint8_t* s1 = sc + (size_t)(ly + 1) * L.SW + cx0 + 1;
-        while (m) {
-            const int lx = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            const int s = s1[lx];
-            const uint8_t* s0 = s1 - L.SW;
-            const uint8_t* s2 = s1 + L.SW;
-            bool keep = s > s0[lx] && s > s2[lx];
-            if (lx > 0) keep = keep && s > s0[lx - 1] && s > s1[lx - 1] && s > s2[lx - 1];
-            if (lx < cw - 1) keep = keep && s > s0[lx + 1] && s > s1[lx + 1] && s > s2[lx + 1];
-            if (keep) {
-                all |= 1ull << lx;
-                if (s >= g.iniTh) strong |= 1ull << lx;
+    // ---- one thread per corner: non-maximum suppression clipped to the corner's cell, per-cell threshold statistics
+    const int wCell = G.wCell;
+    const int ncorner = min(*list_n, L.LCAP);
+    const unsigned magic = 0xFFFFFFFFu / (unsigned)wCell + 1u;  // floor(x / wCell) == umulhi(x, magic) for x * wCell < 2^32
+    for (int i = threadIdx.x; i < ncorner; i += FT) {
+        const int e = list[i], ly = e >> 10, x = e & 1023;
+        const int cidx = (int)__umulhi((unsigned)x, magic), cx0 = cidx * wCell, lx = x - cx0, cw = min(cx0 + wCell, tw) - cx0;
+        const uint8_t* s1 = sc + (size_t)(ly + 1) * L.SW + x + 1;
+        const uint8_t* s0 = s1 - L.SW;
+        const uint8_t* s2 = s1 + L.SW;
+        const int s = s1[0];
+        bool keep = s > s0[0] && s > s2[0];
+        if (lx > 0) keep = keep && s > s0[-1] && s > s1[-1] && s > s2[-1];
+        if (lx < cw - 1) keep = keep && s > s0[1] && s > s1[1] && s > s2[1];
+        if (keep) {
+            const int w = (ly + 1) * L.NWB + (x >> 5);
+            const uint32_t bit = 1u << (x & 31);
+            atomicOr(keepAll + w, bit);
+            atomicAdd(&cntAll[cidx], 1);
+            if (s >= g.iniTh) {
+                atomicOr(keepStr + w, bit);
+                atomicAdd(&cntStr[cidx], 1);
+                cellflag[cidx] = 1;
             }
-        }
-        masks[2 * it] = all;
-        masks[2 * it + 1] = strong;
-        if (all) atomicAdd(&cntAll[cidx], __popcll(all));
-        if (strong) {
-            atomicAdd(&cntStr[cidx], __popcll(strong));
-            cellflag[cidx] = 1;
         }
     }
     __syncthreads();
@@ -251,11 +315,12 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
     }
     uint32_t* out = tile_buf + (size_t)slot * tile_buf_per_slot + t.out_off;
     for (int cidx = warp; cidx < t.ncells; cidx += FW) {
-        const int which = cellflag[cidx], cx0 = cidx * wCell;
+        const uint32_t* keep = cellflag[cidx] ? keepStr : keepAll;
+        const int cx0 = cidx * wCell, cw = min(cx0 + wCell, tw) - cx0;
         int run = __shfl_sync(0xFFFFFFFFu, mybase, cidx);
         for (int r0 = 0; r0 < th; r0 += 32) {
             const int ly = r0 + lane;
-            unsigned long long m = ly < th ? masks[2 * (cidx * th + ly) + which] : 0ull;
+            unsigned long long m = ly < th ? row_bits(keep + (ly + 1) * L.NWB, cx0, cw) : 0ull;
             const int c = __popcll(m);
             int incl = c;
 #pragma unroll
@@ -275,7 +340,7 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
     }
     if (threadIdx.x == 0) {
         tile_cnt[(size_t)slot * n_tiles + blockIdx.x] = min(total, t.out_cap);
-        if (total > t.out_cap) atomicOr(flags + slot, SVO_FLAG_TILE_OVERFLOW);
+        if (total > t.out_cap || *list_n > L.LCAP) atomicOr(flags + slot, SVO_FLAG_TILE_OVERFLOW);
     }
 }
 
@@ -402,7 +467,8 @@ __global__ void __launch_bounds__(FT) k_fast_full(LevelGeom G, SlotMap map, cons
     __syncthreads();
     // map row of image row y is y - (t.y0 - 1); the score stage writes row (y - ys0) + 1, hence the shift
     const int shift = ys0 - t.y0;
-    score_region(pix, L.PW, t.x0 - xa, 3, tw, nsr, thr, sc + shift * L.SW, L.SW, nz + shift * L.NWB, L.NWB, queues + warp * QCAP, queues + FW * QCAP);
+    const CornerSink sink{nz + shift * L.NWB, L.NWB, nullptr, nullptr, 0};
+    score_region<false, false>(pix, L.PW, t.x0 - xa, 3, tw, nsr, thr, sc + shift * L.SW, L.SW, sink, queues + warp * QCAP, queues + FW * QCAP);
     __syncthreads();
     // ---- one thread per bitmap word of the strip's own rows: 3x3 non-maximum suppression
     const int nck = (tw + 31) >> 5, ni = th * nck;
@@ -533,6 +599,7 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
         StageTimer t(c, 1);
         if (c->n_tiles > 0) {
             FastSmem L{};
+            int max_area = 0;
             for (const FastTile& ft : c->tiles) {
                 const int xa = (ft.x0 - 3) & ~15;
                 L.PW = std::max(L.PW, (int)svo_align(ft.x1 + 3 - xa + 4, 16));
@@ -540,16 +607,19 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
                 L.SW = std::max(L.SW, (int)svo_align(ft.x1 - ft.x0 + 2, 16));
                 L.SH = std::max(L.SH, ft.y1 - ft.y0 + 2);
                 L.NWB = std::max(L.NWB, (ft.x1 - ft.x0 + 31) / 32 + 3);
-                L.CH = std::max(L.CH, ft.y1 - ft.y0);
+                max_area = std::max(max_area, (ft.x1 - ft.x0) * (ft.y1 - ft.y0));
                 if (g.lvl[ft.level].wCell > 64) return c->fail(SVO_ERR_INVALID, "FAST cells wider than 64 px are not supported");
+                if (ft.x1 - ft.x0 > 1024 || ft.y1 - ft.y0 > 64) return c->fail(SVO_ERR_INVALID, "FAST tile larger than 1024 x 64 px");
             }
             L.MC = 32;  // the cell scan is one warp wide
+            L.LCAP = std::max(256, max_area / 2);  // corners (score >= minTh) before suppression; overflow -> SVO_ERR_CAPACITY
             const size_t smem = L.total();
             if (smem > 200 * 1024) return c->fail(SVO_ERR_INVALID, "FAST tile does not fit in shared memory");
-            SVO_CUDA_TRY(c, cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const bool pow2 = g.minTh + 1 <= 128 && ((g.minTh + 1) & g.minTh) == 0;
+            auto kern = pow2 ? k_fast_cells<true> : k_fast_cells<false>;
+            SVO_CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dim3 grid(c->n_tiles, n_img);
-            k_fast_cells<<<grid, FT, smem, c->stream>>>(g, map, c->d_tiles, L, c->d_tile_buf, c->d_tile_cnt, c->d_flags,
-                                                        c->tile_buf_per_slot, c->n_tiles);
+            kern<<<grid, FT, smem, c->stream>>>(g, map, c->d_tiles, L, c->d_tile_buf, c->d_tile_cnt, c->d_flags, c->tile_buf_per_slot, c->n_tiles);
             ++c->launches;
         }
     }

@@ -240,12 +240,18 @@ __global__ void __launch_bounds__(LW * 32, 4) k_lk_track(LkParams P, const svo_k
     if (lane < 32 * NK - NPIX) tmpl[NPIX + lane] = make_uint2(0u, 0u);  // the 7 pad pixels: zero gradient, never rewritten
     // flattened form: lane owns pixels lane + 32 k; offset of the (x, x+1) pair of row y in a tile whose byte 0 is column x = 0
     int offJ[NK];
+    {
+        int y = lane >= WIN ? 1 : 0, x = lane - WIN * y;
 #pragma unroll
-    for (int k = 0; k < NK; ++k) {
-        int idx = lane + 32 * k;
-        if (idx >= NPIX) idx = 0;
-        const int y = idx / WIN, x = idx - WIN * y;
-        offJ[k] = y * TROW + pair_off(x);
+        for (int k = 0; k < NK; ++k) {
+            offJ[k] = lane + 32 * k < NPIX ? y * TROW + pair_off(x) : 0;
+            x += 32 - WIN;  // pixel index + 32 = one row down and 11 columns to the right
+            y += 1;
+            if (x >= WIN) {
+                x -= WIN;
+                y += 1;
+            }
+        }
     }
     const int ccol = min(lane, 23);  // setup: tile column of this lane
 
