@@ -96,7 +96,9 @@ __device__ __forceinline__ void score_pixel(const uint8_t* pix, int PW, int sx0,
         if (bal) {
             const int lane = threadIdx.x & 31, leader = __ffs((int)bal) - 1;
             int base = 0;
-            if (lane == leader) base = atomicAdd(sink.list_n, __popc(bal));
+            // plain PTX atomic: the aggregation is already done by hand (nvcc would wrap atomicAdd in its own MATCH / REDUX pass)
+            if (lane == leader)
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"((uint32_t)__cvta_generic_to_shared(sink.list_n)), "r"(__popc(bal)) : "memory");
             base = __shfl_sync(act, base, leader);
             const int o = base + __popc(bal & ((1u << lane) - 1));
             if (hit && o < sink.list_cap) sink.list[o] = (uint16_t)((ey << 10) | ex);

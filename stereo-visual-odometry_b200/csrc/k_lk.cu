@@ -15,6 +15,7 @@
 //
 // f32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) to follow OpenCV's scalar expressions.
 #include <cfloat>
+#include <climits>
 
 #include "svo_common.cuh"
 
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(LW * 32, 4) k_lk_track(LkParams P, const svo_k
         ny = __fsub_rn(ny, half);
         float pdx = 0.f, pdy = 0.f;
         const uint2* tl = tmpl + lane;
+        int tx = INT_MIN, ty = INT_MIN;  // origin of the staged next-image tile (none yet: the tile holds the previous image)
         for (int j = 0; j < P.max_iter; ++j) {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
             if (inx < -WIN || inx >= G.w || iny < -WIN || iny >= G.h) {
@@ -389,9 +391,13 @@ __global__ void __launch_bounds__(LW * 32, 4) k_lk_track(LkParams P, const svo_k
             weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
             Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16);
             Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
-            __syncwarp();  // the previous tile (and, in the first iteration, the template stores) are complete
-            stage_tile(tile, J, G.pitch, inx, iny, lane);
-            __syncwarp();
+            if (inx != tx || iny != ty) {  // sub-pixel steps usually stay in the same integer cell: the staged tile is still valid
+                __syncwarp();              // the previous tile (and, in the first iteration, the template stores) are complete
+                stage_tile(tile, J, G.pitch, inx, iny, lane);
+                __syncwarp();
+                tx = inx;
+                ty = iny;
+            }
             int b1 = 0, b2 = 0;
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
@@ -430,9 +436,11 @@ __global__ void __launch_bounds__(LW * 32, 4) k_lk_track(LkParams P, const svo_k
                 weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), iw00, iw01, iw10, iw11);
                 Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16);
                 Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
-                __syncwarp();
-                stage_tile(tile, J, G.pitch, inx, iny, lane);
-                __syncwarp();
+                if (inx != tx || iny != ty) {
+                    __syncwarp();
+                    stage_tile(tile, J, G.pitch, inx, iny, lane);
+                    __syncwarp();
+                }
                 int e = 0;
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
