@@ -214,6 +214,8 @@ def run_b200(a):
         bpi = algorithmic_bytes_per_image(w, h)
         t_pf = stage["pyramid"] + stage["fast_cells"] + stage["compact"]
         achieved = bpi * 2 * B / (t_pf * 1e-3) / 1e9 if t_pf > 0 else None
+        t_lk = sum(stage[f"lk_track{i}"] for i in (1, 2, 3, 4))
+        tracks = 4 * int(np.sum(out.n_seed))  # points handed to each of the 4 calls in the last e2e step
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -233,6 +235,12 @@ def run_b200(a):
                          "kernels": "K1 k_pyramid_fused (one-pass, TMA-staged) + K2 k_fast_cells + K2b k_compact (pyramid + FAST stages)",
                          "algorithmic_bytes_per_launch": bpi * 2 * B, "ms_per_launch": t_pf},
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage.items()},
+            # the kernel with the largest share of the step is the LK tracker; it is bound by instruction issue and the
+            # shared-memory pipe, not by HBM or tensor throughput (profiles/*_ncu_full_all_kernels.txt), so it is reported as
+            # tracks/s next to the HBM roofline of the pyramid + FAST stages that north_star asks for
+            "dominant_kernel": {"name": "K8 k_lk_track (4 launches per step)", "ms_per_step": round(t_lk, 4), "share_of_step": round(t_lk / (ms_dev / K), 3),
+                                "tracks_per_step": tracks, "tracks_per_s": tracks / (t_lk * 1e-3) if t_lk > 0 else None,
+                                "bound": "instruction issue + shared-memory pipe (integer; no HBM or tensor bound)"},
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
