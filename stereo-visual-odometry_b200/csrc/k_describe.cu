@@ -17,7 +17,7 @@ namespace {
 constexpr int DW = 4;            // warps (keypoints) per CTA
 constexpr int PR = 21;           // source patch radius: 18 (max rotated tap) + 3 (blur)
 constexpr int PS = 2 * PR + 1;   // 43
-constexpr int PP = 48;           // patch pitch in bytes (12 words; the horizontal pass reads words 0..11)
+constexpr int PP = 52;           // patch pitch in bytes: 13 words (odd), so that a column of words is bank-conflict free; words 0..11 are read
 constexpr int BR = 18;           // blurred patch radius
 constexpr int HC = 40;           // columns of the horizontal pass (37 needed, 10 words x 4)
 constexpr int HP = 46;           // pitch (u16 units, even) of the TRANSPOSED horizontal-pass array hT[col][row]
@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
     uint16_t* hT = s_hT[warp];
     {
         const uint32_t K0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), K1 = 48u | (34u << 8) | (18u << 16);
+        // lanes take consecutive ROWS of one word column: the patch reads (pitch 13 words) and the transposed u16 stores
+        // (consecutive rows of one output column) are then free of bank conflicts
         for (int it = lane; it < PS * (HC / 4); it += 32) {
-            const int r = it / (HC / 4), j = it - r * (HC / 4);
+            const int j = it / PS, r = it - j * PS;
             const uint32_t* w = reinterpret_cast<const uint32_t*>(patch + r * PP) + j;
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
             uint16_t* o = hT + (4 * j) * HP + r;
