@@ -142,8 +142,8 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
     const int w0e = w0 & ~1;
     const uint32_t m_first = 0x80808080u << (8 * (sx0 & 3));                  // bytes >= sx0 of word w0
     const uint32_t m_last = 0x80808080u >> (8 * (3 - ((sx0 + sw - 1) & 3)));  // bytes <= last column of word w1
-    const uint32_t lt = (1u << lane) - 1;
-    int qn = 0;
+    volatile int* wcnt = reinterpret_cast<volatile int*>(tail_q) + 4 + warp;  // this warp's queue fill (zeroed by the caller)
+    const uint32_t wcnt_addr = (uint32_t)__cvta_generic_to_shared(const_cast<int*>(wcnt));
     for (int yy = warp; yy < sh; yy += FW) {
         const uint32_t* row = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy) * PW);
         const uint32_t* rup = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy - 3) * PW);
@@ -166,33 +166,38 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
                     if (wi + 1 > w1) pass1 = 0;
                 }
             }
+            // survivors -> the warp's queue.  The kernel is bound by instruction issue, not by the shared-memory pipe, so the
+            // slot comes from ONE shared-memory atomic per lane with survivors (order inside the queue is irrelevant) instead
+            // of a ballot / popc prefix; plain PTX so that nvcc does not wrap it in its own MATCH / REDUX aggregation.
             const int n = __popc(pass0) + __popc(pass1);  // 0..8 survivors in this lane
-            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, n & 1), b1 = __ballot_sync(0xFFFFFFFFu, n & 2), b2 = __ballot_sync(0xFFFFFFFFu, n & 4),
-                           b3 = __ballot_sync(0xFFFFFFFFu, n & 8);
-            if (b0 | b1 | b2 | b3) {
-                if (n) {
-                    int pos = qn + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
-                    const uint32_t e0 = ((uint32_t)yy << (E16 ? 10 : 16)) + (uint32_t)(4 * wi - sx0);
+            if (n) {
+                uint32_t pos;
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(pos) : "r"(wcnt_addr), "r"(n) : "memory");
+                const uint32_t e0 = ((uint32_t)yy << (E16 ? 10 : 16)) + (uint32_t)(4 * wi - sx0);
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (pass0 & (0x80u << (8 * b))) wq[pos++] = e0 + b;
+                for (int b = 0; b < 4; ++b)
+                    if (pass0 & (0x80u << (8 * b))) wq[pos++] = e0 + b;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (pass1 & (0x80u << (8 * b))) wq[pos++] = e0 + 4 + b;
-                }
-                qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
-                __syncwarp();
-                while (qn >= 32) {
+                for (int b = 0; b < 4; ++b)
+                    if (pass1 & (0x80u << (8 * b))) wq[pos++] = e0 + 4 + b;
+            }
+            __syncwarp();
+            int qn = *wcnt;
+            if (qn >= 32) {
+                do {
                     qn -= 32;
                     score_pixel<E16>(pix, PW, sx0, sy0, wq[qn + lane], thr, sc, SW, sink);
-                    __syncwarp();
-                }
+                } while (qn >= 32);
+                __syncwarp();
+                if (lane == 0) *wcnt = qn;
+                __syncwarp();
             }
         }
     }
+    const int qn = *wcnt;
     // leftovers (< 32 per warp) are pooled in the first warp's queue area and scored by full warps after a barrier
     int* tail_n = reinterpret_cast<int*>(tail_q);
-    uint32_t* tail = tail_q + 4;
+    uint32_t* tail = tail_q + 4 + FW;
     if (qn) {
         int base = 0;
         if (lane == 0) base = atomicAdd(tail_n, qn);
@@ -227,7 +232,7 @@ struct FastSmem {
     __host__ __device__ size_t list_off() const { return cell_off() + (size_t)(3 * MC + 4) * sizeof(int); }
     __host__ __device__ size_t queue_off() const { return list_off() + (((size_t)LCAP * 2 + 15) & ~(size_t)15); }
     __host__ __device__ size_t tail_off() const { return queue_off() + (((size_t)FW * QCAP * 2 + 15) & ~(size_t)15); }
-    __host__ __device__ size_t total() const { return tail_off() + (size_t)(4 + FW * 32) * sizeof(uint32_t); }
+    __host__ __device__ size_t total() const { return tail_off() + (size_t)(4 + FW + FW * 32) * sizeof(uint32_t); }
 };
 
 template <bool POW2>
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const
         uint4* z = reinterpret_cast<uint4*>(sc);
         const int nz16 = (int)((L.list_off() - L.sc_off() + 15) >> 4);
         for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) tailq[0] = 0;
+        if (threadIdx.x < 4 + FW) tailq[threadIdx.x] = 0;  // pooled-leftover counter and the per-warp queue fills
     }
     __syncthreads();
 
@@ -407,7 +412,7 @@ struct FullSmem {
     __host__ __device__ size_t nz_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
     __host__ __device__ size_t item_off() const { return nz_off() + (((size_t)NWB * SH * 4 + 15) & ~(size_t)15); }
     __host__ __device__ size_t queue_off() const { return item_off() + (size_t)(2 * NI + 16) * sizeof(int); }
-    __host__ __device__ size_t total() const { return queue_off() + (size_t)(FW * QCAP + 4 + FW * 32) * sizeof(uint32_t); }
+    __host__ __device__ size_t total() const { return queue_off() + (size_t)(FW * QCAP + 4 + FW + FW * 32) * sizeof(uint32_t); }
 };
 
 __device__ int block_scan_excl_ft(int* a, int n, int* wtmp) {  // in-place exclusive scan, all FT threads call
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(FT) k_fast_full(LevelGeom G, SlotMap map, cons
         uint4* z = reinterpret_cast<uint4*>(sc);
         const int nz16 = (int)((L.item_off() - L.sc_off()) >> 4);
         for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) queues[FW * QCAP] = 0;
+        if (threadIdx.x < 4 + FW) queues[FW * QCAP + threadIdx.x] = 0;  // pooled-leftover counter and the per-warp queue fills
     }
     __syncthreads();
     // map row of image row y is y - (t.y0 - 1); the score stage writes row (y - ys0) + 1, hence the shift

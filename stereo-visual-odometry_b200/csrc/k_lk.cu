@@ -117,29 +117,18 @@ __global__ void __launch_bounds__(128) k_lk_pad(LkPadParams P, SlotMap map) {
     const int ry = reflect101_any(yp, D.h);
     uint8_t* drow = D.base + (size_t)slot * D.plane + (ptrdiff_t)yp * D.pitch;
     const bool yin = yp >= 0 && yp < D.h;
-    if (l == 0) {
-        const uint8_t* __restrict__ srow = P.src0.base + (size_t)slot * P.src0.plane + (size_t)ry * P.src0.pitch;
-        for (int x = -SVO_LK_PADX + 4 * (int)threadIdx.x; x < D.w + SVO_LK_PADX; x += 4 * 128) {
-            uint32_t v;
-            if (x >= 0 && x + 3 < D.w) {
-                v = __ldg(reinterpret_cast<const uint32_t*>(srow + x));
-            } else {
-                v = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v |= (uint32_t)__ldg(srow + reflect101_any(x + i, D.w)) << (8 * i);
-            }
-            *reinterpret_cast<uint32_t*>(drow + x) = v;
-        }
-    } else {
-        const uint8_t* srow = D.base + (size_t)slot * D.plane + (ptrdiff_t)ry * D.pitch;
-        if (yin) {  // left / right pads only
-            for (int i = threadIdx.x; i < 2 * SVO_LK_PADX; i += 128) {
-                const int x = i < SVO_LK_PADX ? i - SVO_LK_PADX : D.w + i - SVO_LK_PADX;
-                drow[x] = srow[reflect101_any(x, D.w)];
-            }
-        } else {
-            for (int x = -SVO_LK_PADX + (int)threadIdx.x; x < D.w + SVO_LK_PADX; x += 128) drow[x] = srow[reflect101_any(x, D.w)];
-        }
+    // source row: level 0 comes from the (unpadded) ORB plane, the other levels from their own interior
+    const uint8_t* __restrict__ srow = l == 0 ? P.src0.base + (size_t)slot * P.src0.plane + (size_t)ry * P.src0.pitch
+                                              : D.base + (size_t)slot * D.plane + (ptrdiff_t)ry * D.pitch;
+    if (l == 0 || !yin) {  // interior columns: 16-byte copies (both rows are 16-byte aligned), then the ragged end
+        const int nv = D.w >> 4;
+        for (int v = threadIdx.x; v < nv; v += 128) reinterpret_cast<uint4*>(drow)[v] = __ldg(reinterpret_cast<const uint4*>(srow) + v);
+        for (int x = (nv << 4) + (int)threadIdx.x; x < D.w; x += 128) drow[x] = __ldg(srow + x);
+    }
+    // left / right pads
+    for (int i = threadIdx.x; i < 2 * SVO_LK_PADX; i += 128) {
+        const int x = i < SVO_LK_PADX ? i - SVO_LK_PADX : D.w + i - SVO_LK_PADX;
+        drow[x] = __ldg(srow + reflect101_any(x, D.w));
     }
 }
 
