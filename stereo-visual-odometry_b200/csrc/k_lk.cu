@@ -99,7 +99,7 @@ struct LkParams {
 struct LkPadParams {
     LkLevelGeom src0;               // unpadded level 0
     LkLevelGeom lv[SVO_LK_LEVELS];  // padded planes (base = interior origin)
-    int row0[SVO_LK_LEVELS + 1];    // first CTA row of every level (padded rows are h + 2 * PADY)
+    int row0[SVO_LK_LEVELS + 1];    // first CTA of every level (a CTA handles PAD_ROWS of the h + 2 * PADY padded rows)
     int levels;
 };
 
@@ -108,27 +108,57 @@ __device__ __forceinline__ int reflect101_any(int i, int n) {
     return i;
 }
 
+constexpr int PAD_ROWS = 8;  // padded rows per CTA of k_lk_pad
+
 __global__ void __launch_bounds__(128) k_lk_pad(LkPadParams P, SlotMap map) {
+    // P.row0[] counts CTAs here: level l owns CTAs [row0[l], row0[l+1]), each PAD_ROWS consecutive padded rows
     int l = 0;
     while (l + 1 < P.levels && (int)blockIdx.x >= P.row0[l + 1]) ++l;
     const LkLevelGeom& D = P.lv[l];
     const int slot = map.slot(blockIdx.y);
-    const int yp = (int)blockIdx.x - P.row0[l] - SVO_LK_PADY;  // padded row, interior coordinates
-    const int ry = reflect101_any(yp, D.h);
-    uint8_t* drow = D.base + (size_t)slot * D.plane + (ptrdiff_t)yp * D.pitch;
-    const bool yin = yp >= 0 && yp < D.h;
-    // source row: level 0 comes from the (unpadded) ORB plane, the other levels from their own interior
-    const uint8_t* __restrict__ srow = l == 0 ? P.src0.base + (size_t)slot * P.src0.plane + (size_t)ry * P.src0.pitch
-                                              : D.base + (size_t)slot * D.plane + (ptrdiff_t)ry * D.pitch;
-    if (l == 0 || !yin) {  // interior columns: 16-byte copies (both rows are 16-byte aligned), then the ragged end
-        const int nv = D.w >> 4;
-        for (int v = threadIdx.x; v < nv; v += 128) reinterpret_cast<uint4*>(drow)[v] = __ldg(reinterpret_cast<const uint4*>(srow) + v);
-        for (int x = (nv << 4) + (int)threadIdx.x; x < D.w; x += 128) drow[x] = __ldg(srow + x);
+    const int r0 = ((int)blockIdx.x - P.row0[l]) * PAD_ROWS - SVO_LK_PADY;  // first padded row, interior coordinates
+    const int nrows = min(PAD_ROWS, D.h + SVO_LK_PADY - r0);
+    uint8_t* dbase = D.base + (size_t)slot * D.plane;
+    // source: level 0 comes from the (unpadded) ORB plane, the other levels from their own interior
+    const uint8_t* __restrict__ sbase = l == 0 ? P.src0.base + (size_t)slot * P.src0.plane : dbase;
+    const int spitch = l == 0 ? P.src0.pitch : D.pitch;
+    // ---- interior columns of the rows that need them (all rows of level 0, the top / bottom border rows of the others):
+    //      16-byte copies (rows are 16-byte aligned), four independent loads in flight per thread
+    const int nv = D.w >> 4, items = nrows * nv;
+    for (int i0 = threadIdx.x; i0 < items; i0 += 4 * 128) {
+        uint4 v[4];
+        int off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 128;
+            off[u] = -1;
+            if (i < items) {
+                const int rr = i / nv, c = i - rr * nv, yp = r0 + rr;
+                if (l == 0 || yp < 0 || yp >= D.h) {
+                    v[u] = __ldg(reinterpret_cast<const uint4*>(sbase + (ptrdiff_t)reflect101_any(yp, D.h) * spitch) + c);
+                    off[u] = rr * nv + c;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (off[u] >= 0) {
+                const int rr = off[u] / nv, c = off[u] - rr * nv;
+                reinterpret_cast<uint4*>(dbase + (ptrdiff_t)(r0 + rr) * D.pitch)[c] = v[u];
+            }
     }
-    // left / right pads
-    for (int i = threadIdx.x; i < 2 * SVO_LK_PADX; i += 128) {
-        const int x = i < SVO_LK_PADX ? i - SVO_LK_PADX : D.w + i - SVO_LK_PADX;
-        drow[x] = __ldg(srow + reflect101_any(x, D.w));
+    // ---- ragged end of the interior (w % 16 bytes) and the left / right pads, byte-wise
+    const int tailw = D.w & 15, per = 2 * SVO_LK_PADX + tailw;
+    for (int i = threadIdx.x; i < nrows * per; i += 128) {
+        const int rr = i / per, k = i - rr * per, yp = r0 + rr;
+        int x;
+        if (k < SVO_LK_PADX) x = k - SVO_LK_PADX;
+        else if (k < 2 * SVO_LK_PADX) x = D.w + k - SVO_LK_PADX;
+        else {
+            x = (nv << 4) + k - 2 * SVO_LK_PADX;
+            if (!(l == 0 || yp < 0 || yp >= D.h)) continue;  // interior rows of levels >= 1 already hold their pixels
+        }
+        dbase[(ptrdiff_t)yp * D.pitch + x] = __ldg(sbase + (ptrdiff_t)reflect101_any(yp, D.h) * spitch + reflect101_any(x, D.w));
     }
 }
 
@@ -468,7 +498,7 @@ int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
     P.row0[0] = 0;
     for (int l = 0; l < c->lk_levels; ++l) {
         if (l) P.lv[l] = c->lk[l];
-        P.row0[l + 1] = P.row0[l] + P.lv[l].h + 2 * SVO_LK_PADY;
+        P.row0[l + 1] = P.row0[l] + (P.lv[l].h + 2 * SVO_LK_PADY + PAD_ROWS - 1) / PAD_ROWS;
     }
     k_lk_pad<<<dim3(P.row0[c->lk_levels], n_img), 128, 0, c->stream>>>(P, map);
     ++c->launches;
