@@ -287,7 +287,7 @@ def main():
     p.add_argument("--steps", type=int, default=50)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
+    p.add_argument("--frames", type=int, default=128, help="stereo frames per step per GPU")
     p.add_argument("--width", type=int, default=1241)
     p.add_argument("--height", type=int, default=376)
     p.add_argument("--nfeatures", type=int, default=1000)

@@ -37,6 +37,27 @@ def test_random_geometries_match_oracle(pkg, orc):
         ctx.close()
 
 
+@pytest.mark.parametrize("ini_th,min_th", [(20, 7), (30, 10), (12, 5), (40, 15), (9, 3), (7, 7), (100, 31)])
+def test_fast_threshold_pairs_match_oracle(pkg, orc, ini_th, min_th):
+    """iniThFAST / minThFAST other than the reference's defaults: minTh + 1 a power of two (OR-combined pre-test) or not
+    (per-difference pre-test), equal thresholds, and a high pair that leaves most cells empty."""
+    w, h = 752, 480
+    left, _ = pkg.synth_stereo_frame(4242, 3, w, h)
+    ctx = pkg.Context(0, w, h, 1)
+    ctx.orb_configure(800, 1.2, 6, ini_th, min_th)
+    k, d = ctx.orb_extract(left)
+    o = orc.OrbOracle(800, 1.2, 6, ini_th, min_th)
+    ok, od = o.extract(left)
+    for l in range(6):
+        g, c = ctx.orb_read_candidates(0, l), o.candidates(l)
+        assert len(g) == len(c), (l, len(g), len(c))
+        for f in ("x", "y", "response"):
+            assert np.array_equal(g[f], c[f]), (l, f)
+    assert len(k) == len(ok) and np.array_equal(k, ok)
+    assert np.unpackbits(d ^ od).sum() <= 2
+    ctx.close()
+
+
 def test_shard_equivalence(pkg):
     """Frames split over 2 'ranks' with a one-frame overlap give exactly the units of the unsharded run (no collective)."""
     sh = importlib.import_module("svo_b200.sharding")
