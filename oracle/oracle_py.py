@@ -195,6 +195,77 @@ class OrbOracle:
         return {"rounds": r.value, "break_in_tie_group": t.value}
 
 
+# ---- the reference's own ORBextractor.cpp, compiled where it lies against oracle/ref_shim (oracle/Makefile, target `ref`) ----
+_REF = None
+REF_SRC = "/root/reference/src/ORBextractor.cpp"
+
+
+def build_ref(force=False):
+    """oracle/_ref/liborb_ref.so, or None where neither the prebuilt library nor /root/reference exists (e.g. a GPU box
+    that received no prebuilt copy).  Never reads /root/reference at run time once the library is built."""
+    so = os.path.join(_HERE, "_ref", "liborb_ref.so")
+    if os.path.exists(REF_SRC):
+        deps = [REF_SRC] + [os.path.join(_HERE, f) for f in ("ref_capi.cpp", "ref_shim/shim_cv.hpp", "oracle_prims.cpp", "Makefile")]
+        if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return so if os.path.exists(so) else None
+
+
+def ref_lib():
+    global _REF
+    if _REF is None:
+        so = build_ref()
+        if so is None:
+            return None
+        L = C.CDLL(so)
+        L.ref_orb_create.restype = C.c_void_p
+        L.ref_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_orb_destroy.argtypes = [C.c_void_p]
+        L.ref_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_orb_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.ref_set_allocator.restype = C.c_size_t
+        L.ref_set_allocator.argtypes = [C.c_int]
+        _REF = L
+    return _REF
+
+
+class RefOrb:
+    """lzb_vio::ORBextractor as compiled from the reference's source.  monotone=True serves the library's allocations from
+    a bump arena (addresses grow with creation order): the allocator under which the octree's pointer tie-break
+    (ORBextractor.cpp:636) is reproducible; monotone=False uses the system malloc (heap-history dependent)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, monotone=True):
+        self.L = ref_lib()
+        assert self.L is not None, "oracle/_ref/liborb_ref.so is not available"
+        self.monotone, self.nfeatures, self.nlevels = monotone, nfeatures, nlevels
+        self.L.ref_set_allocator(1 if monotone else 0)
+        self._h = self.L.ref_orb_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.L.ref_set_allocator(0)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_orb_destroy(self._h)
+            self._h = None
+
+    def extract(self, img):
+        img = _img(img)
+        cap = self.nfeatures + 64 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        self.L.ref_set_allocator(1 if self.monotone else 0)
+        n = self.L.ref_orb_extract(C.c_void_p(self._h), _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+        self.L.ref_set_allocator(0)
+        assert 0 <= n <= cap, n
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l):
+        w, h = C.c_int(), C.c_int()
+        assert self.L.ref_orb_level(C.c_void_p(self._h), l, None, 0, C.byref(w), C.byref(h)) == 0
+        out = np.empty((h.value, w.value), np.uint8)
+        self.L.ref_orb_level(C.c_void_p(self._h), l, _p(out), out.strides[0], C.byref(w), C.byref(h))
+        return out
+
+
 def orb_match_filter(idx1, dist1, idx2, dist2, n_last_right, n_cur_left, last_left, last_right, fme=3.0):
     n = len(idx1)
     acc = np.zeros((max(n, 1), 3), np.int32)

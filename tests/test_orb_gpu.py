@@ -133,3 +133,29 @@ def test_match_real_descriptors(pkg, orc):
     dx = kl["x"][good] - kr["x"][gi[good]]
     assert good.sum() > 300 and np.median(dx) == pytest.approx(8.0, abs=1.0)
     ctx.close()
+
+
+def test_cuda_equals_reference_source_vectors(pkg, orc):
+    """The CUDA path against outputs of the REFERENCE'S OWN ORBextractor.cpp (compiled against oracle/ref_shim, monotone
+    allocator; tests/golden/ref_orbextractor.npz made by oracle/make_golden_ref.py) and, where oracle/_ref is present, against
+    that library live: keypoints bit-exact in order with all fields, descriptors within 2 bits per image."""
+    import ast
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_orbextractor.npz"))
+    live = orc.ref_lib() is not None
+    for case in gold["cases"]:
+        key, seed, frame, w, h, nf, sf, nl, ini, mn = ast.literal_eval(str(case))
+        img, _ = pkg.synth_stereo_frame(seed, frame, w, h)
+        ctx = pkg.Context(0, w, h, 1)
+        ctx.orb_configure(nf, sf, nl, ini, mn)
+        k, d = ctx.orb_extract(img)
+        refs = [(gold[key + "_kps"], gold[key + "_desc"])]
+        if live:
+            refs.append(orc.RefOrb(nf, sf, nl, ini, mn, monotone=True).extract(img))
+        for rk, rd in refs:
+            assert len(k) == len(rk)
+            for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+                assert np.array_equal(k[f], rk[f]), (key, f)
+            assert int(np.unpackbits(d ^ rd).sum()) <= 2, key
+        ctx.close()
+    print("reference library live:", live)
