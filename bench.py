@@ -271,12 +271,15 @@ def run_reference(a):
         total += dt
     pool.close()
     v = a.steps * units / total
+    kind = ref_pipeline.orb_kind()
+    orb_desc = ("the reference's own src/ORBextractor.cpp compiled into oracle/_ref (its OpenCV calls served by cv2-pinned restatements)"
+                if kind == "reference" else "C++ oracle port of ORBextractor (AVX2 -O3)")
     sample = (f"{units} consecutive stereo frames of the same synthetic sequence per step, split over {pool.workers} worker processes "
-              f"(1 OpenCV thread each); cv2 4.13 FAST/BFMatcher/calcOpticalFlowPyrLK + C++ oracle port of ORBextractor (AVX2 -O3)")
+              f"(1 OpenCV thread each); cv2 4.13 FAST/BFMatcher/calcOpticalFlowPyrLK + {orb_desc}")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "stereo pairs/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": total / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": workload_config(a),
-            "cpu_baseline": {"value": v, "unit": "stereo pairs/s", "cores": pool.workers, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "stereo pairs/s", "cores": pool.workers, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "stereo pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

@@ -121,6 +121,23 @@ void fast9_detect(const Image& roi, int threshold, bool nms, std::vector<KeyPoin
             const int v = c[0], st = (int)roi.stride;
             if (std::abs(v - c[3 * st]) <= threshold && std::abs(v - c[-3 * st]) <= threshold) continue;
             if (std::abs(v - c[3]) <= threshold && std::abs(v - c[-3]) <= threshold) continue;
+            // segment test at this threshold on the 16-bit ring masks (9 contiguous set bits of the doubled mask); the exact
+            // score is only computed for pixels that pass, like cv::FAST does
+            uint32_t mb = 0, md = 0;
+            for (int k = 0; k < 16; ++k) {
+                const int dd = v - c[(ptrdiff_t)kRingDy[k] * st + kRingDx[k]];
+                mb |= (uint32_t)(dd < -threshold) << k;
+                md |= (uint32_t)(dd > threshold) << k;
+            }
+            auto run9 = [](uint32_t m) {
+                uint32_t x = m | (m << 16);
+                x &= x >> 1;
+                x &= x >> 2;
+                x &= x >> 4;
+                x &= x >> 1;
+                return x != 0;
+            };
+            if (!run9(mb) && !run9(md)) continue;
             int s = fast9_score(c, roi.stride);
             if (s >= threshold) {
                 is_corner[(size_t)y * w + x] = 1;
@@ -149,23 +166,35 @@ void fast9_detect(const Image& roi, int threshold, bool nms, std::vector<KeyPoin
 // site ORBextractor.cpp:1035.  Exact 2-D integer convolution with k=[18,34,48,56,48,34,18]/256 per axis.
 // ---------------------------------------------------------------------------------------------------------------
 void gaussian_blur7_sigma2(const Image& src, uint8_t* dst, size_t dstride) {
+    // separable form of the exact 2-D integer convolution: the horizontal sums (<= 255 * 256) are kept unrounded in 16 bits,
+    // the vertical pass rounds once.  Interior loops carry no border logic so that the compiler vectorises them.
     static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
     const int w = src.w, h = src.h;
-    std::vector<uint32_t> hrow((size_t)w * h);
+    std::vector<uint16_t> hrow((size_t)w * h);
     for (int y = 0; y < h; ++y) {
         const uint8_t* S = src.data + (size_t)y * src.stride;
-        for (int x = 0; x < w; ++x) {
+        uint16_t* H = hrow.data() + (size_t)y * w;
+        auto edge = [&](int x) {
             uint32_t acc = 0;
             for (int j = 0; j < 7; ++j) acc += k[j] * S[reflect101(x + j - 3, w)];
-            hrow[(size_t)y * w + x] = acc;
+            H[x] = (uint16_t)acc;
+        };
+        const int x0 = std::min(3, w), x1 = std::max(x0, w - 3);
+        for (int x = 0; x < x0; ++x) edge(x);
+        for (int x = x0; x < x1; ++x)
+            H[x] = (uint16_t)(18 * (S[x - 3] + S[x + 3]) + 34 * (S[x - 2] + S[x + 2]) + 48 * (S[x - 1] + S[x + 1]) + 56 * S[x]);
+        for (int x = x1; x < w; ++x) edge(x);
+    }
+    for (int y = 0; y < h; ++y) {
+        const uint16_t* r[7];
+        for (int i = 0; i < 7; ++i) r[i] = hrow.data() + (size_t)reflect101(y + i - 3, h) * w;
+        uint8_t* D = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; ++x) {
+            const uint32_t acc = 18u * ((uint32_t)r[0][x] + r[6][x]) + 34u * ((uint32_t)r[1][x] + r[5][x]) + 48u * ((uint32_t)r[2][x] + r[4][x]) +
+                                 56u * (uint32_t)r[3][x];
+            D[x] = (uint8_t)((acc + 32768u) >> 16);
         }
     }
-    for (int y = 0; y < h; ++y)
-        for (int x = 0; x < w; ++x) {
-            uint32_t acc = 0;
-            for (int i = 0; i < 7; ++i) acc += k[i] * hrow[(size_t)reflect101(y + i - 3, h) * w + x];
-            dst[y * dstride + x] = (uint8_t)((acc + 32768u) >> 16);
-        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

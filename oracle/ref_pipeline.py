@@ -1,12 +1,14 @@
 """CPU reference arm of bench.py (TEST / BASELINE INFRASTRUCTURE, never on the product path).
 
-The reference binary cannot be built in this image (no OpenCV C++ / Sophus / glog / g2o / Pangolin),
+The whole reference binary cannot be built in this image (no OpenCV C++ / Sophus / glog / g2o / Pangolin),
 so the reference's CPU front-end is reproduced as closely as the image allows:
   * the OpenCV primitives the reference calls directly from tracking.cpp -- cv::FAST (tracking.cpp:101), BFMatcher
     (tracking.cpp:539-544), cv::calcOpticalFlowPyrLK (tracking.cpp:593-618) -- are the REAL OpenCV ones (cv2 4.13, SIMD,
     one OpenCV thread per worker);
-  * ORBextractor::operator() is the C++ oracle port (oracle_orb.cpp, -O3 AVX2), because its per-cell cv::FAST loop, octree,
-    IC_Angle and descriptor are the reference's own code;
+  * ORBextractor::operator() is the reference's OWN src/ORBextractor.cpp, compiled where it lies against oracle/ref_shim into
+    oracle/_ref/liborb_ref.so (system malloc, the reference's -O3 flags; the OpenCV calls inside it are the oracle's cv2-pinned
+    restatements).  Where that library is absent, the C++ oracle port (oracle_orb.cpp, -O3 AVX2) stands in -- same speed
+    within a few percent, same results up to the octree's heap-address tie-break;
   * the reference is single-threaded; to give it every host core the sequence is split over one worker process per core
     (contiguous chunks overlapping by one frame, the same sharding rule as the GPU path).
 """
@@ -28,7 +30,7 @@ def _worker(args):
     sys.path.insert(0, _HERE)
     import oracle_py as O
     left, right = _G["left"], _G["right"]
-    orb = O.OrbOracle(nfeat, 1.2, 8, 20, 7)
+    orb = O.RefOrb(nfeat, 1.2, 8, 20, 7, monotone=False) if O.ref_lib() is not None else O.OrbOracle(nfeat, 1.2, 8, 20, 7)
     bf = cv2.BFMatcher(cv2.NORM_HAMMING)
     fast = cv2.FastFeatureDetector_create(20, True)
     lk = dict(winSize=(21, 21), maxLevel=3, criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01), flags=0,
@@ -65,6 +67,13 @@ def _worker(args):
             cur["L"], cur["R"] = L, R
         last = cur
     return checksum
+
+
+def orb_kind():
+    """'reference' when ORBextractor runs from the reference's compiled source (oracle/_ref), else 'port'."""
+    sys.path.insert(0, _HERE)
+    import oracle_py as O
+    return "reference" if O.ref_lib() is not None else "port"
 
 
 class ReferencePool:
