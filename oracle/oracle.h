@@ -19,9 +19,10 @@
 //      (oracle/make_golden_ref.py).  Under the system malloc the octree's pair<int, ExtractorNode*> sort
 //      (ORBextractor.cpp:636) makes ~1-3 % of the keypoints depend on the heap's history (measured, same test file):
 //      parity of the SELECTED keypoints is therefore defined under the monotone allocator (see distribute_octree()).
-// Still unpinned against compiled reference code: the tracking.cpp post-filters (tracking.cpp needs Sophus / g2o / the
-// whole Frame graph to compile); they are restated line by line with file:line citations, and the OpenCV calls around
-// them (BFMatcher, calcOpticalFlowPyrLK, triangulatePoints) are pinned by (1).
+//  (3) the three front-end member functions of src/tracking.cpp (:534-660: the ORB association filter, the four-call LK
+//      chain, deleteBadmatchFeatures) are cut out of the reference file at build time into oracle/_ref/ and compiled inside
+//      oracle/ref_tracking_capi.cpp (tracking.cpp as a whole needs Eigen / Sophus / g2o); orb_match_filter() and
+//      lk_chain_filter() below equal that compiled code exactly (tests/test_reference_cpu.py).
 //
 // All citations "ORBextractor.cpp:N" / "tracking.cpp:N" are into /root/reference/src/.
 #pragma once

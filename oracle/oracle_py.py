@@ -205,7 +205,8 @@ def build_ref(force=False):
     that received no prebuilt copy).  Never reads /root/reference at run time once the library is built."""
     so = os.path.join(_HERE, "_ref", "liborb_ref.so")
     if os.path.exists(REF_SRC):
-        deps = [REF_SRC] + [os.path.join(_HERE, f) for f in ("ref_capi.cpp", "ref_shim/shim_cv.hpp", "oracle_prims.cpp", "Makefile")]
+        deps = [REF_SRC, "/root/reference/src/tracking.cpp"] + [os.path.join(_HERE, f) for f in (
+            "ref_capi.cpp", "ref_tracking_capi.cpp", "ref_shim/shim_cv.hpp", "oracle_prims.cpp", "Makefile")]
         if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
     return so if os.path.exists(so) else None
@@ -264,6 +265,53 @@ class RefOrb:
         out = np.empty((h.value, w.value), np.uint8)
         self.L.ref_orb_level(C.c_void_p(self._h), l, _p(out), out.strides[0], C.byref(w), C.byref(h))
         return out
+
+
+_REFT = None
+
+
+def ref_tracking_lib():
+    """oracle/_ref/libtracking_ref.so: Tracking::{ORB,LK}_Robust_Find_MuliImage_MatchedFeatures and deleteBadmatchFeatures compiled
+    from the text of /root/reference/src/tracking.cpp:534-660 (cut out at build time), or None if unavailable."""
+    global _REFT
+    if _REFT is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "libtracking_ref.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ref_orb_robust_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_lk_robust_track.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 4 + [C.c_int]
+        _REFT = L
+    return _REFT
+
+
+def ref_orb_robust_match(last_kl, last_dl, last_kr, last_dr, cur_kl, cur_dl, fme=3.0):
+    """The reference's compiled ORB association (tracking.cpp:534-581) -> (t2_left, t1_left, t1_right) point lists."""
+    L = ref_tracking_lib()
+    arrs = [np.ascontiguousarray(a) for a in (last_kl, last_dl, last_kr, last_dr, cur_kl, cur_dl)]
+    cap = max(len(last_kl), 1)
+    out = [np.zeros((cap, 2), np.float32) for _ in range(3)]
+    n = L.ref_orb_robust_match(_p(arrs[0]), _p(arrs[1]), len(arrs[0]), _p(arrs[2]), _p(arrs[3]), len(arrs[2]), _p(arrs[4]), _p(arrs[5]),
+                               len(arrs[4]), fme, _p(out[0]), _p(out[1]), _p(out[2]), cap)
+    assert 0 <= n <= cap
+    return tuple(o[:n] for o in out)
+
+
+def ref_lk_robust_track(last_left, last_right, cur_left, cur_right, seeds, fme=3.0):
+    """The reference's compiled 4-call LK chain + deleteBadmatchFeatures (tracking.cpp:583-660) ->
+    (t2_left, t2_right, t1_left, t1_right) lists of the surviving tracks."""
+    L = ref_tracking_lib()
+    imgs = [_img(a) for a in (last_left, last_right, cur_left, cur_right)]
+    seeds = np.ascontiguousarray(seeds, np.float32).reshape(-1, 2)
+    cap = max(len(seeds), 1)
+    out = [np.zeros((cap, 2), np.float32) for _ in range(4)]
+    n = L.ref_lk_robust_track(_p(imgs[0]), _p(imgs[1]), _p(imgs[2]), _p(imgs[3]), imgs[0].shape[1], imgs[0].shape[0], _p(seeds), len(seeds), fme,
+                              _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), cap)
+    assert 0 <= n <= cap
+    return tuple(o[:n] for o in out)
 
 
 def orb_match_filter(idx1, dist1, idx2, dist2, n_last_right, n_cur_left, last_left, last_right, fme=3.0):

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "../oracle.h"
@@ -224,5 +225,64 @@ struct KeyPointsFilter {  // only reached from ComputeKeyPointsOld (dead code, O
         }
     }
 };
+
+// ---- the slice of features2d / video that tracking.cpp:534-660 uses (oracle/ref_tracking_capi.cpp) --------------------
+struct DMatch {
+    int queryIdx, trainIdx, imgIdx;
+    float distance;
+    DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.4028235e38f) {}
+};
+
+template <typename T>
+using Ptr = std::shared_ptr<T>;
+
+// DescriptorMatcher::create("BruteForce-Hamming")->match(query, train, matches): one DMatch per query, lowest train index on ties
+class DescriptorMatcher {
+public:
+    static Ptr<DescriptorMatcher> create(const std::string& type) {
+        assert(type == "BruteForce-Hamming");
+        (void)type;
+        return std::make_shared<DescriptorMatcher>();
+    }
+    void match(const Mat& q, const Mat& t, std::vector<DMatch>& matches) const {
+        matches.clear();
+        if (q.empty() || t.empty()) return;  // empty train set: no matches
+        assert(q.cols == 32 && t.cols == 32 && q.step == 32 && t.step == 32);
+        std::vector<int32_t> idx((size_t)q.rows), dist((size_t)q.rows);
+        orc::match_hamming(q.data, q.rows, t.data, t.rows, idx.data(), dist.data());
+        matches.resize((size_t)q.rows);
+        for (int i = 0; i < q.rows; ++i) {
+            matches[i].queryIdx = i;
+            matches[i].trainIdx = idx[i];
+            matches[i].imgIdx = 0;
+            matches[i].distance = (float)dist[i];
+        }
+    }
+};
+
+struct TermCriteria {
+    enum { COUNT = 1, MAX_ITER = COUNT, EPS = 2 };
+    int type, maxCount;
+    double epsilon;
+    TermCriteria(int t, int c, double e) : type(t), maxCount(c), epsilon(e) {}
+};
+
+// cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, winSize, maxLevel, criteria, flags, minEigThreshold)
+inline void calcOpticalFlowPyrLK(const Mat& prev, const Mat& next, const std::vector<Point2f>& prevPts, std::vector<Point2f>& nextPts,
+                                 std::vector<uchar>& status, Mat& err, Size winSize, int maxLevel, TermCriteria criteria, int flags,
+                                 double minEigThreshold) {
+    assert(flags == 0 && winSize.width == winSize.height && criteria.type == (TermCriteria::COUNT + TermCriteria::EPS));
+    (void)flags;
+    (void)err;  // the reference never reads the error matrices
+    const int n = (int)prevPts.size();
+    nextPts.assign((size_t)n, Point2f());
+    status.assign((size_t)n, 0);
+    if (!n) return;
+    static_assert(sizeof(Point2f) == 8, "Point2f layout");
+    std::vector<float> e((size_t)n);
+    orc::calc_optical_flow_pyr_lk(view_of(prev), view_of(next), reinterpret_cast<const float*>(prevPts.data()), n,
+                                  reinterpret_cast<float*>(nextPts.data()), status.data(), e.data(), winSize.width, maxLevel,
+                                  criteria.maxCount, criteria.epsilon, minEigThreshold);
+}
 
 }  // namespace cv

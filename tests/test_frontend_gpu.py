@@ -216,3 +216,35 @@ def test_frontend_triangulated_lists(pkg, orc):
         z = out.lk_points3d[i, :out.n_lk_matched[i], 2]
         assert abs(np.median(z) - 386.1448 / 8) < 1.0
     ctx.close()
+
+
+def test_frontend_equals_reference_tracking_source(pkg, orc):
+    """The batch front-end against tracking.cpp:534-660 compiled from the reference's own text (oracle/_ref/libtracking_ref.so):
+    the ORB association lists bit-exact (same keypoints / descriptors in), the surviving LK tracks identical in number and
+    within 0.01 px."""
+    if orc.ref_tracking_lib() is None:
+        pytest.skip("oracle/_ref/libtracking_ref.so not present (built where /root/reference exists)")
+    w, h, B = 1241, 376, 4
+    left, right = pkg.synth_sequence(1000, 14, B, w, h)  # crosses the canvas re-seed at frame 16
+    ctx = pkg.Context(0, w, h, 2 * (B + 1))
+    ctx.orb_configure(1000, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    out = pkg.FrontendBuffers(B, ctx.orb_capacity(w, h), max(1024, w * h // 64))
+    ctx.frontend_batch(left, right, out)
+    for i in range(1, B):
+        nl0, nr0, nl1 = out.n_left[i - 1], out.n_right[i - 1], out.n_left[i]
+        t2l, t1l, t1r = orc.ref_orb_robust_match(out.kps_left[i - 1, :nl0], out.desc_left[i - 1, :nl0], out.kps_right[i - 1, :nr0],
+                                                 out.desc_right[i - 1, :nr0], out.kps_left[i, :nl1], out.desc_left[i, :nl1], 3.0)
+        nm = out.n_orb_matched[i]
+        assert nm == len(t2l) and nm > 20
+        assert np.array_equal(out.orb_t2_left[i, :nm], t2l) and np.array_equal(out.orb_t1_left[i, :nm], t1l)
+        assert np.array_equal(out.orb_t1_right[i, :nm], t1r)
+        ns = out.n_seed[i]
+        seeds = np.stack([out.fast_kps[i - 1, :ns]["x"], out.fast_kps[i - 1, :ns]["y"]], 1)
+        r_t2l, r_t2r, r_t1l, r_t1r = orc.ref_lk_robust_track(left[i - 1], right[i - 1], left[i], right[i], seeds, 3.0)
+        nk = out.n_lk_matched[i]
+        assert nk == len(r_t1l) and nk > 50, (nk, len(r_t1l))
+        assert np.array_equal(out.lkf_t1_left[i, :nk], r_t1l)
+        for g, r in ((out.lkf_t1_right, r_t1r), (out.lkf_t2_right, r_t2r), (out.lkf_t2_left, r_t2l)):
+            assert np.abs(g[i, :nk] - r).max() <= 0.01
+    ctx.close()

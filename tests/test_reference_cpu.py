@@ -77,3 +77,34 @@ def test_reference_source_is_heap_dependent_under_malloc(pkg, orc):
         total += len(a)
         assert len(a & b) >= 0.9 * len(a)
     print(f"system malloc: {differing} of {total} keypoints ({100.0 * differing / total:.2f} %) differ from the canonical tie-break")
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,nfeat,seed,frame", [(640, 200, 500, 7, 2), (1241, 376, 1000, 1000, 15)])  # frame 15 -> 16 crosses the re-seed
+def test_oracle_filters_equal_reference_tracking_source(pkg, orc, w, h, nfeat, seed, frame):
+    """tracking.cpp:534-660 compiled from the reference's text (oracle/_ref/libtracking_ref.so) against the oracle's
+    restatements: the ORB association filter, the order of the four LK calls and deleteBadmatchFeatures."""
+    assert orc.ref_tracking_lib() is not None
+    (l0, l1), (r0, r1) = pkg.synth_sequence(seed, frame, 2, w, h)
+    o = orc.OrbOracle(nfeat, 1.2, 8, 20, 7)
+    (kl0, dl0), (kr0, dr0), (kl1, dl1) = o.extract(l0), o.extract(r0), o.extract(l1)
+    # ---- ORB_Robust_Find_MuliImage_MatchedFeatures
+    si, sd = orc.match_hamming(dl0, dr0)
+    ti, td = orc.match_hamming(dl0, dl1)
+    acc = orc.orb_match_filter(si, sd, ti, td, len(dr0), len(dl1), kl0, kr0, 3.0)
+    xy = lambda k: np.stack([k["x"], k["y"]], 1)
+    t2l, t1l, t1r = orc.ref_orb_robust_match(kl0, dl0, kr0, dr0, kl1, dl1, 3.0)
+    assert len(acc) == len(t2l) and len(acc) > 20
+    assert np.array_equal(t1l, xy(kl0)[acc[:, 0]]) and np.array_equal(t1r, xy(kr0)[acc[:, 1]]) and np.array_equal(t2l, xy(kl1)[acc[:, 2]])
+    # ---- LK_Robust_Find_MuliImage_MatchedFeatures + deleteBadmatchFeatures
+    fk = orc.fast9(l0, 20)
+    seeds = np.stack([fk["x"], fk["y"]], 1)
+    p1, s1, _ = orc.lk_track(l0, r0, seeds)
+    p2, s2, _ = orc.lk_track(r0, r1, p1)
+    p3, s3, _ = orc.lk_track(r1, l1, p2)
+    p0r, s4, _ = orc.lk_track(l1, l0, p3)
+    keep = orc.lk_chain_filter(seeds, p1, p2, p3, p0r, s1, s2, s3, s4, 3.0)
+    g_t2l, g_t2r, g_t1l, g_t1r = orc.ref_lk_robust_track(l0, r0, l1, r1, seeds, 3.0)
+    assert keep.sum() == len(g_t1l) and keep.sum() > 50
+    assert np.array_equal(g_t1l, seeds[keep]) and np.array_equal(g_t1r, p1[keep])
+    assert np.array_equal(g_t2r, p2[keep]) and np.array_equal(g_t2l, p3[keep])
