@@ -123,6 +123,7 @@ def run_b200(a):
     ctx = pkg.Context(local, w, h, 2 * (2 * B + 1))  # ring of 2 batches + the carried frame: downloads overlap the next run
     ctx.orb_configure(a.nfeatures, 1.2, 8, 20, 7)
     ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    ctx.frontend_set_overlap(not a.no_overlap)
     stream = torch.cuda.Stream()  # a real (non-null) stream shared by torch events and the library's kernels
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -296,6 +297,7 @@ def main():
     p.add_argument("--nfeatures", type=int, default=1000)
     p.add_argument("--sample-units", type=int, default=0, help="reference arm: stereo frames per step (0 = 3 per core)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-overlap", action="store_true", help="run the ORB tail and the FAST + LK chain on one stream")
     a = p.parse_args()
     if a.impl == "reference":
         run_reference(a)

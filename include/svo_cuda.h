@@ -176,6 +176,10 @@ int svo_frontend_configure(svo_ctx* ctx, int w, int h, int mode, int max_frames)
 int svo_frontend_reset(svo_ctx* ctx);
 /* Tracking::feature_match_error_ (parameter.cpp:53, config/default.yaml:66; default 3) used by the device-side post-filters */
 int svo_frontend_set_match_error(svo_ctx* ctx, double feature_match_error);
+/* Both modes in one batch: run the ORB tail (octree, orientation + descriptors, the two Hamming matches, the association filter)
+ * on a side stream concurrently with the FAST + LK chain (they share no data; the big kernels still mostly serialise, the small
+ * ones fill each other's tails: ~1 % at 1241x376).  On by default; 0 = one stream. */
+int svo_frontend_set_overlap(svo_ctx* ctx, int enable);
 /* Sensors::projMatr1_ / projMatr2_ (3x4, row-major doubles; sensors.cpp:8-24): enables the device-side triangulation of
  * the filtered lists.  Call after svo_frontend_configure(). */
 int svo_frontend_set_projection(svo_ctx* ctx, const double* proj_left, const double* proj_right);

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "svo_ctx_launch_count", "svo_ctx_enable_stage_timing", "svo_ctx_set_timing_slot", "svo_ctx_stage_ms", "svo_orb_configure", "svo_orb_tables",
     "svo_orb_capacity", "svo_orb_level_size", "svo_orb_extract", "svo_orb_extract_batch", "svo_orb_read_level",
     "svo_orb_read_candidates", "svo_fast_detect", "svo_match_hamming", "svo_lk_track", "svo_frontend_configure",
-    "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_projection", "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
+    "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_overlap", "svo_frontend_set_projection", "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
     "svo_synth_stereo_frame",
 ]
 
@@ -246,6 +246,9 @@ class Context:
 
     def frontend_set_match_error(self, fme):
         self._check(self._L.svo_frontend_set_match_error(self._h, C.c_double(fme)))
+
+    def frontend_set_overlap(self, enable):
+        self._check(self._L.svo_frontend_set_overlap(self._h, int(bool(enable))))
 
     def frontend_set_projection(self, p1, p2):
         p1 = np.ascontiguousarray(p1, np.float64).reshape(12)

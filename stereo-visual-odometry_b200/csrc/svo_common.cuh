@@ -199,6 +199,10 @@ struct svo_ctx {
     DoneRun fe_q[2] = {};  // completed, not yet downloaded runs (oldest at fe_qhead)
     int fe_qhead = 0, fe_nq = 0, fe_depth = 1;
     cudaStream_t d2h_stream = nullptr;
+    // ORB tail || FAST + LK chain: side stream and the fork / join events
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fe_overlap = true;
     cudaEvent_t ev_done[2] = {};
     bool fe_has_last = false;
     bool fe_configured = false;

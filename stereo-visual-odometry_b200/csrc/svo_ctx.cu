@@ -87,6 +87,12 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
         }
         cudaStreamDestroy(c->copy_stream);
     }
+    if (c->side_stream) {
+        cudaStreamSynchronize(c->side_stream);
+        cudaStreamDestroy(c->side_stream);
+        cudaEventDestroy(c->ev_fork);
+        cudaEventDestroy(c->ev_join);
+    }
     if (c->ev) {
         for (int k = 0; k < SVO_TIMING_SLOTS; ++k)
             for (int s = 0; s < SVO_NUM_STAGES; ++s) {

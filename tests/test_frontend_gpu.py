@@ -248,3 +248,27 @@ def test_frontend_equals_reference_tracking_source(pkg, orc):
         for g, r in ((out.lkf_t1_right, r_t1r), (out.lkf_t2_right, r_t2r), (out.lkf_t2_left, r_t2l)):
             assert np.abs(g[i, :nk] - r).max() <= 0.01
     ctx.close()
+
+
+def test_frontend_overlap_equals_single_stream(pkg):
+    """The ORB tail on the side stream (default) gives exactly the outputs of the single-stream schedule."""
+    w, h, B = 640, 200, 4
+    left, right = pkg.synth_sequence(31, 0, 2 * B, w, h)
+    res = []
+    for overlap in (True, False):
+        ctx = pkg.Context(0, w, h, 2 * (B + 1))
+        ctx.orb_configure(400, 1.2, 8, 20, 7)
+        ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+        ctx.frontend_set_overlap(overlap)
+        outs = []
+        for b in range(2):
+            out = pkg.FrontendBuffers(B, ctx.orb_capacity(w, h), max(1024, w * h // 64))
+            ctx.frontend_batch(np.ascontiguousarray(left[b * B:(b + 1) * B]), np.ascontiguousarray(right[b * B:(b + 1) * B]), out)
+            outs.append(out)
+        res.append(outs)
+        ctx.close()
+    for a, b in zip(*res):
+        for name in pkg.FrontendBuffers.ALL:
+            x, y = getattr(a, name), getattr(b, name)
+            if x is not None and name not in ("orb_points3d", "lk_points3d"):
+                assert np.array_equal(x, y), name
