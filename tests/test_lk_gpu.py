@@ -89,3 +89,23 @@ def test_lk_levels_and_iterations(pkg, orc):
         ok = o[1] == 1
         assert np.abs(g[0] - o[0])[ok].max() <= LK_TOL
     ctx.close()
+
+
+@pytest.mark.parametrize("gap", [3, 6, 11])
+def test_lk_large_motion_many_iterations(pkg, orc, gap):
+    """Frames several steps apart (2 px of motion per step + the 8 px disparity): tracks need many Gauss-Newton steps, leave their
+    integer cell repeatedly (tile re-staging), oscillate or get lost -- status identical, points within 0.01 px."""
+    w, h = 800, 300
+    l0, r0 = pkg.synth_stereo_frame(321, 1, w, h)
+    l1, r1 = pkg.synth_stereo_frame(321, 1 + gap, w, h)
+    ctx = pkg.Context(0, w, h, 2)
+    kp = ctx.fast_detect(l0, 20)
+    pts = np.stack([kp["x"], kp["y"]], 1) + np.float32(0.37)  # sub-pixel seeds
+    for a, b in ((l0, l1), (l0, r1), (r1, l0)):
+        g, o = ctx.lk_track(a, b, pts), orc.lk_track(a, b, pts)
+        assert np.array_equal(g[1], o[1])
+        ok = o[1] == 1
+        assert ok.sum() > 20
+        assert np.abs(g[0] - o[0])[ok].max() <= LK_TOL
+        assert np.abs(g[2] - o[2])[ok].max() <= 1e-3
+    ctx.close()
