@@ -476,7 +476,7 @@ int svo_layout(svo_ctx* c, int w, int h) {
             if (G.nIni < 1) return c->fail(SVO_ERR_INVALID, "portrait images (width/height < 0.5) are undefined in the reference (nIni == 0)");
             G.hX = (float)G.Wp / G.nIni;
             const int xe = G.w - SVO_EDGE, ye = G.h - SVO_EDGE;  // exclusive end of the FAST inner domain
-            const int cells_per_tile = std::max(1, std::min(32, 384 / G.wCell));  // ~46 KB of shared memory per tile: 4 CTAs / SM
+            const int cells_per_tile = std::max(1, std::min(32, 249 / G.wCell));  // <= 249 px: one full 64-word pre-test step per row in every alignment
             uint32_t lvl_cap = 0;
             for (int i = 0; i < G.nRows; ++i) {
                 const int y0 = SVO_EDGE + i * G.hCell, y1 = std::min(y0 + G.hCell, ye);
