@@ -144,6 +144,19 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
     const uint32_t m_last = 0x80808080u >> (8 * (3 - ((sx0 + sw - 1) & 3)));  // bytes <= last column of word w1
     volatile int* wcnt = reinterpret_cast<volatile int*>(tail_q) + 4 + warp;  // this warp's queue fill (zeroed by the caller)
     const uint32_t wcnt_addr = (uint32_t)__cvta_generic_to_shared(const_cast<int*>(wcnt));
+    // validity masks of a lane's two words (bytes inside [sx0, sx0 + sw)); with a single step per row (tiles of K2) they are the
+    // same for every row and are computed once
+    auto lane_masks = [&](int wi, uint32_t& k0, uint32_t& k1) {
+        k0 = wi < w0 || wi > w1 ? 0u : 0x80808080u;
+        k1 = wi + 1 < w0 || wi + 1 > w1 ? 0u : 0x80808080u;
+        if (wi == w0) k0 &= m_first;
+        if (wi == w1) k0 &= m_last;
+        if (wi + 1 == w0) k1 &= m_first;
+        if (wi + 1 == w1) k1 &= m_last;
+    };
+    const bool single = w1 - w0e < 64;
+    uint32_t k0 = 0, k1 = 0;
+    if (single) lane_masks(w0e + 2 * lane, k0, k1);
     for (int yy = warp; yy < sh; yy += FW) {
         const uint32_t* row = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy) * PW);
         const uint32_t* rup = reinterpret_cast<const uint32_t*>(pix + (size_t)(sy0 + yy - 3) * PW);
@@ -151,20 +164,13 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
         for (int wb = w0e; wb <= w1; wb += 64) {
             const int wi = wb + 2 * lane;  // this lane: words wi, wi + 1
             uint32_t pass0 = 0, pass1 = 0;
-            if (wi <= w1) {
+            if (!single) lane_masks(wi, k0, k1);
+            if (k0 | k1) {
                 const uint2 c = *reinterpret_cast<const uint2*>(row + wi);
                 const uint2 u = *reinterpret_cast<const uint2*>(rup + wi), d = *reinterpret_cast<const uint2*>(rdn + wi);
                 const uint32_t cm = row[wi - 1], cp = row[wi + 2];
-                pass0 = pretest4<POW2>(c.x, cm, c.y, u.x, d.x, K7);
-                pass1 = pretest4<POW2>(c.y, c.x, cp, u.y, d.y, K7);
-                if (wi <= w0 || wi + 1 >= w1) {  // region edges (rare)
-                    if (wi < w0) pass0 = 0;
-                    if (wi == w0) pass0 &= m_first;
-                    if (wi == w1) pass0 &= m_last;
-                    if (wi + 1 == w0) pass1 &= m_first;
-                    if (wi + 1 == w1) pass1 &= m_last;
-                    if (wi + 1 > w1) pass1 = 0;
-                }
+                pass0 = pretest4<POW2>(c.x, cm, c.y, u.x, d.x, K7) & k0;
+                pass1 = pretest4<POW2>(c.y, c.x, cp, u.y, d.y, K7) & k1;
             }
             // survivors -> the warp's queue.  The kernel is bound by instruction issue, not by the shared-memory pipe, so the
             // slot comes from ONE shared-memory atomic per lane with survivors (order inside the queue is irrelevant) instead
