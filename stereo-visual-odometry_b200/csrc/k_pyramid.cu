@@ -160,8 +160,11 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
         const int d_orgx = r.x0 & ~3;
         const int ng = (r.x1n - d_orgx + 3) >> 2;             // 4-pixel groups
         const int d_pitch = ng * 4 + 8;
-        const int nrl = 256 / ng;                             // row lanes
-        const int gi = threadIdx.x % ng, rl = threadIdx.x / ng;
+        // small-integer divisions through the float reciprocal (exact here: operands < 2^9, (a + 0.5) / b is never within
+        // 2^-8 of an integer): the generic 32-bit division costs ~25 instructions, three times per thread and level
+        const float inv_ng = __frcp_rn((float)ng);
+        const int nrl = (int)(256.5f * inv_ng);               // row lanes = 256 / ng
+        const int rl = (int)(((float)threadIdx.x + 0.5f) * inv_ng), gi = (int)threadIdx.x - rl * ng;
         if (rl < nrl) {
             const int gx = d_orgx + 4 * gi;                   // level x of the group's first pixel
             // column coefficients of the 4 pixels (tables are padded to a multiple of 4 entries)
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
             uint8_t* gdst = D.base + (size_t)slot * D.plane + gx;
             // each row lane owns a contiguous run of rows, so the horizontal pass of the lower source row is reused as the
             // upper row of the next destination row (5 of 6 rows at scale 1.2)
-            const int chunk = (nh + nrl - 1) / nrl;
+            const int chunk = (int)(((float)(nh + nrl - 1) + 0.5f) * __frcp_rn((float)nrl));  // ceil(nh / nrl)
             const int ya = r.y0 + rl * chunk, yb = min(ya + chunk, (int)r.y1n);
             int cached_row = -1;
             int Tc[4] = {0, 0, 0, 0};
