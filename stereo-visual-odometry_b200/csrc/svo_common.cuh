@@ -79,7 +79,13 @@ struct FastTile {
 // batch image index -> image slot (see svo_ctx.cu: plain batches use slots 0..n-1; the frontend uses a ring of frames)
 struct SlotMap {
     int sides, side_stride, first, ring;
-    __host__ __device__ inline int slot(int b) const { return (b % sides) * side_stride + (first + b / sides) % ring; }
+    // sides is 1 or 2 and first, b / sides < ring (see the four constructions in svo_ctx.cu / svo_frontend.cu): no division
+    __host__ __device__ inline int slot(int b) const {
+        const int side = sides == 2 ? (b & 1) : 0, f = sides == 2 ? (b >> 1) : b;
+        int r = first + f;
+        if (r >= ring) r -= ring;
+        return side * side_stride + r;
+    }
 };
 
 #define SVO_FLAG_TILE_OVERFLOW 1
