@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(MT) k_match_one(const uint8_t* q, int nq, cons
 __global__ void __launch_bounds__(MT) k_match_frontend(const uint8_t* __restrict__ desc, const int* __restrict__ nkp, int kp_cap,
                                                        int first, int ring, int skip_first, int* __restrict__ match) {
     const int f = blockIdx.y >> 1, kind = blockIdx.y & 1;
-    const int cur = (first + f) % ring, prev = (first + f - 1 + ring) % ring;
+    const int cu = first + f, cur = cu >= ring ? cu - ring : cu, prev = cur == 0 ? ring - 1 : cur - 1;  // first, f < ring
     int* out = match + ((size_t)cur * 4 + 2 * kind) * kp_cap;
     if (f == 0 && skip_first) return;  // no predecessor: StereoInit_f2f only detects (tracking.cpp:78-92)
     const int qs = prev, ts = kind == 0 ? ring + prev : cur;
