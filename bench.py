@@ -239,7 +239,7 @@ def run_b200(a):
             # the kernel with the largest share of the step is the LK tracker; it is bound by instruction issue and the
             # shared-memory pipe, not by HBM or tensor throughput (profiles/*_ncu_full_all_kernels.txt), so it is reported as
             # tracks/s next to the HBM roofline of the pyramid + FAST stages that north_star asks for
-            "dominant_kernel": {"name": "K8 k_lk_track (4 launches per step)", "ms_per_step": round(t_lk, 4), "share_of_step": round(t_lk / (ms_dev / K), 3),
+            "dominant_kernel": {"name": "K8 k_lk_track (the 4-call chain, one launch per step)", "ms_per_step": round(t_lk, 4), "share_of_step": round(t_lk / (ms_dev / K), 3),
                                 "tracks_per_step": tracks, "tracks_per_s": tracks / (t_lk * 1e-3) if t_lk > 0 else None,
                                 "bound": "instruction issue + shared-memory pipe (integer; no HBM or tensor bound)"},
             "cpu_baseline": cpu_baseline,

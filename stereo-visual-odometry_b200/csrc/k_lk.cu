@@ -14,6 +14,7 @@
 //                   (int64 across the warp), converted to float once.
 //
 // f32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) to follow OpenCV's scalar expressions.
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 
@@ -84,7 +85,8 @@ struct LkParams {
     LkLevelGeom lv[SVO_LK_LEVELS];  // padded planes (REFLECT_101 border of SVO_LK_PADX / SVO_LK_PADY materialised)
     int levels;      // pyramid levels available (maxLevel + 1)
     int first, ring, skip_first;
-    LkCall call;
+    LkCall calls[4];  // the chain: the output list of call k is the source list of call k + 1
+    int ncalls;
     int standalone;  // 1: src points are a plain xy list (list index call.src_list), n given by n_fixed
     int n_fixed;
     int max_iter;
@@ -239,22 +241,6 @@ __global__ void __launch_bounds__(LW * 32, 8) k_lk_track(LkParams P, const svo_k
     const int n = P.standalone ? P.n_fixed : nfast[seed_fs];
     const int pt = blockIdx.x * LW + warp;
     if (pt >= n) return;  // warp-uniform; most warps of the fixed-size grid leave here
-    const int pfs = P.call.prev_back ? seed_fs : cur, nfs = P.call.next_back ? seed_fs : cur;  // back is 0 or 1
-    const int prev_slot = P.call.prev_side * P.ring + pfs, next_slot = P.call.next_side * P.ring + nfs;
-
-    float px, py;
-    if (!P.standalone && P.call.src_list == 0) {
-        const svo_keypoint kp = fast_kps[(size_t)seed_fs * P.pt_cap + pt];
-        px = kp.x;
-        py = kp.y;
-    } else {
-        const float* src = lk_pts + ((size_t)cur * 5 + P.call.src_list) * P.pt_cap * 2;
-        px = src[2 * pt];
-        py = src[2 * pt + 1];
-    }
-    float* dst = lk_pts + ((size_t)cur * 5 + P.call.dst_list) * P.pt_cap * 2;
-    uint8_t* st_out = lk_status + ((size_t)cur * 4 + P.call.status_row) * P.pt_cap;
-
     uint8_t* tile = s_mem + warp * WARP_SMEM;
     uint2* tmpl = reinterpret_cast<uint2*>(tile + TILE_BYTES);  // [pixel y * 21 + x] = (256 - 512 * I, Ix | Iy << 16)
     if (lane < 32 * NK - NPIX) tmpl[NPIX + lane] = make_uint2(0u, 0u);  // the 7 pad pixels: zero gradient, never rewritten
@@ -274,6 +260,27 @@ __global__ void __launch_bounds__(LW * 32, 8) k_lk_track(LkParams P, const svo_k
         }
     }
     const int ccol = min(lane, 23);  // setup: tile column of this lane
+
+    // the whole chain of calls for this point in one launch (tracking.cpp:593-618 chains four calls: each call's output list is
+    // the next call's input, failed points included -- exactly what separate launches would read back from memory)
+    float px = 0.f, py = 0.f;
+    for (int ci = 0; ci < P.ncalls; ++ci) {
+    const LkCall& call = P.calls[ci];
+    const int pfs = call.prev_back ? seed_fs : cur, nfs = call.next_back ? seed_fs : cur;  // back is 0 or 1
+    const int prev_slot = call.prev_side * P.ring + pfs, next_slot = call.next_side * P.ring + nfs;
+    if (ci == 0) {
+        if (!P.standalone && call.src_list == 0) {
+            const svo_keypoint kp = fast_kps[(size_t)seed_fs * P.pt_cap + pt];
+            px = kp.x;
+            py = kp.y;
+        } else {
+            const float* src = lk_pts + ((size_t)cur * 5 + call.src_list) * P.pt_cap * 2;
+            px = src[2 * pt];
+            py = src[2 * pt + 1];
+        }
+    }
+    float* dst = lk_pts + ((size_t)cur * 5 + call.dst_list) * P.pt_cap * 2;
+    uint8_t* st_out = lk_status + ((size_t)cur * 4 + call.status_row) * P.pt_cap;
 
     const float half = 10.f;   // (win - 1) * 0.5
     float nx = 0.f, ny = 0.f;  // nextPts[pt] carried across levels
@@ -478,6 +485,9 @@ __global__ void __launch_bounds__(LW * 32, 8) k_lk_track(LkParams P, const svo_k
         st_out[pt] = (uint8_t)status;
         if (P.want_err && lk_err) lk_err[pt] = status ? err : 0.f;
     }
+    px = nx;  // source point of the next call of the chain
+    py = ny;
+    }  // calls
 }
 
 }  // namespace
@@ -517,15 +527,19 @@ static void fill_params(svo_ctx* c, LkParams& P, int max_level, int max_iter, do
     P.pt_cap = c->pt_cap;
 }
 
-int launch_lk_track(svo_ctx* c, int first, int ring, int n_frames, int skip_first, const LkCall& call, int max_iter, double eps,
+int launch_lk_chain(svo_ctx* c, int first, int ring, int n_frames, int skip_first, const LkCall* calls, int ncalls, int max_iter, double eps,
                     double min_eig) {
-    StageTimer t(c, 8 + call.status_row);
+    StageTimer t(c, 8);
     LkParams P{};
     fill_params(c, P, SVO_LK_LEVELS - 1, max_iter, eps, min_eig);
     P.first = first;
     P.ring = ring;
     P.skip_first = skip_first;
-    P.call = call;
+    P.ncalls = std::min(ncalls, 4);
+    for (int k = 0; k < P.ncalls; ++k) {
+        P.calls[k] = calls[k];
+        if (k && calls[k].src_list != calls[k - 1].dst_list) return c->fail(SVO_ERR_INVALID, "launch_lk_chain: calls do not form a chain");
+    }
     P.standalone = 0;
     P.want_err = 0;
     dim3 grid((c->pt_cap + LW - 1) / LW, n_frames);
@@ -543,7 +557,8 @@ int launch_lk_standalone(svo_ctx* c, int n, int max_level, int max_iter, double 
     P.first = 0;
     P.ring = 1;
     P.skip_first = 0;
-    P.call = LkCall{0, 0, 1, 0, 0, 1, 0};
+    P.calls[0] = LkCall{0, 0, 1, 0, 0, 1, 0};
+    P.ncalls = 1;
     P.standalone = 1;
     P.n_fixed = n;
     P.want_err = want_err;

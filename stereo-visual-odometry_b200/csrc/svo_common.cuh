@@ -266,13 +266,13 @@ int launch_lk_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_fir
 int launch_triangulate_frontend(svo_ctx* c, int first, int ring, int n_frames);            // K12
 int launch_fast_full(svo_ctx* c, const SlotMap& map, int n_img, int threshold);      // K9 (+ ordered compaction)
 int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img);                    // K7
-// one call of the 4-call LK chain for n_frames unit frames (K8); see k_lk.cu
+// the 4-call LK chain for n_frames unit frames in ONE launch (K8); see k_lk.cu
 struct LkCall {
     int prev_side, prev_back;  // prev image: side (0 left, 1 right) of frame (current - prev_back)
     int next_side, next_back;
     int src_list, dst_list, status_row;
 };
-int launch_lk_track(svo_ctx* c, int first, int ring, int n_frames, int skip_first, const LkCall& call, int max_iter, double eps,
+int launch_lk_chain(svo_ctx* c, int first, int ring, int n_frames, int skip_first, const LkCall* calls, int ncalls, int max_iter, double eps,
                     double min_eig);
 
 int svo_orb_run(svo_ctx* c, const SlotMap& map, int n_img);

@@ -349,8 +349,7 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
         if ((rc = launch_lk_pyramid(c, both, 2 * n)) != SVO_OK) return rc;
         // the 4-call chain (tracking.cpp:593-618): L(t-1)->R(t-1), R(t-1)->R(t), R(t)->L(t), L(t)->L(t-1)
         const LkCall calls[4] = {{0, 1, 1, 1, 0, 1, 0}, {1, 1, 1, 0, 1, 2, 1}, {1, 0, 0, 0, 2, 3, 2}, {0, 0, 0, 1, 3, 4, 3}};
-        for (int k = 0; k < 4; ++k)
-            if ((rc = launch_lk_track(c, first, ring, n, skip_first, calls[k], 30, 0.01, 0.001)) != SVO_OK) return rc;
+        if ((rc = launch_lk_chain(c, first, ring, n, skip_first, calls, 4, 30, 0.01, 0.001)) != SVO_OK) return rc;
         if ((rc = launch_lk_filter(c, first, ring, n, skip_first)) != SVO_OK) return rc;
     }
     if (overlap) SVO_CUDA_TRY(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));  // join before anything reads the ORB results
