@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int WIN = SVO_LK_WIN;  // 21
-constexpr int LW = 4;            // warps (points) per CTA
+constexpr int LW = 1;            // warps (points) per CTA
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     // |offset| <= WIN beyond the image and n > WIN on every level, so one reflection suffices
@@ -229,7 +229,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restr
 //  iterations (next image): the 441 window pixels are spread over all 32 lanes (14 each): per pixel two 16-bit loads of the
 //    staged tile, one 64-bit template load, 2 IDP.2A, one shift, two sign extensions, two IMAD.
 // All window sums are exact integers; float expressions follow OpenCV's scalar order with _rn intrinsics.
-__global__ void __launch_bounds__(LW * 32, 8) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
+__global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
                                                       float* __restrict__ lk_pts, uint8_t* __restrict__ lk_status, float* __restrict__ lk_err) {
     __shared__ __align__(16) uint8_t s_mem[LW * WARP_SMEM];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
