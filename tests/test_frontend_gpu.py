@@ -272,3 +272,25 @@ def test_frontend_overlap_equals_single_stream(pkg):
             x, y = getattr(a, name), getattr(b, name)
             if x is not None and name not in ("orb_points3d", "lk_points3d"):
                 assert np.array_equal(x, y), name
+
+
+def test_frontend_lk_full_hd_many_points(pkg, orc):
+    """Full HD, LK mode only: several thousand FAST corners per frame through the fused 4-call chain, against the oracle chain."""
+    w, h, B = 1920, 1080, 2
+    left, right = pkg.synth_sequence(2000, 3, B, w, h)
+    ctx = pkg.Context(0, w, h, 2 * (B + 1))
+    ctx.frontend_configure(w, h, pkg.MODE_LK, B)
+    pt_cap = max(1024, w * h // 64)
+    out = pkg.FrontendBuffers(B, 64, pt_cap, fields=("fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status", "n_lk_matched"))
+    ctx.frontend_batch(left, right, out)
+    ns = int(out.n_seed[1])
+    assert ns > 2048, ns
+    seeds = np.stack([out.fast_kps[0, :ns]["x"], out.fast_kps[0, :ns]["y"]], 1)
+    (p1, p2, p3, p0r), sts = _oracle_chain(orc, left[0], right[0], left[1], right[1], seeds)
+    cum = np.ones(ns, bool)
+    for k, (gp, op) in enumerate(zip((out.lk_p1, out.lk_p2, out.lk_p3, out.lk_p0r), (p1, p2, p3, p0r))):
+        assert np.array_equal(out.lk_status[1, k, :ns][cum], sts[k][cum])
+        cum &= sts[k] == 1
+        assert np.abs(gp[1, :ns] - op)[cum].max() <= 0.01
+    assert cum.sum() > 1000
+    ctx.close()
