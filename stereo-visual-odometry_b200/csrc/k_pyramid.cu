@@ -100,13 +100,34 @@ __global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ lef
                                                  LevelGeom L0, int first, int ring) {
     const int y = blockIdx.x, f = blockIdx.y, side = blockIdx.z;
     const uint8_t* __restrict__ src = (side ? right : left) + ((size_t)f * L0.h + y) * stride;
-    uint8_t* dst = L0.base + (size_t)(side * ring + (first + f) % ring) * L0.plane + (size_t)y * L0.pitch;
-    for (int x = threadIdx.x * 4; x < L0.w; x += 256 * 4) {
-        uint32_t v = 0;
+    const int fr = first + f, slot = side * ring + (fr >= ring ? fr - ring : fr);
+    uint8_t* dst = L0.base + (size_t)slot * L0.plane + (size_t)y * L0.pitch;
+    // 16 destination bytes per thread: the source row starts at an arbitrary byte, so five aligned words are funnel-shifted
+    // into four (the pitched row has room for the last partial vector; the row's last, partial source word is read byte-wise)
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(src) & 3u), sh = mis * 8u;
+    const uint32_t* __restrict__ sw = reinterpret_cast<const uint32_t*>(src - mis);
+    const int nwords = (L0.w + (int)mis + 3) >> 2;  // aligned source words that hold bytes of this row
+    const int tailb = ((L0.w + (int)mis - 1) & 3) + 1;  // valid bytes of the last of them
+    for (int x = threadIdx.x * 16; x < L0.w; x += 256 * 16) {
+        const int w0 = x >> 2;
+        uint32_t a[5];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (x + i < L0.w) v |= (uint32_t)__ldg(src + x + i) << (8 * i);
-        *reinterpret_cast<uint32_t*>(dst + x) = v;
+        for (int i = 0; i < 5; ++i) {
+            const int wi = w0 + i;
+            if (wi < nwords - 1 || (wi == nwords - 1 && tailb == 4)) {
+                a[i] = __ldg(sw + wi);
+            } else {
+                a[i] = 0u;
+                if (wi == nwords - 1)  // last, partial word of the row: byte loads, never past the caller's buffer
+                    for (int b = 0; b < tailb; ++b) a[i] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(sw + wi) + b) << (8 * b);
+            }
+        }
+        uint4 v;
+        v.x = __funnelshift_r(a[0], a[1], sh);
+        v.y = __funnelshift_r(a[1], a[2], sh);
+        v.z = __funnelshift_r(a[2], a[3], sh);
+        v.w = __funnelshift_r(a[3], a[4], sh);
+        *reinterpret_cast<uint4*>(dst + x) = v;  // pitch is a multiple of 64: the vector stays inside the destination row
     }
 }
 
