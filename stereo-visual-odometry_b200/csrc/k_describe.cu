@@ -162,7 +162,14 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
     double sd, cd;
     sincos((double)ang, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
-    const int8_t* pat = pattern + lane * 32;
+    // this lane's 8 pattern pairs (32 signed bytes) as two 16-byte loads: byte loads here would be 32 warp instructions with
+    // 32 scattered sectors each -- as much L1 traffic as the whole shared-memory work of the keypoint
+    uint32_t pw[8];
+    {
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(pattern + lane * 32)), p1 = __ldg(reinterpret_cast<const uint4*>(pattern + lane * 32) + 1);
+        pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w;
+        pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
+    }
     // vertical taps as packed u8 weights for even / odd first rows
     const uint32_t E0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), E1 = 48u | (34u << 8) | (18u << 16);
     const uint32_t O0 = (18u << 8) | (34u << 16) | (48u << 24), O1 = 56u | (48u << 8) | (34u << 16) | (18u << 24);
@@ -183,8 +190,9 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int t0 = sample((float)pat[4 * k], (float)pat[4 * k + 1]);
-        const int t1 = sample((float)pat[4 * k + 2], (float)pat[4 * k + 3]);
+        const uint32_t w = pw[k];  // (x0, y0, x1, y1) as signed bytes
+        const int t0 = sample((float)(int8_t)(w & 0xFFu), (float)(int8_t)((w >> 8) & 0xFFu));
+        const int t1 = sample((float)(int8_t)((w >> 16) & 0xFFu), (float)(int8_t)(w >> 24));
         val |= (t0 < t1) << k;
     }
     desc_all[((size_t)slot * kp_cap + kidx) * 32 + lane] = (uint8_t)val;
