@@ -109,3 +109,26 @@ def test_lk_large_motion_many_iterations(pkg, orc, gap):
         assert np.abs(g[0] - o[0])[ok].max() <= LK_TOL
         assert np.abs(g[2] - o[2])[ok].max() <= 1e-3
     ctx.close()
+
+
+def test_gpu_against_cv2_golden_vectors(pkg):
+    """The CUDA path directly against vectors made by the REAL OpenCV (cv2 4.13, oracle/make_golden.py): full-frame FAST and the
+    BF-Hamming match bit-exact, calcOpticalFlowPyrLK with identical status and within 0.01 px -- no oracle in between."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cv2_primitives.npz"))
+    l0, r0, l1 = g["left0"], g["right0"], g["left1"]
+    h, w = l0.shape
+    ctx = pkg.Context(0, w, h, 2)
+    for thr in (20, 7):
+        k = ctx.fast_detect(l0, thr)
+        assert np.array_equal(np.stack([k["x"], k["y"], k["response"]], 1), g[f"fast_{thr}"])
+    idx, dist = ctx.match_hamming(g["bf_q"], g["bf_t"])
+    assert np.array_equal(idx, g["bf_idx"]) and np.array_equal(dist, g["bf_dist"])
+    pts = g["fast_20"][:, :2].astype(np.float32)
+    for nxt, key in ((r0, "lk_stereo"), (l1, "lk_temporal")):
+        p, st, err = ctx.lk_track(l0, nxt, pts)
+        assert np.array_equal(st, g[key + "_status"])
+        ok = st == 1
+        assert ok.sum() > 50 and np.abs(p - g[key + "_pts"])[ok].max() <= LK_TOL
+        assert np.abs(err - g[key + "_err"])[ok].max() <= 1e-2
+    ctx.close()
