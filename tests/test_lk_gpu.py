@@ -113,6 +113,7 @@ def test_lk_large_motion_many_iterations(pkg, orc, gap):
 
 def test_gpu_against_cv2_golden_vectors(pkg):
     """The CUDA path directly against vectors made by the REAL OpenCV (cv2 4.13, oracle/make_golden.py): full-frame FAST and the
+    the cv2.resize pyramid chain and the
     BF-Hamming match bit-exact, calcOpticalFlowPyrLK with identical status and within 0.01 px -- no oracle in between."""
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cv2_primitives.npz"))
@@ -122,6 +123,10 @@ def test_gpu_against_cv2_golden_vectors(pkg):
     for thr in (20, 7):
         k = ctx.fast_detect(l0, thr)
         assert np.array_equal(np.stack([k["x"], k["y"], k["response"]], 1), g[f"fast_{thr}"])
+    ctx.orb_configure(300, 1.2, 5, 20, 7)
+    ctx.orb_extract(l0)
+    for l in range(1, 5):  # cv2.resize chain exactly as ComputePyramid calls it
+        assert np.array_equal(ctx.orb_read_level(0, l), g[f"resize_l{l}"]), l
     idx, dist = ctx.match_hamming(g["bf_q"], g["bf_t"])
     assert np.array_equal(idx, g["bf_idx"]) and np.array_equal(dist, g["bf_dist"])
     pts = g["fast_20"][:, :2].astype(np.float32)
