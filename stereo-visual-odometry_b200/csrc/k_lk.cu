@@ -194,10 +194,14 @@ __device__ __forceinline__ int dp2(uint32_t a, uint32_t b, int c) {
 // horizontally adjacent pixels (c, c+1) of the bilinear stencil are therefore always ONE aligned 16-bit shared-memory load
 // (from T for even c, from T2 for odd c) that feeds IDP.2A directly -- no shuffles, no byte permutes, no address arithmetic
 // per row (rows are an immediate offset apart).
-constexpr int TROW = 64, TROWS = 24, TILE_BYTES = TROW * TROWS;
+// Rows of one 7-row segment are 64 bytes apart; every further segment is skewed by 16 bytes, so that the three segments a warp
+// reads at the same time during the iterations (rows j, 7 + j, 14 + j of the same columns) fall into different banks.
+constexpr int TROW = 64, TROWS = 24, TILE_BYTES = TROW * TROWS + 64;
+__host__ __device__ constexpr int row_off(int r) { return r * TROW + (r / 7) * 16; }
 constexpr int NPIX = WIN * WIN;  // 441 window pixels
-constexpr int NK = 14;           // window pixels per lane in the flattened (iteration) form: 32 * 14 = 448 >= 441
-constexpr int WARP_SMEM = TILE_BYTES + 32 * NK * 8;
+constexpr int SEG = 7;           // iteration form: the window is cut into 21 columns x 3 segments of 7 rows = 63 strips; a lane
+constexpr int NROUND = 2;        // owns strips (lane) and (lane + 32): 14 pixels, 2 x 8 pair loads (vertical reuse inside a strip)
+constexpr int WARP_SMEM = TILE_BYTES + 32 * NROUND * SEG * 8;
 
 __device__ __forceinline__ int pair_off(int c) {  // byte offset in a tile row of the aligned u16 holding tile bytes (c, c+1)
     const int e = c & ~1;
@@ -210,13 +214,16 @@ __device__ __forceinline__ uint32_t lds_u16(const uint8_t* p) { return *reinterp
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restrict__ img, int pitch, int x0, int y0, int lane) {
     const int a0 = x0 & 3, sh = 8 * a0;
     const uint8_t* __restrict__ p = img + ((ptrdiff_t)(y0 + (lane >> 3)) * pitch + (x0 - a0) + 4 * (lane & 7));
-    uint2* dst = reinterpret_cast<uint2*>(tile + (lane >> 3) * TROW + (lane & 7) * 8);
+    const int rr = lane >> 3;
+    uint8_t* dst = tile + (lane & 7) * 8;
     const ptrdiff_t step = (ptrdiff_t)4 * pitch;
 #pragma unroll
     for (int k = 0; k < TROWS / 4; ++k) {
         const uint32_t W = __ldg(reinterpret_cast<const uint32_t*>(p + k * step));
         const uint32_t Wn = __shfl_down_sync(0xFFFFFFFFu, W, 1);  // next word of the same row (lane & 7 == 7: unused word)
-        dst[k * (4 * TROW / 8)] = make_uint2(__funnelshift_r(W, Wn, sh), __funnelshift_rc(W, Wn, sh + 8));
+        const int r = 4 * k + rr;                                   // (4k + rr) / 7 for rr < 4: one compare against a constant
+        const int seg = (4 * k) / 7 + ((4 * k) % 7 + rr >= 7 ? 1 : 0);
+        *reinterpret_cast<uint2*>(dst + r * TROW + seg * 16) = make_uint2(__funnelshift_r(W, Wn, sh), __funnelshift_rc(W, Wn, sh + 8));
     }
 }
 
@@ -226,8 +233,8 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restr
 //    gradient tap lies inside the image: the image is interpolated once (Ib, un-descaled, 2 IDP.2A per row) and Scharr is
 //    applied to Ib with two shuffles per row.  Otherwise (window across the image border) the general form with OpenCV's
 //    constant-0 derivative outside the image runs.  The template (I, Ix, Iy) goes to shared memory in FLATTENED pixel order.
-//  iterations (next image): the 441 window pixels are spread over all 32 lanes (14 each): per pixel two 16-bit loads of the
-//    staged tile, one 64-bit template load, 2 IDP.2A, one shift, two sign extensions, two IMAD.
+//  iterations (next image): the window is cut into 63 strips (21 columns x 3 segments of 7 rows), two per lane: 8 pair loads
+//    per strip (vertical reuse), and per pixel one 64-bit template load, 2 IDP.2A, one shift, two sign extensions, two IMAD.
 // All window sums are exact integers; float expressions follow OpenCV's scalar order with _rn intrinsics.
 __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
                                                       float* __restrict__ lk_pts, uint8_t* __restrict__ lk_status, float* __restrict__ lk_err) {
@@ -243,21 +250,22 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
     if (pt >= n) return;  // warp-uniform; most warps of the fixed-size grid leave here
     uint8_t* tile = s_mem + warp * WARP_SMEM;
     uint2* tmpl = reinterpret_cast<uint2*>(tile + TILE_BYTES);  // [pixel y * 21 + x] = (256 - 512 * I, Ix | Iy << 16)
-    if (lane < 32 * NK - NPIX) tmpl[NPIX + lane] = make_uint2(0u, 0u);  // the 7 pad pixels: zero gradient, never rewritten
-    // flattened form: lane owns pixels lane + 32 k; offset of the (x, x+1) pair of row y in a tile whose byte 0 is column x = 0
-    int offJ[NK];
-    {
-        int y = lane >= WIN ? 1 : 0, x = lane - WIN * y;
+    // template layout: entry (round s, row-in-strip j, lane) at tmpl[(s * 7 + j) * 32 + lane]; strip g = 3 x + y / 7 of window
+    // pixel (x, y) belongs to lane g & 31 in round g >> 5.  Strip 63 (lane 31, round 1) does not exist: zero gradient, never
+    // rewritten, so it contributes nothing to the sums.
+    if (lane < SEG) tmpl[(SEG + lane) * 32 + 31] = make_uint2(0u, 0u);
+    int offJ[NROUND];  // byte offset of the strip's first pair (column x, row 7 * seg) in a tile whose byte 0 is column x = 0
 #pragma unroll
-        for (int k = 0; k < NK; ++k) {
-            offJ[k] = lane + 32 * k < NPIX ? y * TROW + pair_off(x) : 0;
-            x += 32 - WIN;  // pixel index + 32 = one row down and 11 columns to the right
-            y += 1;
-            if (x >= WIN) {
-                x -= WIN;
-                y += 1;
-            }
-        }
+    for (int sr = 0; sr < NROUND; ++sr) {
+        const int g = min(lane + 32 * sr, 62), x = g / 3, sg = g - 3 * x;
+        offJ[sr] = row_off(SEG * sg) + pair_off(x);
+    }
+    // setup (column-lane form): where this lane's column x = lane - 1 stores row y: base of segment y / 7, plus (y % 7) * 32
+    int tbase[3];
+#pragma unroll
+    for (int sg = 0; sg < 3; ++sg) {
+        const int g = 3 * (lane - 1) + sg;
+        tbase[sg] = (g >> 5) * SEG * 32 + (g & 31);
     }
     const int ccol = min(lane, 23);  // setup: tile column of this lane
 
@@ -320,7 +328,6 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
         stage_tile(tile, I, G.pitch, ipx - 1, ipy - 1, lane);
         __syncwarp();
         int a11 = 0, a12 = 0, a22 = 0;
-        uint2* tw = tmpl + (lane - 1);  // window column x = lane - 1; row y at tw[y * 21]
         // every gradient tap (columns ipx .. ipx+21, rows ipy .. ipy+21) inside the image?  (warp-uniform)
         const bool inside = ipx >= 0 && ipx + WIN < G.w && ipy >= 0 && ipy + WIN < G.h;
         if (inside) {
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             int dH0 = 0, dH1 = 0, S0 = 0, S1 = 0, ibm = 0;
 #pragma unroll
             for (int r = 1; r < TROWS; ++r) {
-                const uint32_t pr = lds_u16(tp + r * TROW);
+                const uint32_t pr = lds_u16(tp + row_off(r));
                 const int ib = dp2(Wbot, pr, top);  // Ib(r - 1)
                 top = dp2(Wtop, pr, 0);
                 const int ibL = __shfl_up_sync(0xFFFFFFFFu, ib, 1), ibR = __shfl_down_sync(0xFFFFFFFFu, ib, 1);
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                     const int ixv = (3 * (dH0 + dH2) + 10 * dH1 + (1 << 13)) >> 14;
                     const int iyv = (S2 - S0 + (1 << 13)) >> 14;
                     const int iv = (ibm + 256) >> 9;
-                    if (wlane) tw[y * WIN] = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
+                    if (wlane) tmpl[tbase[y / SEG] + (y % SEG) * 32] = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
@@ -360,11 +367,11 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             const bool xin = X >= 0 && X < G.w;
             const uint8_t* tb = tile + ((ccol >> 2) << 3) + (ccol & 3);  // T byte of this lane's column
             const uint8_t* tp = tile + pair_off(ccol);
-            int p0 = tb[0], p1 = tb[TROW];
+            int p0 = tb[0], p1 = tb[row_off(1)];
             int top = 0, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;
 #pragma unroll
             for (int r = 0; r < 22; ++r) {
-                const int p2 = tb[(r + 2) * TROW];
+                const int p2 = tb[row_off(r + 2)];
                 // Scharr gradient at (X, Y = ipy + r) (tile row r + 1)
                 const int V = 3 * (p0 + p2) + 10 * p1, Dv = p2 - p0;
                 const int Vl = __shfl_up_sync(0xFFFFFFFFu, V, 1), Vr = __shfl_down_sync(0xFFFFFFFFu, V, 1);
@@ -374,12 +381,12 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 const int gx = in ? Vr - Vl : 0;
                 const int gy = in ? 3 * (Dl + Dr) + 10 * Dv : 0;
                 const int gxn = __shfl_down_sync(0xFFFFFFFFu, gx, 1), gyn = __shfl_down_sync(0xFFFFFFFFu, gy, 1);
-                const uint32_t pr = lds_u16(tp + (r + 1) * TROW);
+                const uint32_t pr = lds_u16(tp + row_off(r + 1));
                 if (r >= 1) {
                     const int iv = (dp2(Wbot, pr, top) + 256) >> 9;
                     const int ixv = descale(tgx * iw00 + tgxn * iw01 + gx * iw10 + gxn * iw11, 14);
                     const int iyv = descale(tgy * iw00 + tgyn * iw01 + gy * iw10 + gyn * iw11, 14);
-                    if (wlane) tw[(r - 1) * WIN] = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
+                    if (wlane) tmpl[tbase[(r - 1) / SEG] + ((r - 1) % SEG) * 32] = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
@@ -426,13 +433,19 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             }
             int b1 = 0, b2 = 0;
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                const uint32_t pt0 = lds_u16(tile + offJ[k]), pt1 = lds_u16(tile + offJ[k] + TROW);
-                const uint2 t = tl[32 * k];
-                const int diff = dp2(Wbot, pt1, dp2(Wtop, pt0, (int)t.x)) >> 9;  // descale(J interpolated, 9) - I
-                const int gxv = (int)(short)(t.y & 0xFFFFu), gyv = (int)t.y >> 16;
-                b1 += diff * gxv;
-                b2 += diff * gyv;
+            for (int sr = 0; sr < NROUND; ++sr) {
+                const uint8_t* tp = tile + offJ[sr];
+                uint32_t pa = lds_u16(tp);  // the pair of row j; row j + 1's pair is reused as the next row's upper pair
+#pragma unroll
+                for (int j = 0; j < SEG; ++j) {
+                    const uint32_t pb = lds_u16(tp + (row_off(j + 1) - row_off(0)));
+                    const uint2 t = tl[(sr * SEG + j) * 32];
+                    const int diff = dp2(Wbot, pb, dp2(Wtop, pa, (int)t.x)) >> 9;  // descale(J interpolated, 9) - I
+                    const int gxv = (int)(short)(t.y & 0xFFFFu), gyv = (int)t.y >> 16;
+                    b1 += diff * gxv;
+                    b2 += diff * gyv;
+                    pa = pb;
+                }
             }
             const long long sb1 = warp_sum64(b1), sb2 = warp_sum64(b2);
             const float b1f = __fmul_rn((float)sb1, FLT_SCALE), b2f = __fmul_rn((float)sb2, FLT_SCALE);
@@ -469,10 +482,16 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 }
                 int e = 0;
 #pragma unroll
-                for (int k = 0; k < NK; ++k) {
-                    const uint32_t pt0 = lds_u16(tile + offJ[k]), pt1 = lds_u16(tile + offJ[k] + TROW);
-                    const int diff = dp2(Wbot, pt1, dp2(Wtop, pt0, (int)tl[32 * k].x)) >> 9;
-                    if (lane + 32 * k < NPIX) e += abs(diff);
+                for (int sr = 0; sr < NROUND; ++sr) {
+                    const uint8_t* tp = tile + offJ[sr];
+                    uint32_t pa = lds_u16(tp);
+#pragma unroll
+                    for (int j = 0; j < SEG; ++j) {
+                        const uint32_t pb = lds_u16(tp + (row_off(j + 1) - row_off(0)));
+                        const int diff = dp2(Wbot, pb, dp2(Wtop, pa, (int)tl[(sr * SEG + j) * 32].x)) >> 9;
+                        if (lane + 32 * sr < 63) e += abs(diff);
+                        pa = pb;
+                    }
                 }
                 const long long se = warp_sum64(e);
                 err = __fdiv_rn((float)se, (float)(32 * WIN * WIN));
