@@ -236,6 +236,9 @@ def run_b200(a):
                          "kernels": "K1 k_pyramid_fused (one-pass, TMA-staged) + K2 k_fast_cells + K2b k_compact (pyramid + FAST stages)",
                          "algorithmic_bytes_per_launch": bpi * 2 * B, "ms_per_launch": t_pf},
             "stage_ms_per_step": {k: round(v, 4) for k, v in stage.items()},
+            "stage_note": ("event-to-event times per kernel group; pyramid / fast_cells / compact run before the stream fork and lk_track1 "
+                           "(the whole 4-call chain) on the main stream; octree / describe / match (side stream) and fast_full / lk_pyramid "
+                           "run concurrently, so their figures include waiting for SMs" if not a.no_overlap else "single stream"),
             # the kernel with the largest share of the step is the LK tracker; it is bound by instruction issue and the
             # shared-memory pipe, not by HBM or tensor throughput (profiles/*_ncu_full_all_kernels.txt), so it is reported as
             # tracks/s next to the HBM roofline of the pyramid + FAST stages that north_star asks for
