@@ -92,12 +92,8 @@ int Tracking::Detect_OpenCVFASTFeatures() {  // tracking.cpp:94-113
     const int fast_threshold = 20;
     if (svo_fast_detect(c, img.data, img.cols, img.rows, img.step, fast_threshold, 1, reinterpret_cast<svo_keypoint*>(keypoints.data()), cap, &n) != SVO_OK)
         throw std::runtime_error(std::string("svo_fast_detect: ") + svo_last_error(c));
-    int cnt_detected = 0;
-    for (int i = 0; i < n; ++i) {
-        current_frame_->features_left_.push_back(Feature::Ptr(new Feature(current_frame_, keypoints[i])));
-        cnt_detected++;
-    }
-    return cnt_detected;
+    Feature::wrap_keypoints(current_frame_, keypoints.data(), (size_t)n, true, current_frame_->features_left_);  // one block, not n `new`s
+    return n;
 }
 
 int Tracking::Detect_MyORBFeatures() {  // tracking.cpp:502-532
@@ -107,16 +103,10 @@ int Tracking::Detect_MyORBFeatures() {  // tracking.cpp:502-532
     (*mpORBextractorLeft_)(current_frame_->right_img_, cv::Mat(), mvKeys2, mDescriptors2);
     current_frame_->left_Descriptors_ = mDescriptors1;
     current_frame_->right_Descriptors_ = mDescriptors2;
-    int cnt_detected1 = 0, cnt_detected2 = 0;
-    for (auto& kp : mvKeys1) {
-        current_frame_->features_left_.push_back(Feature::Ptr(new Feature(current_frame_, kp)));
-        cnt_detected1++;
-    }
-    for (auto& kp : mvKeys2) {
-        current_frame_->features_right_.push_back(Feature::Ptr(new Feature(current_frame_, kp)));
-        cnt_detected2++;
-    }
-    return std::min(cnt_detected1, cnt_detected2);
+    // the reference sets is_on_left_image_ for neither side (default true); kept
+    Feature::wrap_keypoints(current_frame_, mvKeys1.data(), mvKeys1.size(), true, current_frame_->features_left_);
+    Feature::wrap_keypoints(current_frame_, mvKeys2.data(), mvKeys2.size(), true, current_frame_->features_right_);
+    return (int)std::min(mvKeys1.size(), mvKeys2.size());
 }
 
 static void bf_match(svo_ctx* c, const cv::Mat& q, const cv::Mat& t, std::vector<cv::DMatch>& out) {
