@@ -124,43 +124,31 @@ __global__ void __launch_bounds__(128) k_lk_pad(LkPadParams P, SlotMap map) {
     // source: level 0 comes from the (unpadded) ORB plane, the other levels from their own interior
     const uint8_t* __restrict__ sbase = l == 0 ? P.src0.base + (size_t)slot * P.src0.plane : dbase;
     const int spitch = l == 0 ? P.src0.pitch : D.pitch;
-    // ---- interior columns of the rows that need them (all rows of level 0, the top / bottom border rows of the others):
-    //      16-byte copies (rows are 16-byte aligned), four independent loads in flight per thread
-    const int nv = D.w >> 4, items = nrows * nv;
-    for (int i0 = threadIdx.x; i0 < items; i0 += 4 * 128) {
-        uint4 v[4];
-        int off[4];
+    // 16 threads per row, 8 rows per CTA: no index divisions, 256 contiguous bytes per row and step
+    const int rr = threadIdx.x >> 4, t16 = threadIdx.x & 15;
+    if (rr >= nrows) return;
+    const int yp = r0 + rr;
+    const uint8_t* __restrict__ srow = sbase + (ptrdiff_t)reflect101_any(yp, D.h) * spitch;
+    uint8_t* drow = dbase + (ptrdiff_t)yp * D.pitch;
+    if (l == 0 || yp < 0 || yp >= D.h) {
+        // interior columns (all rows of level 0, the top / bottom border rows of the others): 16-byte copies (rows are 16-byte
+        // aligned), four independent loads in flight per thread, then the ragged end byte-wise
+        const int nv = D.w >> 4;
+        for (int c0 = t16; c0 < nv; c0 += 64) {
+            uint4 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * 128;
-            off[u] = -1;
-            if (i < items) {
-                const int rr = i / nv, c = i - rr * nv, yp = r0 + rr;
-                if (l == 0 || yp < 0 || yp >= D.h) {
-                    v[u] = __ldg(reinterpret_cast<const uint4*>(sbase + (ptrdiff_t)reflect101_any(yp, D.h) * spitch) + c);
-                    off[u] = rr * nv + c;
-                }
-            }
+            for (int u = 0; u < 4; ++u)
+                if (c0 + 16 * u < nv) v[u] = __ldg(reinterpret_cast<const uint4*>(srow) + c0 + 16 * u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c0 + 16 * u < nv) reinterpret_cast<uint4*>(drow)[c0 + 16 * u] = v[u];
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (off[u] >= 0) {
-                const int rr = off[u] / nv, c = off[u] - rr * nv;
-                reinterpret_cast<uint4*>(dbase + (ptrdiff_t)(r0 + rr) * D.pitch)[c] = v[u];
-            }
+        for (int x = (nv << 4) + t16; x < D.w; x += 16) drow[x] = __ldg(srow + x);
     }
-    // ---- ragged end of the interior (w % 16 bytes) and the left / right pads, byte-wise
-    const int tailw = D.w & 15, per = 2 * SVO_LK_PADX + tailw;
-    for (int i = threadIdx.x; i < nrows * per; i += 128) {
-        const int rr = i / per, k = i - rr * per, yp = r0 + rr;
-        int x;
-        if (k < SVO_LK_PADX) x = k - SVO_LK_PADX;
-        else if (k < 2 * SVO_LK_PADX) x = D.w + k - SVO_LK_PADX;
-        else {
-            x = (nv << 4) + k - 2 * SVO_LK_PADX;
-            if (!(l == 0 || yp < 0 || yp >= D.h)) continue;  // interior rows of levels >= 1 already hold their pixels
-        }
-        dbase[(ptrdiff_t)yp * D.pitch + x] = __ldg(sbase + (ptrdiff_t)reflect101_any(yp, D.h) * spitch + reflect101_any(x, D.w));
+    // left / right pads
+    for (int k = t16; k < 2 * SVO_LK_PADX; k += 16) {
+        const int x = k < SVO_LK_PADX ? k - SVO_LK_PADX : D.w + k - SVO_LK_PADX;
+        drow[x] = __ldg(srow + reflect101_any(x, D.w));
     }
 }
 
