@@ -11,6 +11,12 @@ namespace {
 
 constexpr int MT = 128;  // queries per CTA == train descriptors per tile
 
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {  // IMAD (FMA pipe), not LEA / IADD3 (ALU pipe)
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __device__ __forceinline__ void match_core(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
                                            int* __restrict__ idx_out, int* __restrict__ dist_out) {
     __shared__ uint4 tile[MT * 2];
@@ -21,7 +27,7 @@ __device__ __forceinline__ void match_core(const uint8_t* __restrict__ q, int nq
         qa = __ldg(reinterpret_cast<const uint4*>(q) + 2 * qi);
         qb = __ldg(reinterpret_cast<const uint4*>(q) + 2 * qi + 1);
     }
-    int best = 1 << 30, bi = -1;
+    uint32_t bestkey = 0xFFFFFFFFu;  // train sets are far below 2^22 descriptors (checked by the launchers)
     for (int t0 = 0; t0 < nt; t0 += MT) {
         const int cnt = min(MT, nt - t0);
         __syncthreads();
@@ -38,16 +44,17 @@ __device__ __forceinline__ void match_core(const uint8_t* __restrict__ q, int nq
             const uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 ^ x4));
             const uint32_t s2 = x6 ^ x7 ^ s0, c2 = (x6 & x7) | (s0 & (x6 ^ x7));
             const uint32_t s3 = c0 ^ c1 ^ c2, c3 = (c0 & c1) | (c2 & (c0 ^ c1));
-            const int d = __popc(s1) + __popc(s2) + 2 * __popc(s3) + 4 * __popc(c3);
-            if (d < best) {
-                best = d;
-                bi = t0 + j;
-            }
+            // the kernel is bound by the ALU pipe (XOR / LOP3 / POPC); the weighted sum and the (distance, index) key go to the
+            // idle FMA pipe as integer multiply-adds, and one unsigned min replaces compare + two selects.  key = d << 22 | index:
+            // the minimum key is the minimum distance with the LOWEST train index on ties == OpenCV's first-minimum rule
+            const uint32_t d = mad_u32((uint32_t)__popc(c3), 4u, mad_u32((uint32_t)__popc(s3), 2u, (uint32_t)(__popc(s1) + __popc(s2))));
+            bestkey = min(bestkey, mad_u32(d, 1u << 22, (uint32_t)(t0 + j)));
         }
     }
     if (qi < nq) {
-        idx_out[qi] = bi;
-        dist_out[qi] = bi < 0 ? -1 : best;
+        const bool any = bestkey != 0xFFFFFFFFu;
+        idx_out[qi] = any ? (int)(bestkey & ((1u << 22) - 1u)) : -1;
+        dist_out[qi] = any ? (int)(bestkey >> 22) : -1;
     }
 }
 
@@ -92,6 +99,7 @@ extern "C" int svo_match_hamming(svo_ctx* c, const uint8_t* q, int nq, const uin
     if (!c) return SVO_ERR_INVALID;
     if (nq < 0 || nt < 0 || (nq > 0 && (!q || !train_idx || !dist)) || (nt > 0 && !t)) return c->fail(SVO_ERR_INVALID, "svo_match_hamming: bad arguments");
     if (nq == 0) return SVO_OK;
+    if (nt >= (1 << 22)) return c->fail(SVO_ERR_INVALID, "svo_match_hamming: train sets of 2^22 descriptors or more are not supported");
     cudaSetDevice(c->device);
     const size_t qb = svo_align((size_t)nq * 32, 256), tb = svo_align((size_t)std::max(nt, 1) * 32, 256), ob = svo_align((size_t)nq * 4, 256);
     int rc = svo_ensure_scratch(c, qb + tb + 2 * ob);
