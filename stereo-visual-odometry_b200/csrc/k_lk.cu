@@ -186,7 +186,6 @@ __device__ __forceinline__ int dp2(uint32_t a, uint32_t b, int c) {
 // reads at the same time during the iterations (rows j, 7 + j, 14 + j of the same columns) fall into different banks.
 constexpr int TROW = 64, TROWS = 24, TILE_BYTES = TROW * TROWS + 64;
 __host__ __device__ constexpr int row_off(int r) { return r * TROW + (r / 7) * 16; }
-constexpr int NPIX = WIN * WIN;  // 441 window pixels
 constexpr int SEG = 7;           // iteration form: the window is cut into 21 columns x 3 segments of 7 rows = 63 strips; a lane
 constexpr int NROUND = 2;        // owns strips (lane) and (lane + 32): 14 pixels, 2 x 8 pair loads (vertical reuse inside a strip)
 constexpr int WARP_SMEM = TILE_BYTES + 32 * NROUND * SEG * 8;
