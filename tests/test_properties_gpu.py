@@ -133,3 +133,38 @@ def test_error_paths(pkg):
         small.frontend_download(None)  # nothing to deliver
     small.close()
     ctx.close()
+
+
+def test_frontend_is_deterministic_at_full_size(pkg):
+    """KITTI-sized batch run three times from reset: every output byte identical.  The kernels use shared-memory atomics whose
+    ORDER varies between runs (FAST queues, corner lists, per-cell counters); no output may depend on that order."""
+    w, h, B = 1241, 376, 12
+    left, right = pkg.synth_sequence(1000, 9, B, w, h)  # crosses the canvas re-seed at frame 16
+    ctx = pkg.Context(0, w, h, 2 * (B + 1))
+    ctx.orb_configure(1000, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    kc, pc = ctx.orb_capacity(w, h), max(1024, w * h // 64)
+    runs = []
+    for _ in range(3):
+        ctx.frontend_reset()
+        out = pkg.FrontendBuffers(B, kc, pc)
+        ctx.frontend_batch(left, right, out)
+        runs.append(out)
+    # valid prefix of every per-frame array (entries behind the counts are not part of the result)
+    count_of = dict(kps_left="n_left", desc_left="n_left", kps_right="n_right", desc_right="n_right", stereo_idx="n_query", stereo_dist="n_query",
+                    temporal_idx="n_query", temporal_dist="n_query", fast_kps="n_fast", lk_p1="n_seed", lk_p2="n_seed", lk_p3="n_seed",
+                    lk_p0r="n_seed", orb_t2_left="n_orb_matched", orb_t1_left="n_orb_matched", orb_t1_right="n_orb_matched",
+                    lkf_t1_left="n_lk_matched", lkf_t1_right="n_lk_matched", lkf_t2_right="n_lk_matched", lkf_t2_left="n_lk_matched")
+    a = runs[0]
+    for b in runs[1:]:
+        for n in ("n_left", "n_right", "n_query", "n_fast", "n_seed", "n_orb_matched", "n_lk_matched"):
+            assert np.array_equal(getattr(a, n), getattr(b, n)), n
+        for name, cnt in count_of.items():
+            for i in range(B):
+                k = int(getattr(a, cnt)[i])
+                assert np.array_equal(getattr(a, name)[i, :k], getattr(b, name)[i, :k]), (name, i)
+        for i in range(B):
+            k = int(a.n_seed[i])
+            assert np.array_equal(a.lk_status[i, :, :k], b.lk_status[i, :, :k]), ("lk_status", i)
+    assert int(runs[0].n_orb_matched[1:].min()) > 50 and int(runs[0].n_lk_matched[1:].min()) > 200
+    ctx.close()
