@@ -168,3 +168,36 @@ def test_frontend_is_deterministic_at_full_size(pkg):
             assert np.array_equal(a.lk_status[i, :, :k], b.lk_status[i, :, :k]), ("lk_status", i)
     assert int(runs[0].n_orb_matched[1:].min()) > 50 and int(runs[0].n_lk_matched[1:].min()) > 200
     ctx.close()
+
+
+def test_long_sequence_is_independent_of_batching(pkg):
+    """BASELINE-sized frames, a few hundred of them (several canvas re-seeds): the units of a sequence do not depend on how it is
+    cut into batches (128 frames per batch as in bench.py vs 48): per-frame counts and order-sensitive checksums of every list."""
+    import zlib
+    w, h, F = 1241, 376, 288
+    left, right = pkg.synth_sequence(1000, 0, F, w, h)
+
+    def run(B):
+        ctx = pkg.Context(0, w, h, 2 * (B + 1))
+        ctx.orb_configure(1000, 1.2, 8, 20, 7)
+        ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+        kc, pc = ctx.orb_capacity(w, h), max(1024, w * h // 64)
+        rows = []
+        for f0 in range(0, F, B):
+            n = min(B, F - f0)
+            out = pkg.FrontendBuffers(n, kc, pc, fields=("kps_left", "desc_left", "n_left", "n_query", "temporal_idx", "n_seed", "lk_p3", "lk_status",
+                                                         "n_orb_matched", "orb_t2_left", "n_lk_matched", "lkf_t2_left"))
+            ctx.frontend_batch(left[f0:f0 + n], right[f0:f0 + n], out)
+            for i in range(n):
+                nl, nq, ns, nm, nk = (int(x[i]) for x in (out.n_left, out.n_query, out.n_seed, out.n_orb_matched, out.n_lk_matched))
+                crc = 0
+                for a in (out.kps_left[i, :nl], out.desc_left[i, :nl], out.temporal_idx[i, :nq], out.lk_p3[i, :ns], out.lk_status[i, :, :ns],
+                          out.orb_t2_left[i, :nm], out.lkf_t2_left[i, :nk]):
+                    crc = zlib.crc32(np.ascontiguousarray(a).tobytes(), crc)
+                rows.append((nl, nq, ns, nm, nk, crc))
+        ctx.close()
+        return rows
+
+    a, b = run(128), run(48)
+    assert len(a) == F and a == b
+    assert min(r[3] for r in a[1:]) > 20 and min(r[4] for r in a[1:]) > 200
