@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t a0 = *reinterpret_cast<const uint32_t*>(row0 + woff[i]), a1 = *reinterpret_cast<const uint32_t*>(row0 + woff[i] + 4);
-                        T0[i] = (int)__dp2a_lo(al[i], __funnelshift_r(a0, a1, sh[i]), 0u);
+                        T0[i] = (int)(__dp2a_lo(al[i], __funnelshift_r(a0, a1, sh[i]), 0u) >> 4);  // rows are kept as T >> 4
                     }
                 }
                 {
@@ -231,14 +231,14 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t c0 = *reinterpret_cast<const uint32_t*>(row1 + woff[i]), c1 = *reinterpret_cast<const uint32_t*>(row1 + woff[i] + 4);
-                        T1[i] = (int)__dp2a_lo(al[i], __funnelshift_r(c0, c1, sh[i]), 0u);
+                        T1[i] = (int)(__dp2a_lo(al[i], __funnelshift_r(c0, c1, sh[i]), 0u) >> 4);
                     }
                 }
                 uint32_t out = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     // pixels outside the needed range read column 0 of the source region: harmless garbage, never used
-                    const int v = (((b0 * (T0[i] >> 4)) >> 16) + ((b1 * (T1[i] >> 4)) >> 16) + 2) >> 2;  // valid pixels: always in [0, 255]
+                    const int v = (((b0 * T0[i]) >> 16) + ((b1 * T1[i]) >> 16) + 2) >> 2;  // valid pixels: always in [0, 255]
                     out |= (uint32_t)(v & 0xFF) << (8 * i);
                     Tc[i] = T1[i];
                 }
