@@ -25,6 +25,8 @@
 // Ordered output without atomics on the order: per-cell (K2) / per-word (K9) keep masks, a scan, then positional writes.
 //
 // Roofline: every level pixel is read from HBM once (window halos come from L2); the kernels are integer-ALU bound.
+#include <cuda.h>
+
 #include <type_traits>
 
 #include "svo_common.cuh"
@@ -215,145 +217,324 @@ __device__ __forceinline__ void score_region(const uint8_t* pix, int PW, int sx0
     for (int i = threadIdx.x; i < tn; i += FT) score_pixel<E16>(pix, PW, sx0, sy0, tail[i], thr, sc, SW, sink);
 }
 
-// bits [x0, x0 + n) (n <= 64) of a bitmap row
-__device__ __forceinline__ unsigned long long row_bits(const uint32_t* nzrow, int x0, int n) {
-    const int w = x0 >> 5, sh = x0 & 31;
-    unsigned long long lo = (unsigned long long)nzrow[w] | ((unsigned long long)nzrow[w + 1] << 32);
-    unsigned long long m = lo >> sh;
-    if (sh) m |= (unsigned long long)nzrow[w + 2] << (64 - sh);
-    return n >= 64 ? m : (m & ((1ull << n) - 1ull));
-}
+// ---------------------------------------------------------------------------------------------------------------
+// K2 (v4).  One CTA = one tile = one cell row x up to 8 cells (<= 250 px wide, <= 64 rows).
+//   load     the pixel window (tile + 3 px) arrives by ONE TMA copy: the level plane is described as a 3-D tensor
+//            [rows][pitch / 16][16 bytes] with a box of 17 chunks, so the box is 272 bytes wide (a 2-D box is limited to 256)
+//            and lands in shared memory with a compile-time pitch -- the 16 ring offsets of the score are immediates.
+//   pretest  a lane tests 16 pixels (one LDS.128 per row) and a warp two rows per step; the 16 pass flags are gathered
+//            into a bit code with IDP.4A and expanded into queue entries through a 256-entry table (no per-bit branches).
+//   score    as before (dense warps from per-warp queues); a hit writes its score into a map whose cells are one column
+//            apart (so the suppression needs no cell-border tests) and sets its bit in a [row][cell] 64-bit hit map.
+//   select   warp w owns cell w, lane = row: non-maximum suppression of the row's hits, the cell's "any corner >= iniTh"
+//            vote, a warp scan of the row counts and the ordered emission all stay in registers of one warp.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PW4 = 272;    // pitch of the pixel window and of the score map
+constexpr int MC4 = 8;      // cells per tile (wCell >= 30, tile <= 250 px)
+constexpr int QCAP4 = 544;  // per-warp queue: up to 31 left over + 512 new per pre-test step
 
-struct FastSmem {
-    int PW, PH;  // pixel window pitch (multiple of 16) / rows
-    int SW, SH;  // score map pitch / rows (1-px zero frame)
-    int NWB;     // bitmap words per row (+3 slack words so that row_bits may read past the end)
-    int MC;      // max cells per tile
-    int LCAP;    // corner list capacity (entries)
-    // the two keep bitmaps (all / strong survivors of the suppression) alias the pixel window, which is dead once the scores exist
-    __host__ __device__ size_t keep_bytes() const { return (size_t)2 * NWB * SH * sizeof(uint32_t); }
-    __host__ __device__ size_t pix_bytes() const { return ((size_t)PW * PH > keep_bytes() ? (size_t)PW * PH : keep_bytes() + 15) & ~(size_t)15; }
-    __host__ __device__ size_t sc_off() const { return pix_bytes(); }
-    __host__ __device__ size_t cell_off() const { return sc_off() + (((size_t)SW * SH + 15) & ~(size_t)15); }
-    __host__ __device__ size_t list_off() const { return cell_off() + (size_t)(3 * MC + 4) * sizeof(int); }
-    __host__ __device__ size_t queue_off() const { return list_off() + (((size_t)LCAP * 2 + 15) & ~(size_t)15); }
-    __host__ __device__ size_t tail_off() const { return queue_off() + (((size_t)FW * QCAP * 2 + 15) & ~(size_t)15); }
-    __host__ __device__ size_t total() const { return tail_off() + (size_t)(4 + FW + FW * 32) * sizeof(uint32_t); }
+struct FastTmaps {
+    CUtensorMap m[SVO_MAX_LEVELS];
+};
+struct FastLevel {
+    int h;            // level height (rows per slot in the tensor)
+    int wCell;
+    unsigned magic;   // floor(x / wCell) == umulhi(x, magic) for x * wCell < 2^32
+    int box_bytes;    // bytes one TMA box delivers: PW4 * (hCell + 6)
+};
+struct FastParams {
+    FastLevel lv[SVO_MAX_LEVELS];
+    int minTh, iniTh;
+    int sc_off, hit_off, q_off, ctl_off, tail_off, zero16;  // shared-memory layout (bytes); zero16: uint4 words to clear from sc_off
 };
 
+// offsets (3 bits each, ascending) of the set bits of an 8-bit code, count in bits 24..27
+struct BitLut {
+    uint32_t v[256];
+    constexpr BitLut() : v() {
+        for (int i = 0; i < 256; ++i) {
+            uint32_t w = 0;
+            int n = 0;
+            for (int b = 0; b < 8; ++b)
+                if ((i >> b) & 1) w |= (uint32_t)b << (3 * n++);
+            v[i] = w | ((uint32_t)n << 24);
+        }
+    }
+};
+__device__ const BitLut kBitLut{};
+
+// FAST-9 score with a compile-time pitch: every ring load is [p + immediate]
+template <int PW>
+__device__ __forceinline__ int fast9_score_c(const uint8_t* p) {
+    const int v = p[0];
+    const uint32_t base = ((uint32_t)(v + 256) << 16) | (uint32_t)(256 - v);
+    constexpr int off[16] = {3 * PW, 3 * PW + 1, 2 * PW + 2, PW + 3, 3, -PW + 3, -2 * PW + 2, -3 * PW + 1,
+                             -3 * PW, -3 * PW - 1, -2 * PW - 2, -PW - 3, -3, PW - 3, 2 * PW - 2, 3 * PW - 1};
+    uint32_t d[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d[k] = (uint32_t)p[off[k]] * 0xFFFF0001u + base;
+    uint32_t m3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    uint32_t best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const uint32_t a = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        const uint32_t b = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+        best = __vimax3_s16x2(best, a, b);
+    }
+    return max((int)(best & 0xFFFF), (int)(best >> 16)) - 257;
+}
+
+// pre-test of one word: flag (0x01 per byte) of the pixels that can still be corners
 template <bool POW2>
-__global__ void __launch_bounds__(FT) k_fast_cells(PyrGeom g, SlotMap map, const FastTile* __restrict__ tiles, FastSmem L,
-                                                   uint32_t* __restrict__ tile_buf, int* __restrict__ tile_cnt, int* __restrict__ flags,
-                                                   uint32_t tile_buf_per_slot, int n_tiles) {
-    extern __shared__ __align__(16) uint8_t smem[];
+__device__ __forceinline__ uint32_t pretest4b(uint32_t c, uint32_t cm, uint32_t cp, uint32_t up, uint32_t dn, uint32_t K7, uint32_t keep) {
+    const uint32_t dl = __vabsdiffu4(c, __funnelshift_r(cm, c, 8));
+    const uint32_t dr = __vabsdiffu4(c, __funnelshift_r(c, cp, 24));
+    const uint32_t du = __vabsdiffu4(c, up), dd = __vabsdiffu4(c, dn);
+    uint32_t x;
+    if (POW2) {
+        const uint32_t h = dl | dr, v = du | dd;
+        x = (((h & 0x7F7F7F7Fu) + K7) | h) & (((v & 0x7F7F7F7Fu) + K7) | v);
+    } else {
+        const uint32_t h = ((dl & 0x7F7F7F7Fu) + K7) | dl | ((dr & 0x7F7F7F7Fu) + K7) | dr;
+        const uint32_t v = ((du & 0x7F7F7F7Fu) + K7) | du | ((dd & 0x7F7F7F7Fu) + K7) | dd;
+        x = h & v;
+    }
+    return (x >> 7) & keep;
+}
+
+struct Score4Ctx {
+    const uint8_t* pix;
+    uint8_t* sc;
+    uint32_t* hit;
+    int sx0, wCell, thr;
+    unsigned magic;
+};
+
+// queue entry: row << 9 | window column
+__device__ __forceinline__ void score_entry4(const Score4Ctx& S, uint32_t e) {
+    const int ey = (int)(e >> 9), px = (int)(e & 511);
+    const int s = fast9_score_c<PW4>(S.pix + (ey + 3) * PW4 + px);
+    if (s >= S.thr && s > 0) {
+        const int ex = px - S.sx0;
+        const int cidx = (int)__umulhi((unsigned)ex, S.magic), lx = ex - cidx * S.wCell;
+        S.sc[(ey + 1) * PW4 + ex + cidx + 1] = (uint8_t)s;
+        atomicOr(S.hit + ((ey * MC4 + cidx) << 1) + (lx >> 5), 1u << (lx & 31));
+    }
+}
+
+__device__ __forceinline__ int lowest_bit64(unsigned long long m) {  // index of the lowest set bit (m != 0)
+    const uint32_t lo = (uint32_t)m;
+    return lo ? __ffs((int)lo) - 1 : 31 + __ffs((int)(uint32_t)(m >> 32));
+}
+
+template <bool POW2>
+__global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastTmaps maps, const __grid_constant__ FastParams P, SlotMap map,
+                                                   const FastTile* __restrict__ tiles, uint32_t* __restrict__ tile_buf, int* __restrict__ tile_cnt,
+                                                   int* __restrict__ flags, uint32_t tile_buf_per_slot, int n_tiles) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) unsigned long long mbar;
     const FastTile t = tiles[blockIdx.x];
     const int slot = map.slot(blockIdx.y);
-    const LevelGeom& G = g.lvl[t.level];
+    const FastLevel fl = P.lv[t.level];
     uint8_t* pix = smem;
-    uint8_t* sc = smem + L.sc_off();
-    uint32_t* keepAll = reinterpret_cast<uint32_t*>(smem);  // [row + 1][NWB]; aliases pix after the score stage
-    uint32_t* keepStr = keepAll + L.NWB * L.SH;
-    int* cellflag = reinterpret_cast<int*>(smem + L.cell_off());  // [MC] flag, [MC] cntAll, [MC] cntStr, [0] list counter
-    int* cntAll = cellflag + L.MC;
-    int* cntStr = cntAll + L.MC;
-    int* list_n = cntStr + L.MC;
-    uint16_t* list = reinterpret_cast<uint16_t*>(smem + L.list_off());
-    uint16_t* queues = reinterpret_cast<uint16_t*>(smem + L.queue_off());
-    uint32_t* tailq = reinterpret_cast<uint32_t*>(smem + L.tail_off());
+    uint8_t* sc = smem + P.sc_off;
+    uint32_t* hit = reinterpret_cast<uint32_t*>(smem + P.hit_off);  // [row][MC4] 64-bit
+    uint16_t* queues = reinterpret_cast<uint16_t*>(smem + P.q_off);
+    int* ctl = reinterpret_cast<int*>(smem + P.ctl_off);  // [0] pooled leftovers, [1..8] queue fills, [16..23] cell totals
+    uint16_t* tail = reinterpret_cast<uint16_t*>(smem + P.tail_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
     const int tw = t.x1 - t.x0, th = t.y1 - t.y0;
-    const int xa = (t.x0 - 3) & ~15;
-    const int nchunk = (t.x1 + 3 - xa + 15) >> 4;
-    load_window(G.base + (size_t)slot * G.plane, G.pitch, xa, t.y0 - 3, th + 6, nchunk, pix, L.PW);
-    {  // zero the score map and the per-cell counters (one contiguous region)
+    const int xa = (t.x0 - 4) & ~15;  // first column of the window: 16-byte aligned (TMA), 4..19 px left of the tile
+    const int sx0 = t.x0 - xa;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar)), "r"(fl.box_bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(pix)),
+                     "l"(&maps.m[t.level]), "r"(0), "r"(xa >> 4), "r"(slot * fl.h + t.y0 - 3), "r"((uint32_t)__cvta_generic_to_shared(&mbar))
+                     : "memory");
+    }
+    {  // while the copy is in flight: clear the score map, the hit map and the counters (one contiguous region)
         uint4* z = reinterpret_cast<uint4*>(sc);
-        const int nz16 = (int)((L.list_off() - L.sc_off() + 15) >> 4);
-        for (int i = threadIdx.x; i < nz16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x < 4 + FW) tailq[threadIdx.x] = 0;  // pooled-leftover counter and the per-warp queue fills
+        for (int i = threadIdx.x; i < P.zero16; i += FT) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();  // the mbarrier is initialised for everybody, the maps are clear
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done)
+                         : "r"((uint32_t)__cvta_generic_to_shared(&mbar))
+                         : "memory");
+    }
+
+    // ---- pre-test + exact score
+    const Score4Ctx S{pix, sc, hit, sx0, fl.wCell, P.minTh, fl.magic};
+    {
+        const int T = min(P.minTh + 1, 128);  // necessary: |difference| >= T
+        const uint32_t K7 = (uint32_t)(0x80 - T) * 0x01010101u;
+        uint16_t* wq = queues + warp * QCAP4;
+        volatile int* wcnt = ctl + 1 + warp;
+        const uint32_t wcnt_addr = (uint32_t)__cvta_generic_to_shared(const_cast<int*>(wcnt));
+        // 0x01 per byte of the 16 pixels from window column colb on whose pixel lies in the tile, [sx0, sx0 + tw)
+        auto keep_masks = [&](int colb, uint32_t (&keep)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int lo = colb + 4 * i;
+                const int skip_lo = min(max(sx0 - lo, 0), 4), skip_hi = min(max(lo + 4 - (sx0 + tw), 0), 4);
+                const uint32_t a = skip_lo >= 4 ? 0u : 0x01010101u << (8 * skip_lo), b = skip_hi >= 4 ? 0u : 0x01010101u >> (8 * skip_hi);
+                keep[i] = a & b;
+            }
+        };
+        // one step of a warp: every active lane tests the 16 pixels of tile row yy from window column colb on, the survivors go
+        // to the warp's queue, and full groups of 32 queued pixels are scored at once
+        auto step = [&](bool active, int yy, int colb, const uint32_t (&keep)[4]) {
+            uint32_t code = 0;
+            if (active) {
+                const uint8_t* rowp = pix + (yy + 3) * PW4 + colb;
+                const uint4 c = *reinterpret_cast<const uint4*>(rowp);
+                const uint4 u = *reinterpret_cast<const uint4*>(rowp - 3 * PW4), d = *reinterpret_cast<const uint4*>(rowp + 3 * PW4);
+                const uint32_t cm = *reinterpret_cast<const uint32_t*>(rowp - 4), cp = *reinterpret_cast<const uint32_t*>(rowp + 16);
+                const uint32_t q0 = pretest4b<POW2>(c.x, cm, c.y, u.x, d.x, K7, keep[0]);
+                const uint32_t q1 = pretest4b<POW2>(c.y, c.x, c.z, u.y, d.y, K7, keep[1]);
+                const uint32_t q2 = pretest4b<POW2>(c.z, c.y, c.w, u.z, d.z, K7, keep[2]);
+                const uint32_t q3 = pretest4b<POW2>(c.w, c.z, cp, u.w, d.w, K7, keep[3]);
+                const uint32_t lo = __dp4a(q1, 0x80402010u, __dp4a(q0, 0x08040201u, 0u));
+                const uint32_t hi = __dp4a(q3, 0x80402010u, __dp4a(q2, 0x08040201u, 0u));
+                code = lo | (hi << 8);
+            }
+            if (code) {
+                uint32_t la = __ldg(&kBitLut.v[code & 255u]), lb = __ldg(&kBitLut.v[code >> 8]);
+                uint32_t pos;
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(pos) : "r"(wcnt_addr), "r"((la >> 24) + (lb >> 24)) : "memory");
+                uint32_t e0 = ((uint32_t)yy << 9) + (uint32_t)colb;
+#pragma unroll 1
+                for (int k = (int)(la >> 24); k > 0; --k) {
+                    wq[pos++] = (uint16_t)(e0 + (la & 7u));
+                    la >>= 3;
+                }
+                e0 += 8;
+#pragma unroll 1
+                for (int k = (int)(lb >> 24); k > 0; --k) {
+                    wq[pos++] = (uint16_t)(e0 + (lb & 7u));
+                    lb >>= 3;
+                }
+            }
+            __syncwarp();
+            int qn = *wcnt;
+            if (qn >= 32) {
+                do {
+                    qn -= 32;
+                    score_entry4(S, wq[qn + lane]);
+                } while (qn >= 32);
+                __syncwarp();
+                if (lane == 0) *wcnt = qn;
+                __syncwarp();
+            }
+        };
+        const int cb = (sx0 >> 4) << 4;  // first window column of lane 0: the 16 lanes of a row cover [cb, cb + 256)
+        {
+            const int half = lane >> 4, colb = cb + 16 * (lane & 15);
+            uint32_t keep[4];
+            keep_masks(colb, keep);
+            for (int rp = warp; 2 * rp < th; rp += FW) step(2 * rp + half < th, 2 * rp + half, colb, keep);
+        }
+        if (sx0 + tw > cb + 256) {  // (CTA-uniform) a 17th chunk of up to 9 pixels: warp w takes rows 8 w .. 8 w + 7 in one more step
+            uint32_t keep[4];
+            keep_masks(cb + 256, keep);
+            if (8 * warp < th) step(lane < 8 && 8 * warp + lane < th, 8 * warp + lane, cb + 256, keep);
+        }
+        const int qn = *wcnt;
+        if (qn) {  // leftovers (< 32 per warp) are pooled and scored by full warps after the barrier
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ctl, qn);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (lane < qn) tail[base + lane] = wq[lane];
+        }
     }
     __syncthreads();
-
-    const CornerSink sink{nullptr, 0, list, list_n, L.LCAP};
-    score_region<POW2, true>(pix, L.PW, t.x0 - xa, 3, tw, th, g.minTh, sc, L.SW, sink, queues + warp * QCAP, tailq);
-    __syncthreads();
-    {  // the pixel window is dead: clear the keep bitmaps that alias it
-        uint32_t* z = keepAll;
-        const int nw = 2 * L.NWB * L.SH;
-        for (int i = threadIdx.x; i < nw; i += FT) z[i] = 0;
-    }
+    if ((int)threadIdx.x < ctl[0]) score_entry4(S, tail[threadIdx.x]);
     __syncthreads();
 
-    // ---- one thread per corner: non-maximum suppression clipped to the corner's cell, per-cell threshold statistics
-    const int wCell = G.wCell;
-    const int ncorner = min(*list_n, L.LCAP);
-    const unsigned magic = 0xFFFFFFFFu / (unsigned)wCell + 1u;  // floor(x / wCell) == umulhi(x, magic) for x * wCell < 2^32
-    for (int i = threadIdx.x; i < ncorner; i += FT) {
-        const int e = list[i], ly = e >> 10, x = e & 1023;
-        const int cidx = (int)__umulhi((unsigned)x, magic), cx0 = cidx * wCell, lx = x - cx0, cw = min(cx0 + wCell, tw) - cx0;
-        const uint8_t* s1 = sc + (size_t)(ly + 1) * L.SW + x + 1;
-        const uint8_t* s0 = s1 - L.SW;
-        const uint8_t* s2 = s1 + L.SW;
-        const int s = s1[0];
-        bool keep = s > s0[0] && s > s2[0];
-        if (lx > 0) keep = keep && s > s0[-1] && s > s1[-1] && s > s2[-1];
-        if (lx < cw - 1) keep = keep && s > s0[1] && s > s1[1] && s > s2[1];
-        if (keep) {
-            const int w = (ly + 1) * L.NWB + (x >> 5);
-            const uint32_t bit = 1u << (x & 31);
-            atomicOr(keepAll + w, bit);
-            atomicAdd(&cntAll[cidx], 1);
-            if (s >= g.iniTh) {
-                atomicOr(keepStr + w, bit);
-                atomicAdd(&cntStr[cidx], 1);
-                cellflag[cidx] = 1;
+    // ---- warp w = cell w, lane = row (two chunks of 32 rows at most): suppression, the cell's threshold vote, row scan
+    unsigned long long sel[2] = {0ull, 0ull};
+    int rowoff[2] = {0, 0};
+    int cell_total = 0;
+    const int cidx = warp;
+    const int gap = cidx + 1;  // column shift of this cell in the score map
+    const int cx0 = cidx * fl.wCell;
+    if (cidx < t.ncells) {
+        unsigned long long kA[2] = {0ull, 0ull}, kS[2] = {0ull, 0ull};
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int ly = 32 * ch + lane;
+            if (ly < th) {
+                unsigned long long m = *reinterpret_cast<const unsigned long long*>(hit + ((ly * MC4 + cidx) << 1));
+                const uint8_t* s1 = sc + (ly + 1) * PW4 + cx0 + gap;
+                while (m) {
+                    const int b = lowest_bit64(m);
+                    m &= m - 1;
+                    const uint8_t* q = s1 + b;
+                    const int s = q[0];
+                    const bool k = s > q[-PW4 - 1] && s > q[-PW4] && s > q[-PW4 + 1] && s > q[-1] && s > q[1] && s > q[PW4 - 1] && s > q[PW4] &&
+                                   s > q[PW4 + 1];
+                    if (k) {
+                        kA[ch] |= 1ull << b;
+                        if (s >= P.iniTh) kS[ch] |= 1ull << b;
+                    }
+                }
             }
         }
-    }
-    __syncthreads();
-    // ---- every warp scans the (<= 32) per-cell counts, then owns whole cells: lanes = rows, warp scan of the row counts,
-    //      and each lane writes the survivors of its row at their final position (cell-major, row-major inside the cell)
-    int total;
-    int mybase;
-    {
-        const int v = lane < t.ncells ? (cellflag[lane] ? cntStr[lane] : cntAll[lane]) : 0;
-        int incl = v;
+        const bool strong = __any_sync(0xFFFFFFFFu, (kS[0] | kS[1]) != 0ull);
+        int run = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += n;
-        }
-        total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        mybase = incl - v;  // lane c holds the base of cell c
-    }
-    uint32_t* out = tile_buf + (size_t)slot * tile_buf_per_slot + t.out_off;
-    for (int cidx = warp; cidx < t.ncells; cidx += FW) {
-        const uint32_t* keep = cellflag[cidx] ? keepStr : keepAll;
-        const int cx0 = cidx * wCell, cw = min(cx0 + wCell, tw) - cx0;
-        int run = __shfl_sync(0xFFFFFFFFu, mybase, cidx);
-        for (int r0 = 0; r0 < th; r0 += 32) {
-            const int ly = r0 + lane;
-            unsigned long long m = ly < th ? row_bits(keep + (ly + 1) * L.NWB, cx0, cw) : 0ull;
-            const int c = __popcll(m);
+        for (int ch = 0; ch < 2; ++ch) {
+            sel[ch] = strong ? kS[ch] : kA[ch];
+            const int c = __popcll(sel[ch]);
             int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                 if (lane >= o) incl += n;
             }
-            int o = run + incl - c;
+            rowoff[ch] = run + incl - c;
             run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (th <= 32) break;
+        }
+        cell_total = run;
+        if (lane == 0) ctl[16 + cidx] = run;
+    }
+    __syncthreads();
+    int cell_base = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < MC4; ++k) {
+        const int v = ctl[16 + k];
+        if (k < cidx) cell_base += v;
+        total += v;
+    }
+    if (cidx < t.ncells && cell_total) {
+        uint32_t* out = tile_buf + (size_t)slot * tile_buf_per_slot + t.out_off;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int ly = 32 * ch + lane;
+            unsigned long long m = sel[ch];
+            int o = cell_base + rowoff[ch];
+            const uint8_t* s1 = sc + (ly + 1) * PW4 + cx0 + gap;
             while (m) {
-                const int lx = __ffsll((long long)m) - 1;
+                const int b = lowest_bit64(m);
                 m &= m - 1;
-                if (o < t.out_cap) out[o] = pack_cand(t.x0 + cx0 + lx - SVO_MINB, t.y0 + ly - SVO_MINB, sc[(size_t)(ly + 1) * L.SW + cx0 + lx + 1]);
+                if (o < t.out_cap) out[o] = pack_cand(t.x0 + cx0 + b - SVO_MINB, t.y0 + ly - SVO_MINB, s1[b]);
                 ++o;
             }
         }
     }
     if (threadIdx.x == 0) {
         tile_cnt[(size_t)slot * n_tiles + blockIdx.x] = min(total, t.out_cap);
-        if (total > t.out_cap || *list_n > L.LCAP) atomicOr(flags + slot, SVO_FLAG_TILE_OVERFLOW);
+        if (total > t.out_cap) atomicOr(flags + slot, SVO_FLAG_TILE_OVERFLOW);
     }
 }
 
@@ -455,7 +636,7 @@ __device__ int block_scan_excl_ft(int* a, int n, int* wtmp) {  // in-place exclu
 __global__ void __launch_bounds__(FT) k_fast_full(LevelGeom G, SlotMap map, const FastTile* __restrict__ tiles, FullSmem L, int thr,
                                                   uint32_t* __restrict__ tile_buf, int* __restrict__ tile_cnt, int* __restrict__ flags,
                                                   uint32_t buf_per_slot, int n_tiles) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     const FastTile t = tiles[blockIdx.x];
     const int slot = map.slot(blockIdx.y);
     uint8_t* pix = smem;
@@ -611,28 +792,37 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
     {
         StageTimer t(c, 1);
         if (c->n_tiles > 0) {
-            FastSmem L{};
-            int max_area = 0;
+            if (!c->fast_tma) return c->fail(SVO_ERR_CUDA, "FAST tensor maps are not available (cuTensorMapEncodeTiled failed)");
+            FastParams P{};
+            int PH = 0, TH = 0;
             for (const FastTile& ft : c->tiles) {
-                const int xa = (ft.x0 - 3) & ~15;
-                L.PW = std::max(L.PW, (int)svo_align(ft.x1 + 3 - xa + 4, 16));
-                L.PH = std::max(L.PH, ft.y1 - ft.y0 + 6);
-                L.SW = std::max(L.SW, (int)svo_align(ft.x1 - ft.x0 + 2, 16));
-                L.SH = std::max(L.SH, ft.y1 - ft.y0 + 2);
-                L.NWB = std::max(L.NWB, (ft.x1 - ft.x0 + 31) / 32 + 3);
-                max_area = std::max(max_area, (ft.x1 - ft.x0) * (ft.y1 - ft.y0));
-                if (g.lvl[ft.level].wCell > 64) return c->fail(SVO_ERR_INVALID, "FAST cells wider than 64 px are not supported");
-                if (ft.x1 - ft.x0 > 1024 || ft.y1 - ft.y0 > 64) return c->fail(SVO_ERR_INVALID, "FAST tile larger than 1024 x 64 px");
+                const LevelGeom& G = g.lvl[ft.level];
+                const int xa = (ft.x0 - 4) & ~15;
+                if (ft.x1 + 3 - xa > PW4 || ft.ncells > MC4 || ft.y1 - ft.y0 > 64 || G.wCell > 64 || ft.y1 - ft.y0 > G.hCell)
+                    return c->fail(SVO_ERR_INVALID, "FAST tile outside the supported geometry (<= 250 x 64 px, <= 8 cells of <= 64 px)");
+                PH = std::max(PH, G.hCell + 6);
+                TH = std::max(TH, ft.y1 - ft.y0);
             }
-            L.MC = 32;  // the cell scan is one warp wide
-            L.LCAP = std::max(256, max_area / 2);  // corners (score >= minTh) before suppression; overflow -> SVO_ERR_CAPACITY
-            const size_t smem = L.total();
-            if (smem > 200 * 1024) return c->fail(SVO_ERR_INVALID, "FAST tile does not fit in shared memory");
+            for (int l = 0; l < g.nlevels; ++l) {
+                const LevelGeom& G = g.lvl[l];
+                if (G.tile_count == 0) continue;
+                P.lv[l] = FastLevel{G.h, G.wCell, 0xFFFFFFFFu / (unsigned)G.wCell + 1u, PW4 * (G.hCell + 6)};
+            }
+            P.minTh = g.minTh;
+            P.iniTh = g.iniTh;
+            P.sc_off = (int)svo_align((size_t)PW4 * PH, 128);
+            P.hit_off = P.sc_off + PW4 * (TH + 2);
+            P.ctl_off = P.hit_off + TH * MC4 * 8;
+            P.q_off = P.ctl_off + 32 * (int)sizeof(int);
+            P.zero16 = (P.q_off - P.sc_off) / 16;
+            P.tail_off = P.q_off + FW * QCAP4 * 2;
+            const size_t smem = (size_t)P.tail_off + FT * 2;
             const bool pow2 = g.minTh + 1 <= 128 && ((g.minTh + 1) & g.minTh) == 0;
             auto kern = pow2 ? k_fast_cells<true> : k_fast_cells<false>;
             SVO_CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dim3 grid(c->n_tiles, n_img);
-            kern<<<grid, FT, smem, c->stream>>>(g, map, c->d_tiles, L, c->d_tile_buf, c->d_tile_cnt, c->d_flags, c->tile_buf_per_slot, c->n_tiles);
+            kern<<<grid, FT, smem, c->stream>>>(*reinterpret_cast<const FastTmaps*>(c->tmap_fast), P, map, c->d_tiles, c->d_tile_buf, c->d_tile_cnt,
+                                                c->d_flags, c->tile_buf_per_slot, c->n_tiles);
             ++c->launches;
         }
     }

@@ -175,92 +175,66 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& D = g.lvl[l];
         const PyrRect r = T.lv[l];
-        const int nw = r.x1n - r.x0, nh = r.y1n - r.y0;
-        if (nw <= 0 || nh <= 0) break;  // deeper levels of this tile are empty too (CTA-uniform)
+        if (r.ng <= 0) break;  // deeper levels of this tile are empty too (CTA-uniform)
         uint8_t* dbuf = (l & 1) ? bufB : bufA;
-        const int d_orgx = r.x0 & ~3;
-        const int ng = (r.x1n - d_orgx + 3) >> 2;             // 4-pixel groups
-        const int d_pitch = ng * 4 + 8;
-        // small-integer divisions through the float reciprocal (exact here: operands < 2^9, (a + 0.5) / b is never within
-        // 2^-8 of an integer): the generic 32-bit division costs ~25 instructions, three times per thread and level
-        const float inv_ng = __frcp_rn((float)ng);
-        const int nrl = (int)(256.5f * inv_ng);               // row lanes = 256 / ng
-        const int rl = (int)(((float)threadIdx.x + 0.5f) * inv_ng), gi = (int)threadIdx.x - rl * ng;
-        if (rl < nrl) {
-            const int gx = d_orgx + 4 * gi;                   // level x of the group's first pixel
-            // column coefficients of the 4 pixels (tables are padded to a multiple of 4 entries)
-            const int4 xo = *reinterpret_cast<const int4*>(D.xofs + gx);
-            const int4 alv = *reinterpret_cast<const int4*>(D.alpha + 2 * gx);
-            const uint32_t al[4] = {(uint32_t)alv.x, (uint32_t)alv.y, (uint32_t)alv.z, (uint32_t)alv.w};
-            const int sxs[4] = {xo.x, xo.y, xo.z, xo.w};
-            unsigned woff[4], sh[4];
-            bool valid[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                valid[i] = gx + i >= r.x0 && gx + i < r.x1n;
-                const int rel = valid[i] ? sxs[i] - s_orgx : 0;
-                woff[i] = (unsigned)rel & ~3u;
-                sh[i] = ((unsigned)rel & 3u) * 8u;
-            }
-            const bool own_full = gx >= r.x0 && gx + 4 <= r.x1o;
+        const int d_orgx = (r.x0 & ~3) - 4;  // level x of byte 0 of a buffer row (one group of front margin)
+        const int rl = ((int)threadIdx.x * r.magic) >> 16, gi = (int)threadIdx.x - rl * r.ng;  // row lane, 4-pixel group
+        if (rl < r.nrl) {
+            const int gx = d_orgx + 4 + 4 * gi;  // level x of the group's first pixel
+            const int4 m0 = __ldg(D.xmeta + (gx >> 1)), m1 = __ldg(D.xmeta + (gx >> 1) + 1);
+            const int rel0 = m0.x - s_orgx;  // >= 0 (host-checked): source byte of pixel 0's left tap in the buffer row
+            const unsigned woff = (unsigned)rel0 & ~3u, sh0 = ((unsigned)rel0 & 3u) * 8u;
+            const uint32_t sel1 = (uint32_t)m0.y, sel2 = sel1 >> 8, sel3 = sel1 >> 16;
+            const uint32_t al0 = (uint32_t)m0.z, al1 = (uint32_t)m0.w, al2 = (uint32_t)m1.x, al3 = (uint32_t)m1.y;
+            const bool store_g = gx >= r.x0 && gx < r.x1o;  // a group is written by the tile that owns its first pixel
             uint8_t* gdst = D.base + (size_t)slot * D.plane + gx;
+            uint8_t* sdst = dbuf + 4 + 4 * gi;
+            const uint8_t* sbase = src + woff;
+            // horizontal pass of one source row for the 4 pixels: 3 aligned words hold all 8 taps; pixel i's byte pair is cut out
+            // with one PRMT (selector from the host table) and multiplied with its (a0, a1) pair by one IDP.2A; kept as T >> 4
+            auto hrow = [&](int sy, uint32_t (&Tq)[4]) {
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(sbase + (sy - s_orgy) * s_pitch);
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                const uint32_t u0 = __funnelshift_r(w0, w1, sh0), u1 = __funnelshift_r(w1, w2, sh0);
+                Tq[0] = __dp2a_lo(al0, u0, 0u) >> 4;
+                Tq[1] = __dp2a_lo(al1, __byte_perm(u0, u1, sel1), 0u) >> 4;
+                Tq[2] = __dp2a_lo(al2, __byte_perm(u0, u1, sel2), 0u) >> 4;
+                Tq[3] = __dp2a_lo(al3, __byte_perm(u0, u1, sel3), 0u) >> 4;
+            };
             // each row lane owns a contiguous run of rows, so the horizontal pass of the lower source row is reused as the
             // upper row of the next destination row (5 of 6 rows at scale 1.2)
-            const int chunk = (int)(((float)(nh + nrl - 1) + 0.5f) * __frcp_rn((float)nrl));  // ceil(nh / nrl)
-            const int ya = r.y0 + rl * chunk, yb = min(ya + chunk, (int)r.y1n);
+            const int ya = r.y0 + rl * r.chunk, yb = min(ya + r.chunk, (int)r.y1n);
             int cached_row = -1;
-            int Tc[4] = {0, 0, 0, 0};
+            uint32_t Tc[4] = {0, 0, 0, 0};
             for (int y = ya; y < yb; ++y) {
-                const int2 yo = *reinterpret_cast<const int2*>(D.yofs + 2 * y);
-                const int bt = *reinterpret_cast<const int*>(D.beta + 2 * y);
-                const int b0 = (short)(bt & 0xFFFF), b1 = (short)(bt >> 16);
-                int T0[4], T1[4];
-                if (yo.x == cached_row) {
+                const int4 ym = __ldg(D.ymeta + y);  // {top tap row, bottom tap row, beta0, beta1}
+                uint32_t T0[4], T1[4];
+                if (ym.x == cached_row) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) T0[i] = Tc[i];
                 } else {
-                    const uint8_t* row0 = src + (yo.x - s_orgy) * s_pitch;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t a0 = *reinterpret_cast<const uint32_t*>(row0 + woff[i]), a1 = *reinterpret_cast<const uint32_t*>(row0 + woff[i] + 4);
-                        T0[i] = (int)(__dp2a_lo(al[i], __funnelshift_r(a0, a1, sh[i]), 0u) >> 4);  // rows are kept as T >> 4
-                    }
+                    hrow(ym.x, T0);
                 }
-                {
-                    const uint8_t* row1 = src + (yo.y - s_orgy) * s_pitch;
+                hrow(ym.y, T1);
+                // v = (((b0 * T0) >> 16) + ((b1 * T1) >> 16) + 2) >> 2 for two pixels at a time: the upper halves of the two
+                // products are gathered by PRMT, both sums and the rounding constant are one 3-input add (no carry between
+                // the halves: each sum is <= 1023), and the bytes of (sum >> 2) are picked by a last PRMT
+                const uint32_t b0 = (uint32_t)ym.z, b1 = (uint32_t)ym.w;
+                const uint32_t s01 = __byte_perm(b0 * T0[0], b0 * T0[1], 0x7632) + __byte_perm(b1 * T1[0], b1 * T1[1], 0x7632) + 0x00020002u;
+                const uint32_t s23 = __byte_perm(b0 * T0[2], b0 * T0[3], 0x7632) + __byte_perm(b1 * T1[2], b1 * T1[3], 0x7632) + 0x00020002u;
+                const uint32_t out = __byte_perm(s01 >> 2, s23 >> 2, 0x6420);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t c0 = *reinterpret_cast<const uint32_t*>(row1 + woff[i]), c1 = *reinterpret_cast<const uint32_t*>(row1 + woff[i] + 4);
-                        T1[i] = (int)(__dp2a_lo(al[i], __funnelshift_r(c0, c1, sh[i]), 0u) >> 4);
-                    }
-                }
-                uint32_t out = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    // pixels outside the needed range read column 0 of the source region: harmless garbage, never used
-                    const int v = (((b0 * T0[i]) >> 16) + ((b1 * T1[i]) >> 16) + 2) >> 2;  // valid pixels: always in [0, 255]
-                    out |= (uint32_t)(v & 0xFF) << (8 * i);
-                    Tc[i] = T1[i];
-                }
-                cached_row = yo.y;
-                *reinterpret_cast<uint32_t*>(dbuf + (y - r.y0) * d_pitch + 4 * gi) = out;
-                if (y < r.y1o) {
-                    uint8_t* p = gdst + (size_t)y * D.pitch;
-                    if (own_full) {
-                        *reinterpret_cast<uint32_t*>(p) = out;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (gx + i >= r.x0 && gx + i < r.x1o) p[i] = (uint8_t)(out >> (8 * i));
-                    }
-                }
+                for (int i = 0; i < 4; ++i) Tc[i] = T1[i];
+                cached_row = ym.y;
+                *reinterpret_cast<uint32_t*>(sdst + (y - r.y0) * r.pitch) = out;
+                if (store_g && y < r.y1o) *reinterpret_cast<uint32_t*>(gdst + (size_t)y * D.pitch) = out;
             }
         }
         __syncthreads();
         src = dbuf;
         s_orgx = d_orgx;
         s_orgy = r.y0;
-        s_pitch = d_pitch;
+        s_pitch = r.pitch;
     }
 }
 

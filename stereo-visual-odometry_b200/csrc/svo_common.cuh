@@ -48,6 +48,10 @@ struct LevelGeom {
     const short* alpha;  // 2 per dst x
     const int* yofs;     // 2 per dst y (clamped row indices)
     const short* beta;   // 2 per dst y
+    // the same tables in the form the one-pass kernel reads (K1 fused): per 4-pixel group {left tap of pixel 0, byte selectors
+    // of pixels 1..3 relative to it, alpha pairs of the 4 pixels, 2 pad words}; per row {top tap row, bottom tap row, beta0, beta1}
+    const int4* xmeta;   // 2 per group
+    const int4* ymeta;   // 1 per dst y
 };
 
 struct PyrGeom {
@@ -61,6 +65,10 @@ struct PyrGeom {
 struct PyrRect {
     short x0, x1o, x1n;  // owned [x0, x1o), needed [x0, x1n)
     short y0, y1o, y1n;
+    // thread layout of the level inside the CTA, tabulated on the host: 4-pixel groups per row (from x0 & ~3), row lanes
+    // (256 / ng), rows per row lane, shared-memory pitch (4-byte front margin + groups + 8), 65536 / ng + 1
+    short ng, nrl, chunk, pitch;
+    int magic;
 };
 struct PyrTile {
     PyrRect lv[SVO_MAX_LEVELS];
@@ -135,11 +143,15 @@ struct svo_ctx {
 
     // ---- one-pass pyramid (K1 fused): tiles, TMA descriptor of level 0, shared-memory budget
     bool fused_pyr = false;
+    bool pyr_meta_ok = false;  // the xmeta / ymeta tables fit the one-pass kernel's assumptions
     std::vector<PyrTile> ptiles;
     PyrTile* d_ptiles = nullptr;
     int n_ptiles = 0;
     int pyr_bufB_bytes = 0;
     alignas(64) unsigned char tmap_l0[128] = {};  // CUtensorMap
+    // K2: one 3-D tensor map per level ([rows][pitch / 16][16 bytes], box 17 chunks x (hCell + 6) rows)
+    alignas(64) unsigned char tmap_fast[SVO_MAX_LEVELS][128] = {};
+    bool fast_tma = false;
 
     // ---- device memory
     uint8_t* d_pyr = nullptr;  // all levels, all slots

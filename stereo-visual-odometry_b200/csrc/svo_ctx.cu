@@ -297,7 +297,7 @@ int svo_layout(svo_ctx* c, int w, int h) {
     // ---- resize coefficient tables (what cv::resize computes per call)
     {
         std::vector<uint8_t> host;
-        std::vector<size_t> off_x(L), off_a(L), off_y(L), off_b(L);
+        std::vector<size_t> off_x(L), off_a(L), off_y(L), off_b(L), off_xm(L), off_ym(L);
         auto reserve = [&](size_t bytes) {
             size_t o = svo_align(host.size(), 16);
             host.resize(o + bytes, 0);
@@ -335,6 +335,47 @@ int svo_layout(svo_ctx* c, int w, int h) {
                 beta[2 * dy + 1] = (short)std::min(32767, std::max(-32768, cv_round_f(fy * 2048.f)));
             }
         }
+        // the K1-fused form of the same tables (see LevelGeom::xmeta / ymeta)
+        c->pyr_meta_ok = true;
+        for (int l = 1; l < L; ++l) {
+            const int dw = g.lvl[l].w, dh = g.lvl[l].h;
+            const int ngr = (dw + 3) / 4 + 2;
+            off_xm[l] = reserve(sizeof(int) * 8 * ngr);
+            off_ym[l] = reserve(sizeof(int) * 4 * dh);
+            const int* xofs = (const int*)(host.data() + off_x[l]);
+            const short* alpha = (const short*)(host.data() + off_a[l]);
+            const int* yofs = (const int*)(host.data() + off_y[l]);
+            const short* beta = (const short*)(host.data() + off_b[l]);
+            int* xm = (int*)(host.data() + off_xm[l]);
+            int* ym = (int*)(host.data() + off_ym[l]);
+            for (int gi = 0; gi < ngr; ++gi) {
+                int sx[4];
+                uint32_t al[4];
+                for (int i = 0; i < 4; ++i) {
+                    const int dx = std::min(4 * gi + i, dw - 1);  // pixels in the pitch padding repeat the last column
+                    sx[i] = xofs[dx];
+                    al[i] = (uint32_t)(uint16_t)alpha[2 * dx] | ((uint32_t)(uint16_t)alpha[2 * dx + 1] << 16);
+                }
+                uint32_t sel = 0;
+                for (int i = 1; i < 4; ++i) {
+                    const int d = sx[i] - sx[0];
+                    if (d < 0 || d > 6) c->pyr_meta_ok = false;  // taps of a group must lie within 8 source bytes (scale < ~1.3)
+                    const int dc = std::min(std::max(d, 0), 6);
+                    sel |= (uint32_t)(dc | ((dc + 1) << 4)) << (8 * (i - 1));
+                }
+                xm[8 * gi + 0] = sx[0];
+                xm[8 * gi + 1] = (int)sel;
+                for (int i = 0; i < 4; ++i) xm[8 * gi + 2 + i] = (int)al[i];
+                xm[8 * gi + 6] = xm[8 * gi + 7] = 0;
+            }
+            for (int dy = 0; dy < dh; ++dy) {
+                ym[4 * dy + 0] = yofs[2 * dy];
+                ym[4 * dy + 1] = yofs[2 * dy + 1];
+                ym[4 * dy + 2] = beta[2 * dy];
+                ym[4 * dy + 3] = beta[2 * dy + 1];
+                if (beta[2 * dy] < 0 || beta[2 * dy + 1] < 0) c->pyr_meta_ok = false;
+            }
+        }
         host.resize(svo_align(host.size() + 16, 16), 0);
         SVO_CUDA_TRY(c, cudaMalloc(&c->d_tables, host.size()));
         SVO_CUDA_TRY(c, cudaMemcpy(c->d_tables, host.data(), host.size(), cudaMemcpyHostToDevice));
@@ -343,6 +384,8 @@ int svo_layout(svo_ctx* c, int w, int h) {
             g.lvl[l].alpha = (const short*)((uint8_t*)c->d_tables + off_a[l]);
             g.lvl[l].yofs = (const int*)((uint8_t*)c->d_tables + off_y[l]);
             g.lvl[l].beta = (const short*)((uint8_t*)c->d_tables + off_b[l]);
+            g.lvl[l].xmeta = (const int4*)((uint8_t*)c->d_tables + off_xm[l]);
+            g.lvl[l].ymeta = (const int4*)((uint8_t*)c->d_tables + off_ym[l]);
         }
     }
 
@@ -351,7 +394,7 @@ int svo_layout(svo_ctx* c, int w, int h) {
     // level l-1 is its owned region plus that small right/bottom fringe, computed redundantly by the neighbours.
     c->fused_pyr = false;
     c->ptiles.clear();
-    if (L >= 2 && !getenv("SVO_PYRAMID_PER_LEVEL")) {
+    if (L >= 2 && c->pyr_meta_ok && !getenv("SVO_PYRAMID_PER_LEVEL")) {
         std::vector<std::vector<int>> hx(L), hy(L);  // host copies of the left / top tap index per destination pixel
         bool ok = true;
         for (int l = 1; l < L && ok; ++l) {
@@ -389,7 +432,10 @@ int svo_layout(svo_ctx* c, int w, int h) {
                         t.lv[l] = PyrRect{(short)x0, (short)x1, (short)x1, (short)y0, (short)y1, (short)y1};
                     }
                     for (int l = L - 1; l >= 1; --l) {  // needed regions, deepest level first
-                        const PyrRect& d = t.lv[l];
+                        PyrRect& d = t.lv[l];
+                        // a 4-pixel group is stored (as one word) by the tile that owns its first pixel, so that tile needs
+                        // valid values for the whole group
+                        if (d.x1o > d.x0 && d.y1o > d.y0) d.x1n = (short)std::max<int>(d.x1n, std::min((d.x1o + 3) & ~3, g.lvl[l].w));
                         const bool empty = d.x1n <= d.x0 || d.y1n <= d.y0;
                         if (l == 1) {
                             PyrRect& s0 = t.lv[0];
@@ -407,15 +453,23 @@ int svo_layout(svo_ctx* c, int w, int h) {
                             if (hx[l][d.x0] < sr.x0 || hy[l][d.y0] < sr.y0) fits = false;  // cannot happen by construction
                         }
                     }
-                    for (int l = 1; l < L; l += 2) {  // odd levels live in buffer B
-                        const PyrRect& r = t.lv[l];
-                        const int pw = (int)svo_align(r.x1n - (r.x0 & ~3), 4) + 8;
-                        maxB = std::max(maxB, pw * std::max(0, r.y1n - r.y0));
-                    }
-                    for (int l = 2; l < L; l += 2) {  // even levels reuse buffer A (the level-0 box)
-                        const PyrRect& r = t.lv[l];
-                        const int pw = (int)svo_align(r.x1n - (r.x0 & ~3), 4) + 8;
-                        if (pw * std::max(0, r.y1n - r.y0) > SVO_PYR_BOX_W * SVO_PYR_BOX_H) fits = false;
+                    for (int l = 1; l < L; ++l) {  // thread layout and shared-memory footprint of every level
+                        PyrRect& r = t.lv[l];
+                        const int nw = r.x1n - r.x0, nh = r.y1n - r.y0;
+                        if (nw <= 0 || nh <= 0) { r.ng = 0; continue; }
+                        const int ng = (r.x1n - (r.x0 & ~3) + 3) >> 2;
+                        if (ng > 256) { fits = false; break; }
+                        r.ng = (short)ng;
+                        r.nrl = (short)(256 / ng);
+                        r.chunk = (short)((nh + r.nrl - 1) / r.nrl);
+                        r.pitch = (short)(4 * ng + 12);
+                        r.magic = 65536 / ng + 1;
+                        // the source row origin of level l >= 2 is 4 px left of the source tile's first group: the first group's
+                        // left tap must not lie further left
+                        if (l >= 2 && hx[l][r.x0 & ~3] < (t.lv[l - 1].x0 & ~3) - 4) fits = false;
+                        const int bytes = r.pitch * nh + 16;
+                        if (l & 1) maxB = std::max(maxB, bytes);  // odd levels live in buffer B, even levels reuse the level-0 box
+                        else if (bytes > SVO_PYR_BOX_W * SVO_PYR_BOX_H) fits = false;
                     }
                     tiles.push_back(t);
                 }
@@ -511,6 +565,30 @@ int svo_layout(svo_ctx* c, int w, int h) {
         ncap = std::max(ncap, G.lkp_cap);
     }
     c->n_tiles = (int)c->tiles.size();
+    // K2 tensor maps: level l of all slots as [S * h rows][pitch / 16 chunks][16 bytes]; the 17-chunk box gives a 272-byte wide
+    // window (a 2-D box could be 256 bytes at most); the start column of a box is a chunk index, i.e. 16-byte aligned
+    c->fast_tma = false;
+    if (c->n_tiles) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) {
+            bool ok = true;
+            for (int l = 0; l < L && ok; ++l) {
+                const LevelGeom& G = g.lvl[l];
+                if (G.tile_count == 0) continue;
+                const cuuint64_t dims[3] = {16, (cuuint64_t)G.pitch / 16, (cuuint64_t)G.h * (cuuint64_t)S};
+                const cuuint64_t strides[2] = {16, (cuuint64_t)G.pitch};
+                const cuuint32_t box[3] = {16, 17, (cuuint32_t)(G.hCell + 6)};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                ok = ((EncodeFn)fn)(reinterpret_cast<CUtensorMap*>(c->tmap_fast[l]), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, G.base, dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            c->fast_tma = ok;
+        }
+    }
     c->tile_buf_per_slot = tile_off;
     c->cand_per_slot = cand_off;
     c->lkp_per_slot = lkp_off;

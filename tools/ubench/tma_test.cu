@@ -40,8 +40,9 @@ int main() {
     CUresult r = ((EncodeFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("encode %d\n", (int)r);
-    for (int t = 0; t < 3; ++t) {
-        int x = t == 0 ? 0 : (t == 1 ? 48 : 1104), y = t == 0 ? 0 : (t == 1 ? 376 + 5 : 700);
+    const int xs[7] = {0, 48, 1104, 13, 1107, 3, 1030}, ys[7] = {0, 381, 700, 7, 690, 375, 1};
+    for (int t = 0; t < 7; ++t) {
+        int x = xs[t], y = ys[t];
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 96 + 1024);
         k<<<1, 256, 256 * 96 + 1024>>>(tm, o, x, y);
         cudaError_t e = cudaDeviceSynchronize();
