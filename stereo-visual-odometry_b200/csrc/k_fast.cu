@@ -245,7 +245,7 @@ struct FastLevel {
 struct FastParams {
     FastLevel lv[SVO_MAX_LEVELS];
     int minTh, iniTh;
-    int sc_off, hit_off, q_off, ctl_off, tail_off, zero16;  // shared-memory layout (bytes); zero16: uint4 words to clear from sc_off
+    int sc_off, hit_off, q_off, ctl_off, tail_off, cl_off, ccap, zero16;  // shared-memory layout (bytes); zero16: uint4 words to clear from sc_off
 };
 
 // offsets (3 bits each, ascending) of the set bits of an 8-bit code, count in bits 24..27
@@ -288,7 +288,7 @@ __device__ __forceinline__ int fast9_score_c(const uint8_t* p) {
 
 // pre-test of one word: flag (0x01 per byte) of the pixels that can still be corners
 template <bool POW2>
-__device__ __forceinline__ uint32_t pretest4b(uint32_t c, uint32_t cm, uint32_t cp, uint32_t up, uint32_t dn, uint32_t K7, uint32_t keep) {
+__device__ __forceinline__ uint32_t pretest4b(uint32_t c, uint32_t cm, uint32_t cp, uint32_t up, uint32_t dn, uint32_t K7) {
     const uint32_t dl = __vabsdiffu4(c, __funnelshift_r(cm, c, 8));
     const uint32_t dr = __vabsdiffu4(c, __funnelshift_r(c, cp, 24));
     const uint32_t du = __vabsdiffu4(c, up), dd = __vabsdiffu4(c, dn);
@@ -301,13 +301,15 @@ __device__ __forceinline__ uint32_t pretest4b(uint32_t c, uint32_t cm, uint32_t 
         const uint32_t v = ((du & 0x7F7F7F7Fu) + K7) | du | ((dd & 0x7F7F7F7Fu) + K7) | dd;
         x = h & v;
     }
-    return (x >> 7) & keep;
+    return (x >> 7) & 0x01010101u;
 }
 
 struct Score4Ctx {
     const uint8_t* pix;
     uint8_t* sc;
-    uint32_t* hit;
+    int* ccount;       // [MC4] corners per cell
+    uint16_t* clist;   // [MC4][ccap] corners of a cell: row << 6 | column in the cell
+    int ccap;
     int sx0, wCell, thr;
     unsigned magic;
 };
@@ -320,7 +322,8 @@ __device__ __forceinline__ void score_entry4(const Score4Ctx& S, uint32_t e) {
         const int ex = px - S.sx0;
         const int cidx = (int)__umulhi((unsigned)ex, S.magic), lx = ex - cidx * S.wCell;
         S.sc[(ey + 1) * PW4 + ex + cidx + 1] = (uint8_t)s;
-        atomicOr(S.hit + ((ey * MC4 + cidx) << 1) + (lx >> 5), 1u << (lx & 31));
+        const int o = atomicAdd(S.ccount + cidx, 1);  // order inside the list is irrelevant
+        if (o < S.ccap) S.clist[cidx * S.ccap + o] = (uint16_t)((ey << 6) | lx);
     }
 }
 
@@ -373,56 +376,60 @@ __global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastT
     }
 
     // ---- pre-test + exact score
-    const Score4Ctx S{pix, sc, hit, sx0, fl.wCell, P.minTh, fl.magic};
+    uint16_t* clist = reinterpret_cast<uint16_t*>(smem + P.cl_off);
+    const Score4Ctx S{pix, sc, ctl + 16, clist, P.ccap, sx0, fl.wCell, P.minTh, fl.magic};
     {
         const int T = min(P.minTh + 1, 128);  // necessary: |difference| >= T
         const uint32_t K7 = (uint32_t)(0x80 - T) * 0x01010101u;
         uint16_t* wq = queues + warp * QCAP4;
         volatile int* wcnt = ctl + 1 + warp;
         const uint32_t wcnt_addr = (uint32_t)__cvta_generic_to_shared(const_cast<int*>(wcnt));
-        // 0x01 per byte of the 16 pixels from window column colb on whose pixel lies in the tile, [sx0, sx0 + tw)
-        auto keep_masks = [&](int colb, uint32_t (&keep)[4]) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int lo = colb + 4 * i;
-                const int skip_lo = min(max(sx0 - lo, 0), 4), skip_hi = min(max(lo + 4 - (sx0 + tw), 0), 4);
-                const uint32_t a = skip_lo >= 4 ? 0u : 0x01010101u << (8 * skip_lo), b = skip_hi >= 4 ? 0u : 0x01010101u >> (8 * skip_hi);
-                keep[i] = a & b;
+        // bit i set: window column colb + i lies in the tile, [sx0, sx0 + tw)
+        auto valid_bits = [&](int colb) {
+            const int lo = min(max(sx0 - colb, 0), 16), hi = min(max(sx0 + tw - colb, 0), 16);
+            return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+        };
+        // up to 8 survivors of one byte code (table word l: 3-bit offsets, count << 24) -> queue; the common counts are predicated
+        // straight-line code, only a code with more than 3 survivors takes the loop
+        auto push8 = [&](uint32_t l, uint32_t e0, uint32_t& pos) {
+            const int n = (int)(l >> 24);
+            if (n > 0) wq[pos] = (uint16_t)(e0 + (l & 7u));
+            if (n > 1) wq[pos + 1] = (uint16_t)(e0 + ((l >> 3) & 7u));
+            if (n > 2) wq[pos + 2] = (uint16_t)(e0 + ((l >> 6) & 7u));
+            if (n > 3) {
+                uint32_t r = l >> 9;
+#pragma unroll 1
+                for (int k = 3; k < n; ++k) {
+                    wq[pos + k] = (uint16_t)(e0 + (r & 7u));
+                    r >>= 3;
+                }
             }
+            pos += n;
         };
         // one step of a warp: every active lane tests the 16 pixels of tile row yy from window column colb on, the survivors go
         // to the warp's queue, and full groups of 32 queued pixels are scored at once
-        auto step = [&](bool active, int yy, int colb, const uint32_t (&keep)[4]) {
+        auto step = [&](bool active, int yy, int colb, uint32_t valid) {
             uint32_t code = 0;
             if (active) {
                 const uint8_t* rowp = pix + (yy + 3) * PW4 + colb;
                 const uint4 c = *reinterpret_cast<const uint4*>(rowp);
                 const uint4 u = *reinterpret_cast<const uint4*>(rowp - 3 * PW4), d = *reinterpret_cast<const uint4*>(rowp + 3 * PW4);
                 const uint32_t cm = *reinterpret_cast<const uint32_t*>(rowp - 4), cp = *reinterpret_cast<const uint32_t*>(rowp + 16);
-                const uint32_t q0 = pretest4b<POW2>(c.x, cm, c.y, u.x, d.x, K7, keep[0]);
-                const uint32_t q1 = pretest4b<POW2>(c.y, c.x, c.z, u.y, d.y, K7, keep[1]);
-                const uint32_t q2 = pretest4b<POW2>(c.z, c.y, c.w, u.z, d.z, K7, keep[2]);
-                const uint32_t q3 = pretest4b<POW2>(c.w, c.z, cp, u.w, d.w, K7, keep[3]);
+                const uint32_t q0 = pretest4b<POW2>(c.x, cm, c.y, u.x, d.x, K7);
+                const uint32_t q1 = pretest4b<POW2>(c.y, c.x, c.z, u.y, d.y, K7);
+                const uint32_t q2 = pretest4b<POW2>(c.z, c.y, c.w, u.z, d.z, K7);
+                const uint32_t q3 = pretest4b<POW2>(c.w, c.z, cp, u.w, d.w, K7);
                 const uint32_t lo = __dp4a(q1, 0x80402010u, __dp4a(q0, 0x08040201u, 0u));
                 const uint32_t hi = __dp4a(q3, 0x80402010u, __dp4a(q2, 0x08040201u, 0u));
-                code = lo | (hi << 8);
+                code = (lo | (hi << 8)) & valid;
             }
             if (code) {
-                uint32_t la = __ldg(&kBitLut.v[code & 255u]), lb = __ldg(&kBitLut.v[code >> 8]);
+                const uint32_t la = __ldg(&kBitLut.v[code & 255u]), lb = __ldg(&kBitLut.v[code >> 8]);
                 uint32_t pos;
                 asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(pos) : "r"(wcnt_addr), "r"((la >> 24) + (lb >> 24)) : "memory");
-                uint32_t e0 = ((uint32_t)yy << 9) + (uint32_t)colb;
-#pragma unroll 1
-                for (int k = (int)(la >> 24); k > 0; --k) {
-                    wq[pos++] = (uint16_t)(e0 + (la & 7u));
-                    la >>= 3;
-                }
-                e0 += 8;
-#pragma unroll 1
-                for (int k = (int)(lb >> 24); k > 0; --k) {
-                    wq[pos++] = (uint16_t)(e0 + (lb & 7u));
-                    lb >>= 3;
-                }
+                const uint32_t e0 = ((uint32_t)yy << 9) + (uint32_t)colb;
+                push8(la, e0, pos);
+                push8(lb, e0 + 8, pos);
             }
             __syncwarp();
             int qn = *wcnt;
@@ -439,14 +446,14 @@ __global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastT
         const int cb = (sx0 >> 4) << 4;  // first window column of lane 0: the 16 lanes of a row cover [cb, cb + 256)
         {
             const int half = lane >> 4, colb = cb + 16 * (lane & 15);
-            uint32_t keep[4];
-            keep_masks(colb, keep);
-            for (int rp = warp; 2 * rp < th; rp += FW) step(2 * rp + half < th, 2 * rp + half, colb, keep);
+            const uint32_t valid = valid_bits(colb);
+            for (int rp = warp; 2 * rp < th; rp += FW) step(2 * rp + half < th, 2 * rp + half, colb, valid);
         }
-        if (sx0 + tw > cb + 256) {  // (CTA-uniform) a 17th chunk of up to 9 pixels: warp w takes rows 8 w .. 8 w + 7 in one more step
-            uint32_t keep[4];
-            keep_masks(cb + 256, keep);
-            if (8 * warp < th) step(lane < 8 && 8 * warp + lane < th, 8 * warp + lane, cb + 256, keep);
+        if (sx0 + tw > cb + 256) {  // (CTA-uniform) a 17th chunk of up to 9 pixels: one warp takes 32 rows of it in one step, lane = row
+            const uint32_t valid = valid_bits(cb + 256);
+            const int w0 = (int)(blockIdx.x & 7u);
+            if (warp == w0) step(lane < th, lane, cb + 256, valid);
+            if (th > 32 && warp == ((w0 + 1) & 7)) step(32 + lane < th, 32 + lane, cb + 256, valid);
         }
         const int qn = *wcnt;
         if (qn) {  // leftovers (< 32 per warp) are pooled and scored by full warps after the barrier
@@ -460,59 +467,70 @@ __global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastT
     if ((int)threadIdx.x < ctl[0]) score_entry4(S, tail[threadIdx.x]);
     __syncthreads();
 
-    // ---- warp w = cell w, lane = row (two chunks of 32 rows at most): suppression, the cell's threshold vote, row scan
+    // ---- warp w = cell w.  Dense suppression over the cell's corner list (one lane per corner, 8 neighbours by a max tree; the
+    // cells are one zero column apart in the score map, rows 0 and th + 1 are zero), the cell's "any corner >= iniTh" vote,
+    // the survivors' bits into a [row][cell] 64-bit map; then lane = row: popcount, warp scan, ordered emission.
     unsigned long long sel[2] = {0ull, 0ull};
     int rowoff[2] = {0, 0};
     int cell_total = 0;
+    bool list_overflow = false;
     const int cidx = warp;
-    const int gap = cidx + 1;  // column shift of this cell in the score map
     const int cx0 = cidx * fl.wCell;
+    const uint8_t* scell = sc + PW4 + cx0 + cidx + 1;  // score of (row 0, column 0) of this cell
     if (cidx < t.ncells) {
-        unsigned long long kA[2] = {0ull, 0ull}, kS[2] = {0ull, 0ull};
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            const int ly = 32 * ch + lane;
-            if (ly < th) {
-                unsigned long long m = *reinterpret_cast<const unsigned long long*>(hit + ((ly * MC4 + cidx) << 1));
-                const uint8_t* s1 = sc + (ly + 1) * PW4 + cx0 + gap;
-                while (m) {
-                    const int b = lowest_bit64(m);
-                    m &= m - 1;
-                    const uint8_t* q = s1 + b;
-                    const int s = q[0];
-                    const bool k = s > q[-PW4 - 1] && s > q[-PW4] && s > q[-PW4 + 1] && s > q[-1] && s > q[1] && s > q[PW4 - 1] && s > q[PW4] &&
-                                   s > q[PW4 + 1];
-                    if (k) {
-                        kA[ch] |= 1ull << b;
-                        if (s >= P.iniTh) kS[ch] |= 1ull << b;
-                    }
-                }
+        int n = ctl[16 + cidx];
+        list_overflow = n > P.ccap;
+        n = min(n, P.ccap);
+        uint16_t* cl = clist + cidx * P.ccap;
+        unsigned any_strong = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            bool strong = false;
+            if (i < n) {
+                const int e = cl[i], ey = e >> 6, lx = e & 63;
+                const uint8_t* q = scell + ey * PW4 + lx;
+                const int s = q[0];
+                const int m1 = __vimax3_s32(q[-PW4 - 1], q[-PW4], q[-PW4 + 1]), m2 = __vimax3_s32(q[-1], q[1], q[PW4 - 1]);
+                const int m = max(__vimax3_s32(q[PW4], q[PW4 + 1], m1), m2);
+                const bool keep = s > m;
+                strong = keep && s >= P.iniTh;
+                cl[i] = (uint16_t)(e | (keep ? 0x4000 : 0) | (strong ? 0x8000 : 0));
+            }
+            any_strong |= __ballot_sync(0xFFFFFFFFu, strong);
+        }
+        const int need = any_strong ? 0xC000 : 0x4000;
+        for (int i = lane; i < n; i += 32) {
+            const int e = cl[i];
+            if ((e & need) == need) {
+                const int ey = (e >> 6) & 63, lx = e & 63;
+                atomicOr(hit + ((ey * MC4 + cidx) << 1) + (lx >> 5), 1u << (lx & 31));
             }
         }
-        const bool strong = __any_sync(0xFFFFFFFFu, (kS[0] | kS[1]) != 0ull);
+        __syncwarp();
         int run = 0;
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-            sel[ch] = strong ? kS[ch] : kA[ch];
+            const int ly = 32 * ch + lane;
+            sel[ch] = ly < th ? *reinterpret_cast<const unsigned long long*>(hit + ((ly * MC4 + cidx) << 1)) : 0ull;
             const int c = __popcll(sel[ch]);
             int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += n;
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
             }
             rowoff[ch] = run + incl - c;
             run += __shfl_sync(0xFFFFFFFFu, incl, 31);
             if (th <= 32) break;
         }
         cell_total = run;
-        if (lane == 0) ctl[16 + cidx] = run;
+        if (lane == 0) ctl[24 + cidx] = run;
     }
     __syncthreads();
     int cell_base = 0, total = 0;
 #pragma unroll
     for (int k = 0; k < MC4; ++k) {
-        const int v = ctl[16 + k];
+        const int v = ctl[24 + k];
         if (k < cidx) cell_base += v;
         total += v;
     }
@@ -523,7 +541,7 @@ __global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastT
             const int ly = 32 * ch + lane;
             unsigned long long m = sel[ch];
             int o = cell_base + rowoff[ch];
-            const uint8_t* s1 = sc + (ly + 1) * PW4 + cx0 + gap;
+            const uint8_t* s1 = scell + ly * PW4;
             while (m) {
                 const int b = lowest_bit64(m);
                 m &= m - 1;
@@ -532,6 +550,7 @@ __global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastT
             }
         }
     }
+    if (list_overflow && lane == 0) atomicOr(flags + slot, SVO_FLAG_TILE_OVERFLOW);
     if (threadIdx.x == 0) {
         tile_cnt[(size_t)slot * n_tiles + blockIdx.x] = min(total, t.out_cap);
         if (total > t.out_cap) atomicOr(flags + slot, SVO_FLAG_TILE_OVERFLOW);
@@ -794,7 +813,7 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
         if (c->n_tiles > 0) {
             if (!c->fast_tma) return c->fail(SVO_ERR_CUDA, "FAST tensor maps are not available (cuTensorMapEncodeTiled failed)");
             FastParams P{};
-            int PH = 0, TH = 0;
+            int PH = 0, TH = 0, ccell = 0;
             for (const FastTile& ft : c->tiles) {
                 const LevelGeom& G = g.lvl[ft.level];
                 const int xa = (ft.x0 - 4) & ~15;
@@ -802,6 +821,7 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
                     return c->fail(SVO_ERR_INVALID, "FAST tile outside the supported geometry (<= 250 x 64 px, <= 8 cells of <= 64 px)");
                 PH = std::max(PH, G.hCell + 6);
                 TH = std::max(TH, ft.y1 - ft.y0);
+                ccell = std::max(ccell, G.wCell * (ft.y1 - ft.y0));
             }
             for (int l = 0; l < g.nlevels; ++l) {
                 const LevelGeom& G = g.lvl[l];
@@ -816,7 +836,9 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
             P.q_off = P.ctl_off + 32 * (int)sizeof(int);
             P.zero16 = (P.q_off - P.sc_off) / 16;
             P.tail_off = P.q_off + FW * QCAP4 * 2;
-            const size_t smem = (size_t)P.tail_off + FT * 2;
+            P.cl_off = P.tail_off + FT * 2;
+            P.ccap = (int)svo_align(std::max(64, ccell / 2), 8);  // corners (score >= minTh) of one cell; overflow -> SVO_ERR_CAPACITY
+            const size_t smem = (size_t)P.cl_off + (size_t)MC4 * P.ccap * 2;
             const bool pow2 = g.minTh + 1 <= 128 && ((g.minTh + 1) & g.minTh) == 0;
             auto kern = pow2 ? k_fast_cells<true> : k_fast_cells<false>;
             SVO_CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -187,13 +187,11 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
             const uint32_t sel1 = (uint32_t)m0.y, sel2 = sel1 >> 8, sel3 = sel1 >> 16;
             const uint32_t al0 = (uint32_t)m0.z, al1 = (uint32_t)m0.w, al2 = (uint32_t)m1.x, al3 = (uint32_t)m1.y;
             const bool store_g = gx >= r.x0 && gx < r.x1o;  // a group is written by the tile that owns its first pixel
-            uint8_t* gdst = D.base + (size_t)slot * D.plane + gx;
-            uint8_t* sdst = dbuf + 4 + 4 * gi;
-            const uint8_t* sbase = src + woff;
+            const uint8_t* rowbase = src + woff - s_orgy * s_pitch;  // + sy * s_pitch: the 3 words of source row sy
             // horizontal pass of one source row for the 4 pixels: 3 aligned words hold all 8 taps; pixel i's byte pair is cut out
             // with one PRMT (selector from the host table) and multiplied with its (a0, a1) pair by one IDP.2A; kept as T >> 4
             auto hrow = [&](int sy, uint32_t (&Tq)[4]) {
-                const uint32_t* w = reinterpret_cast<const uint32_t*>(sbase + (sy - s_orgy) * s_pitch);
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(rowbase + sy * s_pitch);
                 const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
                 const uint32_t u0 = __funnelshift_r(w0, w1, sh0), u1 = __funnelshift_r(w1, w2, sh0);
                 Tq[0] = __dp2a_lo(al0, u0, 0u) >> 4;
@@ -204,30 +202,38 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
             // each row lane owns a contiguous run of rows, so the horizontal pass of the lower source row is reused as the
             // upper row of the next destination row (5 of 6 rows at scale 1.2)
             const int ya = r.y0 + rl * r.chunk, yb = min(ya + r.chunk, (int)r.y1n);
+            const int ystore = store_g ? min(yb, (int)r.y1o) : ya;  // rows [ya, ystore) of this group go to HBM
+            uint8_t* sp = dbuf + 4 + 4 * gi + (ya - r.y0) * r.pitch;
+            uint8_t* gp = D.base + (size_t)slot * D.plane + gx + (size_t)ya * D.pitch;
+            const int4* ymp = D.ymeta + ya;
+            int4 ym = ya < yb ? __ldg(ymp) : make_int4(0, 0, 0, 0);  // {top tap row, bottom tap row, beta0, beta1}; next row prefetched
             int cached_row = -1;
             uint32_t Tc[4] = {0, 0, 0, 0};
             for (int y = ya; y < yb; ++y) {
-                const int4 ym = __ldg(D.ymeta + y);  // {top tap row, bottom tap row, beta0, beta1}
+                const int4 cur = ym;
+                if (y + 1 < yb) ym = __ldg(++ymp);
                 uint32_t T0[4], T1[4];
-                if (ym.x == cached_row) {
+                if (cur.x == cached_row) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) T0[i] = Tc[i];
                 } else {
-                    hrow(ym.x, T0);
+                    hrow(cur.x, T0);
                 }
-                hrow(ym.y, T1);
+                hrow(cur.y, T1);
                 // v = (((b0 * T0) >> 16) + ((b1 * T1) >> 16) + 2) >> 2 for two pixels at a time: the upper halves of the two
                 // products are gathered by PRMT, both sums and the rounding constant are one 3-input add (no carry between
                 // the halves: each sum is <= 1023), and the bytes of (sum >> 2) are picked by a last PRMT
-                const uint32_t b0 = (uint32_t)ym.z, b1 = (uint32_t)ym.w;
+                const uint32_t b0 = (uint32_t)cur.z, b1 = (uint32_t)cur.w;
                 const uint32_t s01 = __byte_perm(b0 * T0[0], b0 * T0[1], 0x7632) + __byte_perm(b1 * T1[0], b1 * T1[1], 0x7632) + 0x00020002u;
                 const uint32_t s23 = __byte_perm(b0 * T0[2], b0 * T0[3], 0x7632) + __byte_perm(b1 * T1[2], b1 * T1[3], 0x7632) + 0x00020002u;
                 const uint32_t out = __byte_perm(s01 >> 2, s23 >> 2, 0x6420);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) Tc[i] = T1[i];
-                cached_row = ym.y;
-                *reinterpret_cast<uint32_t*>(sdst + (y - r.y0) * r.pitch) = out;
-                if (store_g && y < r.y1o) *reinterpret_cast<uint32_t*>(gdst + (size_t)y * D.pitch) = out;
+                cached_row = cur.y;
+                *reinterpret_cast<uint32_t*>(sp) = out;
+                sp += r.pitch;
+                if (y < ystore) *reinterpret_cast<uint32_t*>(gp) = out;
+                gp += D.pitch;
             }
         }
         __syncthreads();

@@ -77,7 +77,7 @@ struct PyrTile {
 #define SVO_PYR_BOX_H 96
 
 // One FAST tile = one cell row x a run of cells of one level (K2), or a full-width strip of rows (K9).
-struct FastTile {
+struct alignas(16) FastTile {
     short level, cell_i;
     short cell_j0, ncells;
     int x0, x1, y0, y1;  // inner pixel domain [x0,x1) x [y0,y1), level coordinates
