@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SVO_ABI_VERSION 3
+#define SVO_ABI_VERSION 4
 
 typedef enum svo_status {
     SVO_OK = 0,
@@ -170,6 +170,9 @@ typedef struct svo_frontend_out {
      * after svo_frontend_set_projection(); 3 floats per point */
     float* orb_points3d;    /* kp_cap*3 floats per frame, n_orb_matched valid */
     float* lk_points3d;     /* pt_cap*3 floats per frame, n_lk_matched valid */
+    /* the `err` output of the four calcOpticalFlowPyrLK calls (tracking.cpp:593-618 pass it; unused by the reference afterwards):
+     * 4 x pt_cap floats per frame (err1..err4), computed unless svo_frontend_set_lk_err(ctx, 0) */
+    float* lk_err;
 } svo_frontend_out;
 
 int svo_frontend_configure(svo_ctx* ctx, int w, int h, int mode, int max_frames);
@@ -180,6 +183,9 @@ int svo_frontend_set_match_error(svo_ctx* ctx, double feature_match_error);
  * on a side stream concurrently with the FAST + LK chain (they share no data; the big kernels still mostly serialise, the small
  * ones fill each other's tails: ~1 % at 1241x376).  On by default; 0 = one stream. */
 int svo_frontend_set_overlap(svo_ctx* ctx, int enable);
+/* The reference passes `err` to every calcOpticalFlowPyrLK call, so OpenCV computes it; the LK chain does the same by default
+ * (svo_frontend_out.lk_err).  0 skips that work (the reference never reads err). */
+int svo_frontend_set_lk_err(svo_ctx* ctx, int enable);
 /* Sensors::projMatr1_ / projMatr2_ (3x4, row-major doubles; sensors.cpp:8-24): enables the device-side triangulation of
  * the filtered lists.  Call after svo_frontend_configure(). */
 int svo_frontend_set_projection(svo_ctx* ctx, const double* proj_left, const double* proj_right);
@@ -191,15 +197,25 @@ int svo_frontend_upload_dev(svo_ctx* ctx, const uint8_t* left_dev, const uint8_t
 int svo_frontend_run(svo_ctx* ctx);
 /* device -> host for every non-NULL field of out, for the OLDEST run not yet delivered (runs are delivered in order; with
  * max_images >= 2 * (2 * max_frames + 1) one more run may be in flight while this one is downloaded on its own stream).
- * out == NULL retires the run without copying anything. */
+ * The run leaves the queue only when it has been delivered; SVO_ERR_CAPACITY because a caller capacity (kp_cap / pt_cap) is too
+ * small writes nothing and keeps the run queued, so the call can be repeated with larger buffers (or svo_frontend_discard).
+ * A DEVICE capacity overflow (SVO_ERR_CAPACITY, "device capacity exceeded") retires the run: its results are incomplete.
+ * out == NULL retires the run without copying anything (device-resident pipelines); such a caller MUST call
+ * svo_frontend_check() before trusting the device-side results, because nothing else reports a capacity overflow. */
 int svo_frontend_download(svo_ctx* ctx, svo_frontend_out* out);
+/* SVO_ERR_CAPACITY if any run retired with svo_frontend_download(ctx, NULL) since the last check overflowed a device capacity
+ * (one 4-byte read-back and a stream synchronisation). */
+int svo_frontend_check(svo_ctx* ctx);
+/* drop the oldest undelivered run without reading anything */
+int svo_frontend_discard(svo_ctx* ctx);
 /* upload + run + download */
 int svo_frontend_batch(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride,
                        svo_frontend_out* out);
 
 /* ---- deterministic synthetic stereo sequences (bench / tests input; host code, needs no GPU) --------------------- */
 /* Frame `frame` of sequence `seed`: textured canvas, 8-px disparity, 2-px/frame motion, canvas
- * re-seeded every 16 frames.  left/right: h rows of `stride` bytes. */
+ * re-seeded every 16 frames.  left/right: h rows of `stride` bytes.  Lives in its own host-only library, libsvo_synth.so
+ * (no CUDA in it), so that the CPU reference arm of bench.py never maps the CUDA library. */
 int svo_synth_stereo_frame(uint64_t seed, int frame, int w, int h, uint8_t* left, uint8_t* right, size_t stride);
 
 #ifdef __cplusplus

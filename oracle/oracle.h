@@ -102,6 +102,11 @@ struct OrbResult {
 // ORBextractor::operator() (ORBextractor.cpp:990-1055)
 void orb_extract(const OrbParams& p, const Image& img, OrbResult& out, bool keep_intermediates = true);
 
+// tail of operator() (octree, IC_Angle, steered BRIEF, rescale) on externally built levels / blurs / candidates (CPU baseline variant
+// with real-OpenCV image primitives, oracle/ref_pipeline.py)
+void orb_finish(const OrbParams& p, const std::vector<Image>& levels, const std::vector<Image>& blurred,
+                const std::vector<std::vector<KeyPoint>>& candidates, std::vector<KeyPoint>& keypoints, std::vector<uint8_t>& descriptors);
+
 // ---- reference restatement: Tracking front-end ----
 // Tracking::ORB_Robust_Find_MuliImage_MatchedFeatures (tracking.cpp:534-581). Returns #accepted; fills index triples.
 int orb_match_filter(const int32_t* idx1, const int32_t* dist1, const int32_t* idx2, const int32_t* dist2, int n_last_left,

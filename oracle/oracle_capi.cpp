@@ -79,6 +79,30 @@ int orc_distribute_octree(const KeyPoint* keys, int n, int minX, int maxX, int m
     return (int)r.size();
 }
 
+// tail of ORBextractor::operator() on caller-built intermediates (see orb_finish).  lv / bl: nlevels pointers to contiguous w[l] x h[l]
+// images; cand: all levels' candidates concatenated, ncand[l] each.
+int orc_orb_finish(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* const* lv, const uint8_t* const* bl,
+                   const int* w, const int* h, const KeyPoint* cand, const int* ncand, KeyPoint* kps, uint8_t* desc, int cap) {
+    std::vector<Image> levels(nlevels), blurred(nlevels);
+    std::vector<std::vector<KeyPoint>> c(nlevels);
+    size_t off = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        levels[l] = Image{lv[l], w[l], h[l], (size_t)w[l]};
+        blurred[l] = Image{bl[l], w[l], h[l], (size_t)w[l]};
+        c[l].assign(cand + off, cand + off + ncand[l]);
+        off += (size_t)ncand[l];
+    }
+    std::vector<KeyPoint> out;
+    std::vector<uint8_t> d;
+    orb_finish(OrbParams{nfeatures, scaleFactor, nlevels, iniTh, minTh}, levels, blurred, c, out, d);
+    const int n = (int)std::min<size_t>(out.size(), (size_t)cap);
+    if (n) {
+        std::memcpy(kps, out.data(), sizeof(KeyPoint) * n);
+        std::memcpy(desc, d.data(), (size_t)32 * n);
+    }
+    return (int)out.size();
+}
+
 // ---- full extractor with intermediates kept in a handle ----
 struct orc_orb_handle {
     OrbParams p;

@@ -329,6 +329,47 @@ void orb_extract(const OrbParams& p, const Image& img, OrbResult& out, bool keep
     if (!keep) { out.pyramid.clear(); out.candidates.clear(); }
 }
 
+// The tail of ORBextractor::operator() (:1006-1052) on externally produced intermediates: pyramid levels, their 7x7 blurs and the
+// cell loop's candidates (coordinates relative to minBorder).  Used by the CPU baseline variant whose image primitives are the
+// REAL OpenCV ones (cv2.resize / cv2.FAST per cell / cv2.GaussianBlur): octree, IC_Angle and the steered BRIEF run here.
+void orb_finish(const OrbParams& p, const std::vector<Image>& levels, const std::vector<Image>& blurred,
+                const std::vector<std::vector<KeyPoint>>& candidates, std::vector<KeyPoint>& keypoints, std::vector<uint8_t>& descriptors) {
+    const OrbTables T = make_tables(p);
+    const int L = p.nlevels;
+    std::vector<std::vector<KeyPoint>> level_kps(L);
+    for (int l = 0; l < L; ++l) {
+        const Image& lvl = levels[l];
+        const int minBX = kEdge - 3, minBY = minBX, maxBX = lvl.w - kEdge + 3, maxBY = lvl.h - kEdge + 3;
+        if (maxBX - minBX < 30 || maxBY - minBY < 30) continue;
+        std::vector<KeyPoint>& kps = level_kps[l];
+        kps = distribute_octree(candidates[l], minBX, maxBX, minBY, maxBY, T.features_per_level[l], nullptr);
+        const int scaledPatch = (int)(kPatchSize * T.scale[l]);
+        for (auto& kp : kps) {
+            kp.x += minBX;
+            kp.y += minBY;
+            kp.octave = l;
+            kp.size = (float)scaledPatch;
+            kp.angle = ic_angle(lvl, kp.x, kp.y, T.umax);
+        }
+    }
+    size_t total = 0;
+    for (int l = 0; l < L; ++l) total += level_kps[l].size();
+    descriptors.assign(total * 32, 0);
+    keypoints.clear();
+    keypoints.reserve(total);
+    size_t off = 0;
+    for (int l = 0; l < L; ++l) {
+        const std::vector<KeyPoint>& kps = level_kps[l];
+        for (size_t i = 0; i < kps.size(); ++i) orb_descriptor(kps[i], blurred[l], &descriptors[(off + i) * 32]);
+        off += kps.size();
+        for (const auto& kp : kps) {
+            KeyPoint o = kp;
+            if (l != 0) { o.x *= T.scale[l]; o.y *= T.scale[l]; }
+            keypoints.push_back(o);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Tracking::ORB_Robust_Find_MuliImage_MatchedFeatures, tracking.cpp:534-581 (the part after the two match() calls)
 // ---------------------------------------------------------------------------------------------------------------

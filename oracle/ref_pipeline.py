@@ -12,6 +12,8 @@ so the reference's CPU front-end is reproduced as closely as the image allows:
   * the reference is single-threaded; to give it every host core the sequence is split over one worker process per core
     (contiguous chunks overlapping by one frame, the same sharding rule as the GPU path).
 """
+import ctypes as C
+import math
 import multiprocessing as mp
 import os
 import sys
@@ -23,14 +25,96 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _G = {}
 
 
+class Cv2PrimitiveOrb:
+    """ORBextractor::operator() with the REAL OpenCV image primitives (BASELINE.md section 2, variant 2): cv2.resize per level
+    (ORBextractor.cpp:1074), cv2.FAST on every cell window with the 20 -> 7 fallback (:742-781; ROI views, no copies),
+    cv2.GaussianBlur per level (:1035); the reference's own loops around them (octree, IC_Angle, steered BRIEF) run compiled in
+    liboracle.so (orc_orb_finish).  Results equal the oracle's (tests/test_oracle_cpu.py)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        import cv2
+        sys.path.insert(0, _HERE)
+        import oracle_py as O
+        self.cv2, self.O = cv2, O
+        self.p = (nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.t = O.orb_tables(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.fast_ini = cv2.FastFeatureDetector_create(ini_th, True)
+        self.fast_min = cv2.FastFeatureDetector_create(min_th, True)
+
+    def extract(self, img):
+        cv2, O = self.cv2, self.O
+        nfeatures, scale_factor, nlevels, ini_th, min_th = self.p
+        h0, w0 = img.shape
+        levels, blurred, cands = [np.ascontiguousarray(img)], [], []
+        for l in range(1, nlevels):
+            s = self.t[1][l]  # inverse scale factors (orb_tables: scale, inv_scale, features per level, umax)
+            w, h = int(np.rint(np.float32(w0) * s)), int(np.rint(np.float32(h0) * s))
+            levels.append(cv2.resize(levels[l - 1], (w, h), interpolation=cv2.INTER_LINEAR))
+        EDGE = 19
+        for l in range(nlevels):
+            lvl = levels[l]
+            h, w = lvl.shape
+            minBX = minBY = EDGE - 3
+            maxBX, maxBY = w - EDGE + 3, h - EDGE + 3
+            pts = []
+            if maxBX - minBX >= 30 and maxBY - minBY >= 30:
+                width, height = float(maxBX - minBX), float(maxBY - minBY)
+                nCols, nRows = int(width / 30), int(height / 30)
+                wCell, hCell = int(math.ceil(width / nCols)), int(math.ceil(height / nRows))
+                for i in range(nRows):
+                    iniY = minBY + i * hCell
+                    maxY = iniY + hCell + 6
+                    if iniY >= maxBY - 3:
+                        continue
+                    maxY = min(maxY, maxBY)
+                    for j in range(nCols):
+                        iniX = minBX + j * wCell
+                        maxX = iniX + wCell + 6
+                        if iniX >= maxBX - 6:
+                            continue
+                        maxX = min(maxX, maxBX)
+                        roi = lvl[iniY:maxY, iniX:maxX]
+                        kps = self.fast_ini.detect(roi)
+                        if not kps:
+                            kps = self.fast_min.detect(roi)
+                        for k in kps:
+                            pts.append((k.pt[0] + j * wCell, k.pt[1] + i * hCell, k.response))
+            c = np.zeros(len(pts), O.KP_DTYPE)
+            if pts:
+                a = np.asarray(pts, np.float32)
+                c["x"], c["y"], c["response"] = a[:, 0], a[:, 1], a[:, 2]
+                c["size"], c["angle"], c["class_id"] = 7.0, -1.0, -1
+            cands.append(c)
+            blurred.append(cv2.GaussianBlur(lvl, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101))
+        cap = nfeatures + 64 * nlevels + 64
+        kps = np.zeros(cap, O.KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        lv_p = (C.c_void_p * nlevels)(*[a.ctypes.data for a in levels])
+        bl_p = (C.c_void_p * nlevels)(*[a.ctypes.data for a in blurred])
+        ws = (C.c_int * nlevels)(*[a.shape[1] for a in levels])
+        hs = (C.c_int * nlevels)(*[a.shape[0] for a in levels])
+        nc = (C.c_int * nlevels)(*[len(c) for c in cands])
+        allc = np.ascontiguousarray(np.concatenate(cands)) if sum(len(c) for c in cands) else np.zeros(1, O.KP_DTYPE)
+        n = O.lib().orc_orb_finish(C.c_int(nfeatures), C.c_float(scale_factor), C.c_int(nlevels), C.c_int(ini_th), C.c_int(min_th), lv_p, bl_p,
+                                   ws, hs, allc.ctypes.data_as(C.c_void_p), nc, kps.ctypes.data_as(C.c_void_p),
+                                   desc.ctypes.data_as(C.c_void_p), C.c_int(cap))
+        assert n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+
 def _worker(args):
-    u0, u1, mode, nfeat = args
+    u0, u1, mode, nfeat, variant, cv_threads = args
     import cv2
-    cv2.setNumThreads(1)
+    cv2.setNumThreads(cv_threads)
     sys.path.insert(0, _HERE)
     import oracle_py as O
     left, right = _G["left"], _G["right"]
-    orb = O.RefOrb(nfeat, 1.2, 8, 20, 7, monotone=False) if O.ref_lib() is not None else O.OrbOracle(nfeat, 1.2, 8, 20, 7)
+    if variant == "cv2prim":
+        orb = Cv2PrimitiveOrb(nfeat, 1.2, 8, 20, 7)
+    elif variant == "port":
+        orb = O.OrbOracle(nfeat, 1.2, 8, 20, 7)
+    else:
+        orb = O.RefOrb(nfeat, 1.2, 8, 20, 7, monotone=False) if O.ref_lib() is not None else O.OrbOracle(nfeat, 1.2, 8, 20, 7)
     bf = cv2.BFMatcher(cv2.NORM_HAMMING)
     fast = cv2.FastFeatureDetector_create(20, True)
     lk = dict(winSize=(21, 21), maxLevel=3, criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01), flags=0,
@@ -79,7 +163,9 @@ def orb_kind():
 class ReferencePool:
     """One worker process per host core over a fixed synthetic sequence; run() processes all units once."""
 
-    def __init__(self, left, right, mode=3, nfeatures=1000, workers=None):
+    def __init__(self, left, right, mode=3, nfeatures=1000, workers=None, variant="ref", cv_threads=1):
+        """variant: 'ref' (ORBextractor from the reference's compiled source, falls back to the port), 'port' (C++ oracle port),
+        'cv2prim' (real-OpenCV image primitives, Cv2PrimitiveOrb); cv_threads: OpenCV-internal threads per worker."""
         self.workers = workers or len(os.sched_getaffinity(0))
         _G["left"], _G["right"] = left, right
         self.units = left.shape[0] - 1
@@ -90,7 +176,7 @@ class ReferencePool:
         for k in range(self.workers):
             u0, u1 = self.units * k // self.workers, self.units * (k + 1) // self.workers
             if u1 > u0:
-                self.chunks.append((u0, u1, mode, nfeatures))
+                self.chunks.append((u0, u1, mode, nfeatures, variant, cv_threads))
 
     def run(self):
         t0 = time.perf_counter()

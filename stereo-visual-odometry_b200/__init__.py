@@ -15,6 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
+SYNTH_LIB_PATH = os.path.join(_HERE, "libsvo_synth.so")  # host-only generator of the synthetic sequences (no CUDA)
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                      ("octave", "<i4"), ("class_id", "<i4")])
@@ -32,9 +33,11 @@ ABI_SYMBOLS = [
     "svo_ctx_launch_count", "svo_ctx_enable_stage_timing", "svo_ctx_set_timing_slot", "svo_ctx_stage_ms", "svo_orb_configure", "svo_orb_tables",
     "svo_orb_capacity", "svo_orb_level_size", "svo_orb_extract", "svo_orb_extract_batch", "svo_orb_read_level",
     "svo_orb_read_candidates", "svo_fast_detect", "svo_match_hamming", "svo_lk_track", "svo_frontend_configure",
-    "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_overlap", "svo_frontend_set_projection", "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_batch",
-    "svo_synth_stereo_frame",
+    "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_overlap", "svo_frontend_set_lk_err", "svo_frontend_set_projection",
+    "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_check",
+    "svo_frontend_discard", "svo_frontend_batch",
 ]
+SYNTH_SYMBOLS = ["svo_synth_stereo_frame"]  # exported by libsvo_synth.so
 
 
 class SvoError(RuntimeError):
@@ -48,10 +51,23 @@ class FrontendOut(C.Structure):
         "kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
         "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status",
         "orb_t2_left", "orb_t1_left", "orb_t1_right", "n_orb_matched", "lkf_t1_left", "lkf_t1_right", "lkf_t2_right", "lkf_t2_left",
-        "n_lk_matched", "orb_points3d", "lk_points3d")]
+        "n_lk_matched", "orb_points3d", "lk_points3d", "lk_err")]
 
 
 _lib = None
+_synth = None
+
+
+def synth_lib():
+    """Load libsvo_synth.so: the host-only synthetic-sequence generator (the CPU reference arm uses it without the CUDA library)."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise ImportError(f"{SYNTH_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(SYNTH_LIB_PATH)
+        L.svo_synth_stereo_frame.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        _synth = L
+    return _synth
 
 
 def lib():
@@ -72,7 +88,6 @@ def lib():
         L.svo_ctx_stage_ms.restype = C.c_float
         L.svo_ctx_stage_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.svo_orb_configure.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
-        L.svo_synth_stereo_frame.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.svo_lk_track.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         _lib = L
@@ -87,7 +102,7 @@ def synth_stereo_frame(seed, frame, w, h):
     """Frame `frame` of the deterministic synthetic stereo sequence `seed`. Host code, no GPU needed."""
     left = np.empty((h, w), np.uint8)
     right = np.empty((h, w), np.uint8)
-    rc = lib().svo_synth_stereo_frame(seed, frame, w, h, _p(left), _p(right), w)
+    rc = synth_lib().svo_synth_stereo_frame(seed, frame, w, h, _p(left), _p(right), w)
     if rc != 0:
         raise SvoError(rc, "svo_synth_stereo_frame")
     return left, right
@@ -97,7 +112,7 @@ def synth_sequence(seed, first, count, w, h):
     left = np.empty((count, h, w), np.uint8)
     right = np.empty((count, h, w), np.uint8)
     for i in range(count):
-        rc = lib().svo_synth_stereo_frame(seed, first + i, w, h, _p(left[i]), _p(right[i]), w)
+        rc = synth_lib().svo_synth_stereo_frame(seed, first + i, w, h, _p(left[i]), _p(right[i]), w)
         if rc != 0:
             raise SvoError(rc, "svo_synth_stereo_frame")
     return left, right
@@ -250,6 +265,16 @@ class Context:
     def frontend_set_overlap(self, enable):
         self._check(self._L.svo_frontend_set_overlap(self._h, int(bool(enable))))
 
+    def frontend_set_lk_err(self, enable):
+        self._check(self._L.svo_frontend_set_lk_err(self._h, int(bool(enable))))
+
+    def frontend_check(self):
+        """Raises SvoError(SVO_ERR_CAPACITY) if a run retired with frontend_download(None) overflowed a device capacity."""
+        self._check(self._L.svo_frontend_check(self._h))
+
+    def frontend_discard(self):
+        self._check(self._L.svo_frontend_discard(self._h))
+
     def frontend_set_projection(self, p1, p2):
         p1 = np.ascontiguousarray(p1, np.float64).reshape(12)
         p2 = np.ascontiguousarray(p2, np.float64).reshape(12)
@@ -301,7 +326,7 @@ class FrontendBuffers:
     ALL = ("kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
            "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status",
            "orb_t2_left", "orb_t1_left", "orb_t1_right", "n_orb_matched", "lkf_t1_left", "lkf_t1_right", "lkf_t2_right", "lkf_t2_left",
-           "n_lk_matched", "orb_points3d", "lk_points3d")
+           "n_lk_matched", "orb_points3d", "lk_points3d", "lk_err")
 
     def __init__(self, n_frames, kp_cap, pt_cap, fields=None, alloc=None):
         fields = self.ALL if fields is None else fields
@@ -317,7 +342,7 @@ class FrontendBuffers:
                       orb_t2_left=((F, K, 2), np.float32), orb_t1_left=((F, K, 2), np.float32), orb_t1_right=((F, K, 2), np.float32),
                       n_orb_matched=((F,), np.int32), lkf_t1_left=((F, P, 2), np.float32), lkf_t1_right=((F, P, 2), np.float32),
                       lkf_t2_right=((F, P, 2), np.float32), lkf_t2_left=((F, P, 2), np.float32), n_lk_matched=((F,), np.int32),
-                      orb_points3d=((F, K, 3), np.float32), lk_points3d=((F, P, 3), np.float32))
+                      orb_points3d=((F, K, 3), np.float32), lk_points3d=((F, P, 3), np.float32), lk_err=((F, 4, P), np.float32))
         self.struct = FrontendOut()
         self.struct.kp_cap = kp_cap
         self.struct.pt_cap = pt_cap
@@ -347,7 +372,7 @@ class FrontendBuffers:
                             ("fast_kps", mf * 28), ("lk_p1", ms * 8), ("lk_p2", ms * 8), ("lk_p3", ms * 8), ("lk_p0r", ms * 8),
                             ("lk_status", ms * 4), ("orb_t2_left", mo * 8), ("orb_t1_left", mo * 8), ("orb_t1_right", mo * 8),
                             ("lkf_t1_left", mk * 8), ("lkf_t1_right", mk * 8), ("lkf_t2_right", mk * 8), ("lkf_t2_left", mk * 8),
-                            ("orb_points3d", mo * 12), ("lk_points3d", mk * 12)):
+                            ("orb_points3d", mo * 12), ("lk_points3d", mk * 12), ("lk_err", ms * 16)):
             if getattr(self, name) is not None:
                 total += width * F
         return total + 3 * 4 * 2 * (F + 1)  # the count / flag arrays

@@ -434,7 +434,9 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                     pa = pb;
                 }
             }
-            const long long sb1 = warp_sum64(b1), sb2 = warp_sum64(b2);
+            // |diff| <= 255 and |Ix|, |Iy| <= 4080 (Scharr of 8-bit pixels): the window sums stay below 441 * 255 * 4080 < 2^31,
+            // so one 32-bit hardware reduction per sum is exact
+            const int sb1 = __reduce_add_sync(0xFFFFFFFFu, b1), sb2 = __reduce_add_sync(0xFFFFFFFFu, b2);
             const float b1f = __fmul_rn((float)sb1, FLT_SCALE), b2f = __fmul_rn((float)sb2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2f), __fmul_rn(A22, b1f)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1f), __fmul_rn(A11, b2f)), D);
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
         dst[2 * pt] = nx;
         dst[2 * pt + 1] = ny;
         st_out[pt] = (uint8_t)status;
-        if (P.want_err && lk_err) lk_err[pt] = status ? err : 0.f;
+        if (P.want_err && lk_err) lk_err[((size_t)cur * 4 + call.status_row) * P.pt_cap + pt] = status ? err : 0.f;
     }
     px = nx;  // source point of the next call of the chain
     py = ny;
@@ -534,7 +536,7 @@ static void fill_params(svo_ctx* c, LkParams& P, int max_level, int max_iter, do
 }
 
 int launch_lk_chain(svo_ctx* c, int first, int ring, int n_frames, int skip_first, const LkCall* calls, int ncalls, int max_iter, double eps,
-                    double min_eig) {
+                    double min_eig, int want_err) {
     StageTimer t(c, 8);
     LkParams P{};
     fill_params(c, P, SVO_LK_LEVELS - 1, max_iter, eps, min_eig);
@@ -547,9 +549,9 @@ int launch_lk_chain(svo_ctx* c, int first, int ring, int n_frames, int skip_firs
         if (k && calls[k].src_list != calls[k - 1].dst_list) return c->fail(SVO_ERR_INVALID, "launch_lk_chain: calls do not form a chain");
     }
     P.standalone = 0;
-    P.want_err = 0;
+    P.want_err = want_err;
     dim3 grid((c->pt_cap + LW - 1) / LW, n_frames);
-    k_lk_track<<<grid, LW * 32, 0, c->stream>>>(P, c->d_fast_kps, c->d_nfast, c->d_lk_pts, c->d_lk_status, nullptr);
+    k_lk_track<<<grid, LW * 32, 0, c->stream>>>(P, c->d_fast_kps, c->d_nfast, c->d_lk_pts, c->d_lk_status, want_err ? c->d_lk_err : nullptr);
     ++c->launches;
     SVO_CUDA_TRY(c, cudaGetLastError());
     return SVO_OK;

@@ -168,13 +168,12 @@ struct svo_ctx {
     uint8_t* d_desc = nullptr;
     int* d_nkp = nullptr;
     int* d_flags = nullptr;  // per slot
+    int* d_flag_accum = nullptr;  // flags of runs retired without a download (svo_frontend_check)
     int8_t* d_pattern = nullptr;
 
     // generic scratch for the standalone calls (match / fast / lk)
     void* d_scratch = nullptr;
     size_t scratch_bytes = 0;
-    void* h_pinned = nullptr;
-    size_t pinned_bytes = 0;
 
     // ---- LK / full-frame FAST
     LkLevelGeom lk[SVO_LK_LEVELS];  // [0]: the ORB level-0 plane (unpadded); [1..3]: padded planes, base = interior origin
@@ -221,6 +220,7 @@ struct svo_ctx {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool fe_overlap = true;
+    bool fe_lk_err = true;  // the reference passes `err` to calcOpticalFlowPyrLK (tracking.cpp:593): the chain computes it too
     cudaEvent_t ev_done[2] = {};
     bool fe_has_last = false;
     bool fe_configured = false;
@@ -285,12 +285,12 @@ struct LkCall {
     int src_list, dst_list, status_row;
 };
 int launch_lk_chain(svo_ctx* c, int first, int ring, int n_frames, int skip_first, const LkCall* calls, int ncalls, int max_iter, double eps,
-                    double min_eig);
+                    double min_eig, int want_err);
 
 int svo_orb_run(svo_ctx* c, const SlotMap& map, int n_img);
 int svo_check_flags(svo_ctx* c, const SlotMap& map, int n_img);
 int svo_ensure_scratch(svo_ctx* c, size_t bytes);
-int svo_ensure_pinned(svo_ctx* c, size_t bytes);
+int svo_standalone_guard(svo_ctx* c);
 
 // host helpers
 int svo_layout(svo_ctx* c, int w, int h);

@@ -72,7 +72,7 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
     free_layout(c);
     if (c->d_pattern) cudaFree(c->d_pattern);
     if (c->d_scratch) cudaFree(c->d_scratch);
-    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->d_flag_accum) cudaFree(c->d_flag_accum);
     if (c->d2h_stream) {
         cudaStreamSynchronize(c->d2h_stream);
         cudaStreamDestroy(c->d2h_stream);
@@ -620,30 +620,6 @@ int svo_layout(svo_ctx* c, int w, int h) {
     return SVO_OK;
 }
 
-int svo_ensure_pinned(svo_ctx* c, size_t bytes) {
-    if (c->pinned_bytes >= bytes) return SVO_OK;
-    if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    if (c->d2h_stream) {
-        cudaStreamSynchronize(c->d2h_stream);
-        cudaStreamDestroy(c->d2h_stream);
-        for (int i = 0; i < 2; ++i) cudaEventDestroy(c->ev_done[i]);
-    }
-    if (c->copy_stream) {
-        cudaStreamSynchronize(c->copy_stream);
-        for (int i = 0; i < 2; ++i) {
-            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
-            cudaEventDestroy(c->ev_copy[i]);
-            cudaEventDestroy(c->ev_repitch[i]);
-        }
-        cudaStreamDestroy(c->copy_stream);
-    }
-    c->h_pinned = nullptr;
-    c->pinned_bytes = 0;
-    SVO_CUDA_TRY(c, cudaMallocHost(&c->h_pinned, bytes));
-    c->pinned_bytes = bytes;
-    return SVO_OK;
-}
-
 int svo_check_flags(svo_ctx* c, const SlotMap& map, int n_img) {
     // reads the per-slot error flags (after the stream has been synchronised by the caller's D2H copies)
     std::vector<int> flags(c->max_images);
@@ -680,8 +656,9 @@ extern "C" int svo_orb_extract_batch(svo_ctx* c, const uint8_t* const* imgs, int
     if (n_imgs == 0 || w == 0 || h == 0 || !imgs) return SVO_OK;  // empty image: silent return (ORBextractor.cpp:993-994)
     if (w < 0 || h < 0 || stride < (size_t)w || !kps || !desc) return c->fail(SVO_ERR_INVALID, "svo_orb_extract_batch: bad geometry / null outputs");
     cudaSetDevice(c->device);
-    int rc = svo_layout(c, w, h);
+    int rc = svo_standalone_guard(c);
     if (rc != SVO_OK) return rc;
+    if ((rc = svo_layout(c, w, h)) != SVO_OK) return rc;
     if (cap_per_img < c->kp_cap) return c->fail(SVO_ERR_CAPACITY, "cap_per_img < svo_orb_capacity()");
     const LevelGeom& L0 = c->geom.lvl[0];
     for (int i = 0; i < n_imgs; ++i) {

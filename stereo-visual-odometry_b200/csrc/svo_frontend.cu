@@ -18,6 +18,18 @@ static int ensure_config(svo_ctx* c) {
     return svo_orb_configure_impl(c, 0, 1.2f, 1, 20, 7, false);  // detector-only layout: level 0 only
 }
 
+// The standalone entry points (svo_orb_extract*, svo_fast_detect, svo_lk_track) use image slots 0 / 1, which are also ring slots of
+// the throughput mode: on a frontend-configured context they refuse to run while results are still queued, and they drop the
+// carried frame (the next svo_frontend_run starts like after svo_frontend_reset).
+int svo_standalone_guard(svo_ctx* c) {
+    if (!c->fe_configured) return SVO_OK;
+    if (c->fe_nq > 0) return c->fail(SVO_ERR_INVALID, "standalone call on a frontend context with undelivered runs: svo_frontend_download() them first");
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+    c->fe_has_last = false;
+    c->fe_pending = 0;
+    return SVO_OK;
+}
+
 // LK pyramid levels 1..3 and the full-frame FAST / LK point buffers for the current image size
 static int layout_aux(svo_ctx* c, int pt_cap) {
     if (c->aux_ready && c->pt_cap >= pt_cap) return SVO_OK;
@@ -30,6 +42,8 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
         *p = nullptr;
     }
     c->aux_ready = false;
+    // the throughput-mode buffers (d_lkf_pts, d_lkf_xyz, ...) were sized with the old pt_cap: svo_frontend_configure() must run again
+    c->fe_configured = false;
     const int S = c->max_images, w = c->cur_w, h = c->cur_h;
     if (w > SVO_MAX_DIM || h > SVO_MAX_DIM) return c->fail(SVO_ERR_INVALID, "full-frame FAST / LK support images up to 4096 x 4096");
     const LevelGeom& L0 = c->geom.lvl[0];
@@ -91,7 +105,7 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nfast, 0, sizeof(int) * S, c->stream));
     SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_pts, sizeof(float) * 2 * 5 * (size_t)c->pt_cap * S));
     SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_status, (size_t)4 * c->pt_cap * S));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_err, sizeof(float) * (size_t)c->pt_cap));
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_err, sizeof(float) * 4 * (size_t)c->pt_cap * S));
     c->aux_ready = true;
     return SVO_OK;
 }
@@ -106,6 +120,7 @@ extern "C" int svo_fast_detect(svo_ctx* c, const uint8_t* img, int w, int h, siz
     if (w < 0 || h < 0 || stride < (size_t)w || cap < 0 || (cap > 0 && !kps)) return c->fail(SVO_ERR_INVALID, "svo_fast_detect: bad arguments");
     cudaSetDevice(c->device);
     int rc;
+    if ((rc = svo_standalone_guard(c)) != SVO_OK) return rc;
     if ((rc = ensure_config(c)) != SVO_OK) return rc;
     if ((rc = svo_layout(c, w, h)) != SVO_OK) return rc;
     if ((rc = layout_aux(c, std::max(cap, w * h / 64))) != SVO_OK) return rc;
@@ -134,6 +149,7 @@ extern "C" int svo_lk_track(svo_ctx* c, const uint8_t* prev, const uint8_t* next
     if (n == 0) return SVO_OK;
     cudaSetDevice(c->device);
     int rc;
+    if ((rc = svo_standalone_guard(c)) != SVO_OK) return rc;
     if ((rc = ensure_config(c)) != SVO_OK) return rc;
     if ((rc = svo_layout(c, w, h)) != SVO_OK) return rc;
     if ((rc = layout_aux(c, std::max(n, w * h / 64))) != SVO_OK) return rc;
@@ -211,6 +227,10 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
         SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nlkf, 0, sizeof(int) * c->fe_ring, c->stream));
         SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkf_xyz, sizeof(float) * 3 * (size_t)c->pt_cap * c->fe_ring));
     }
+    if (!c->d_flag_accum) {
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_flag_accum, sizeof(int)));
+        SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_flag_accum, 0, sizeof(int), c->stream));
+    }
     c->fe_mode = mode;
     c->fe_max_frames = max_frames;
     if (!c->d2h_stream) {
@@ -228,6 +248,12 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
 extern "C" int svo_frontend_set_match_error(svo_ctx* c, double fme) {
     if (!c) return SVO_ERR_INVALID;
     c->fe_match_error = fme;
+    return SVO_OK;
+}
+
+extern "C" int svo_frontend_set_lk_err(svo_ctx* c, int enable) {
+    if (!c) return SVO_ERR_INVALID;
+    c->fe_lk_err = enable != 0;
     return SVO_OK;
 }
 
@@ -311,6 +337,13 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
     const int ring = c->fe_ring, first = (c->fe_head + 1) % ring, n = c->fe_pending, skip_first = c->fe_has_last ? 0 : 1;
     int rc;
     const SlotMap both{2, ring, first, ring}, leftonly{1, 0, first, ring};
+    {  // the capacity flags are per run: clear those of the slots this run writes (left and right side, <= 2 runs of slots each)
+        const int run1 = std::min(n, ring - first), run2 = n - run1;
+        for (int side = 0; side < 2; ++side) {
+            SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_flags + side * ring + first, 0, sizeof(int) * run1, c->stream));
+            if (run2 > 0) SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_flags + side * ring, 0, sizeof(int) * run2, c->stream));
+        }
+    }
     if (c->pend_staged) SVO_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_copy[c->stage_idx], 0));
     if ((rc = launch_repitch(c, c->pend_left, c->pend_right, c->pend_stride, first, ring, n)) != SVO_OK) return rc;
     if (c->pend_staged) {
@@ -349,7 +382,7 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
         if ((rc = launch_lk_pyramid(c, both, 2 * n)) != SVO_OK) return rc;
         // the 4-call chain (tracking.cpp:593-618): L(t-1)->R(t-1), R(t-1)->R(t), R(t)->L(t), L(t)->L(t-1)
         const LkCall calls[4] = {{0, 1, 1, 1, 0, 1, 0}, {1, 1, 1, 0, 1, 2, 1}, {1, 0, 0, 0, 2, 3, 2}, {0, 0, 0, 1, 3, 4, 3}};
-        if ((rc = launch_lk_chain(c, first, ring, n, skip_first, calls, 4, 30, 0.01, 0.001)) != SVO_OK) return rc;
+        if ((rc = launch_lk_chain(c, first, ring, n, skip_first, calls, 4, 30, 0.01, 0.001, c->fe_lk_err ? 1 : 0)) != SVO_OK) return rc;
         if ((rc = launch_lk_filter(c, first, ring, n, skip_first)) != SVO_OK) return rc;
     }
     if (overlap) SVO_CUDA_TRY(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));  // join before anything reads the ORB results
@@ -389,15 +422,63 @@ struct RingCopy {
 };
 }  // namespace
 
+// ORs the capacity flags of a retired run into the context's accumulator (runs retired without a download)
+__global__ void k_accum_flags(const int* __restrict__ flags, int first, int n, int ring, int* __restrict__ accum) {
+    int v = 0;
+    for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
+        const int f = i >> 1, side = i & 1;
+        int fs = first + f;
+        if (fs >= ring) fs -= ring;
+        v |= flags[side * ring + fs];
+    }
+    if (v) atomicOr(accum, v);
+}
+
+extern "C" int svo_frontend_check(svo_ctx* c) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!c->fe_configured || !c->d_flag_accum) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure() first");
+    cudaSetDevice(c->device);
+    int v = 0;
+    SVO_CUDA_TRY(c, cudaMemcpyAsync(&v, c->d_flag_accum, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (v) {
+        SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_flag_accum, 0, sizeof(int), c->stream));
+        char msg[160];
+        snprintf(msg, sizeof msg, "device capacity exceeded in a run retired without download (flags 0x%x: 1 tile, 2 candidates, 4 octree nodes, 8 keypoints, 16 fast)", v);
+        return c->fail(SVO_ERR_CAPACITY, msg);
+    }
+    return SVO_OK;
+}
+
+extern "C" int svo_frontend_discard(svo_ctx* c) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!c->fe_configured || c->fe_nq < 1) return c->fail(SVO_ERR_INVALID, "svo_frontend_discard: nothing to discard");
+    c->fe_qhead = (c->fe_qhead + 1) % 2;
+    --c->fe_nq;
+    return SVO_OK;
+}
+
 extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
     if (!c) return SVO_ERR_INVALID;
     if (!c->fe_configured || c->fe_nq < 1) return c->fail(SVO_ERR_INVALID, "svo_frontend_download: nothing to download");
     cudaSetDevice(c->device);
+    // the run is only PEEKED here: it leaves the queue when it has been delivered (or when the device reported an overflow, in
+    // which case its results are truncated and useless); a caller buffer that is too small leaves it queued for a retry
     const svo_ctx::DoneRun done = c->fe_q[c->fe_qhead];
-    c->fe_qhead = (c->fe_qhead + 1) % 2;
-    --c->fe_nq;
-    if (!out) return SVO_OK;  // results stay on the device (device-resident pipelines): just retire the run
+    auto pop = [&]() {
+        c->fe_qhead = (c->fe_qhead + 1) % 2;
+        --c->fe_nq;
+    };
     const int ring = c->fe_ring, first = done.first, n = done.n, skip = done.skip;
+    if (!out) {
+        // results stay on the device (device-resident pipelines): retire the run; its capacity flags are OR-ed into the
+        // context's accumulator on the compute stream (which is ordered behind the run), read by svo_frontend_check()
+        k_accum_flags<<<1, 128, 0, c->stream>>>(c->d_flags, first, n, ring, c->d_flag_accum);
+        ++c->launches;
+        SVO_CUDA_TRY(c, cudaGetLastError());
+        pop();
+        return SVO_OK;
+    }
     // all copies go on the download stream, behind the event that marks the end of that run's kernels
     cudaStream_t const compute_stream = c->stream;
     SVO_CUDA_TRY(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_done[done.ev], 0));
@@ -419,17 +500,27 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
     SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     for (int f = 0; f < n; ++f) {
         const int fs = (first + f) % ring;
-        if (flags[fs] | flags[ring + fs]) {
-            cudaMemsetAsync(c->d_flags, 0, sizeof(int) * S, c->stream);
+        if (flags[fs] | flags[ring + fs]) {  // (the flags are cleared by the next run that writes these slots)
+            pop();
             char msg[128];
             snprintf(msg, sizeof msg, "device capacity exceeded on frame %d (flags 0x%x / 0x%x)", f, flags[fs], flags[ring + fs]);
             return c->fail(SVO_ERR_CAPACITY, msg);
         }
     }
+    // ---- validate the caller's capacities BEFORE anything is written or retired
+    if ((c->fe_mode & SVO_MODE_ORB) && out->kp_cap < c->kp_cap) return c->fail(SVO_ERR_CAPACITY, "svo_frontend_out.kp_cap < svo_orb_capacity() (run kept queued)");
+    if (c->fe_mode & SVO_MODE_LK) {
+        if (out->pt_cap < 1) return c->fail(SVO_ERR_CAPACITY, "svo_frontend_out.pt_cap < 1 (run kept queued)");
+        for (int f = 0; f < n; ++f) {
+            const int fs = (first + f) % ring, ps = (first + f - 1 + ring) % ring;
+            const int ns = (f == 0 && skip) ? 0 : nfast[ps];
+            if (nfast[fs] > out->pt_cap || ns > out->pt_cap)
+                return c->fail(SVO_ERR_CAPACITY, "more FAST corners / LK seeds than svo_frontend_out.pt_cap (run kept queued)");
+        }
+    }
     RingCopy rcpy{c, first, n, ring};
     if (c->fe_mode & SVO_MODE_ORB) {
         const int K = c->kp_cap;
-        if (out->kp_cap < K) return c->fail(SVO_ERR_CAPACITY, "svo_frontend_out.kp_cap < svo_orb_capacity()");
         int maxL = 0, maxR = 0, maxQ = 0;
         for (int f = 0; f < n; ++f) {
             const int fs = (first + f) % ring, ps = (first + f - 1 + ring) % ring;
@@ -462,7 +553,6 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
     }
     if (c->fe_mode & SVO_MODE_LK) {
         const int P = c->pt_cap;
-        if (out->pt_cap < 1) return c->fail(SVO_ERR_CAPACITY, "svo_frontend_out.pt_cap < 1");
         int maxF = 0, maxS = 0;
         for (int f = 0; f < n; ++f) {
             const int fs = (first + f) % ring, ps = (first + f - 1 + ring) % ring;
@@ -472,7 +562,6 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
             if (out->n_fast) out->n_fast[f] = nfast[fs];
             if (out->n_seed) out->n_seed[f] = ns;
         }
-        if (maxF > out->pt_cap || maxS > out->pt_cap) return c->fail(SVO_ERR_CAPACITY, "more FAST corners / LK seeds than svo_frontend_out.pt_cap");
         const size_t hp = (size_t)out->pt_cap;
         if (out->fast_kps && (rc = rcpy.copy(out->fast_kps, hp * 28, c->d_fast_kps, (size_t)P * 28, (size_t)maxF * 28))) return rc;
         float* ph[4] = {out->lk_p1, out->lk_p2, out->lk_p3, out->lk_p0r};
@@ -491,8 +580,12 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
         if (out->lk_status)
             for (int r = 0; r < 4; ++r)
                 if ((rc = rcpy.copy(out->lk_status + (size_t)r * hp, 4 * hp, c->d_lk_status + (size_t)r * P, (size_t)4 * P, (size_t)maxS))) return rc;
+        if (out->lk_err && c->fe_lk_err)
+            for (int r = 0; r < 4; ++r)
+                if ((rc = rcpy.copy(out->lk_err + (size_t)r * hp, 16 * hp, c->d_lk_err + (size_t)r * P, (size_t)16 * P, (size_t)maxS * 4))) return rc;
     }
     SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    pop();
     return SVO_OK;
 }
 

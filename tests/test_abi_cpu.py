@@ -20,10 +20,12 @@ def test_exports_every_declared_symbol(pkg):
     L = pkg.lib()
     declared = _declared_symbols()
     assert len(declared) >= 25
-    missing = [s for s in declared if not hasattr(L, s)]
+    S = pkg.synth_lib()  # the host-only generator lives in its own library (no CUDA behind the CPU reference arm)
+    missing = [s for s in declared if not hasattr(S if s in pkg.SYNTH_SYMBOLS else L, s)]
     assert not missing, missing
-    assert sorted(pkg.ABI_SYMBOLS) == declared
-    assert L.svo_abi_version() == 3
+    assert sorted(pkg.ABI_SYMBOLS + pkg.SYNTH_SYMBOLS) == declared
+    assert not any(hasattr(L, s) for s in pkg.SYNTH_SYMBOLS), "the generator must not be linked into the CUDA library"
+    assert L.svo_abi_version() == 4
 
 
 def test_keypoint_layout(pkg):
@@ -59,4 +61,4 @@ def test_synth_is_deterministic_and_stereo(pkg):
     assert np.abs(l0[:, 2:].astype(int) - l1[:, :-2].astype(int)).max() <= 6
     l16, _ = pkg.synth_stereo_frame(1000, 16, 1241, 376)  # canvas re-seeded every 16 frames
     assert np.abs(l0.astype(int) - l16.astype(int)).mean() > 10
-    assert pkg.lib().svo_synth_stereo_frame(1, 0, 0, 10, None, None, 0) == pkg.SVO_ERR_INVALID
+    assert pkg.synth_lib().svo_synth_stereo_frame(1, 0, 0, 10, None, None, 0) == pkg.SVO_ERR_INVALID

@@ -15,7 +15,7 @@ def test_cpp_dropin(pkg, orc, tmp_path):
         subprocess.check_call(["make", "-C", os.path.join(pkgdir, "host"), "-s"])
     exe = str(tmp_path / "test_dropin")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_dropin.cpp"),
-                           "-o", exe, "-L" + pkgdir, "-llzb_vio_b200", "-lsvo_b200", "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-o", exe, "-L" + pkgdir, "-llzb_vio_b200", "-lsvo_b200", "-lsvo_synth", "-L" + os.path.join(ROOT, "oracle"), "-loracle",
                            "-Wl,-rpath," + pkgdir, "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-pthread"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "DROPIN PASS" in out.stdout, out.stdout + out.stderr

@@ -179,3 +179,16 @@ def test_live_cv2_cross_check(orc, pkg):
             kk = f20.detect(lvl[y0:y1, x0:x1]) or f7.detect(lvl[y0:y1, x0:x1])
             exp += [(k.pt[0] + j * wC, k.pt[1] + i * hC, k.response) for k in kk]
     assert np.array_equal(_kp3(o.candidates(1)), np.array(exp, np.float32).reshape(-1, 3))
+
+
+def test_cv2_primitive_orb_equals_oracle(pkg, orc):
+    """CPU baseline variant 2 (real cv2.resize / cv2.FAST per cell / cv2.GaussianBlur + the oracle's octree / IC_Angle / BRIEF loops)
+    gives the oracle's keypoints and descriptors: the three baseline variants time the same computation."""
+    cv2 = pytest.importorskip("cv2")
+    import ref_pipeline
+    for (w, h, nfeat, seed) in ((640, 200, 500, 7), (1241, 376, 1000, 1000)):
+        left, _ = pkg.synth_stereo_frame(seed, 2, w, h)
+        k0, d0 = orc.OrbOracle(nfeat, 1.2, 8, 20, 7).extract(left)
+        k1, d1 = ref_pipeline.Cv2PrimitiveOrb(nfeat, 1.2, 8, 20, 7).extract(left)
+        assert len(k0) == len(k1) and np.array_equal(k0, k1)
+        assert np.array_equal(d0, d1)

@@ -66,8 +66,8 @@ def test_shard_equivalence(pkg):
     fields = ("kps_left", "n_left", "n_query", "stereo_idx", "temporal_idx", "temporal_dist", "n_seed", "lk_p3", "lk_status",
               "n_orb_matched", "orb_t2_left", "n_lk_matched", "lkf_t2_left")
 
-    def run(f0, n):
-        ctx = pkg.Context(0, w, h, 2 * (B + 1))
+    def run(f0, n, device=0):
+        ctx = pkg.Context(device, w, h, 2 * (B + 1))
         ctx.orb_configure(400, 1.2, 8, 20, 7)
         ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
         kc, pc = ctx.orb_capacity(w, h), max(1024, w * h // 64)
@@ -87,14 +87,21 @@ def test_shard_equivalence(pkg):
 
     whole = run(0, F)
     assert sorted(whole) == list(range(F - 1))
-    merged = {}
-    for r in range(2):
-        f0, n = sh.shard_units(F, 2, r)
-        merged.update(run(f0, n))
-    assert sorted(merged) == sorted(whole)
-    for u in whole:
-        for a, b in zip(whole[u], merged[u]):
-            assert np.array_equal(a, b), u
+    import torch
+    ndev = torch.cuda.device_count()
+    # two ranks on ONE device, and -- when the box has more than one GPU -- one rank per device (the real sharded layout; the
+    # C5 line of bench.py --config c5 does the same across processes and compares a hash of per-unit signatures)
+    layouts = [[0, 0]] + ([[0, 1]] if ndev >= 2 else []) + ([[0, 1, 2, 3]] if ndev >= 4 else [])
+    for devices in layouts:
+        merged = {}
+        for r, dev in enumerate(devices):
+            f0, n = sh.shard_units(F, len(devices), r)
+            merged.update(run(f0, n, dev))
+        assert sorted(merged) == sorted(whole)
+        for u in whole:
+            for a, b in zip(whole[u], merged[u]):
+                assert np.array_equal(a, b), (devices, u)
+    print(f"shard equivalence checked on device layouts {layouts} ({ndev} GPUs visible)")
 
 
 def test_error_paths(pkg):

@@ -1,0 +1,183 @@
+"""GPU: the state machine of the throughput mode -- capacity overflows are never silent, a download that fails on a caller
+capacity can be retried, standalone calls and batches may be mixed on one context, and the LK chain's `err` output equals the
+oracle's (the reference passes `err` to every calcOpticalFlowPyrLK call, tracking.cpp:593-618)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _dots(n, h, w, step=4):
+    """Isolated bright dots on a dark field: every dot is a FAST corner that survives suppression (1 / step^2 of the pixels)."""
+    img = np.full((n, h, w), 10, np.uint8)
+    img[:, 4:h - 4:step, 4:w - 4:step] = 250
+    return img
+
+
+def test_overflow_is_reported_on_download_and_on_check(pkg):
+    w, h, B = 640, 200, 2
+    ctx = pkg.Context(0, w, h, 2 * (2 * B + 1))
+    ctx.frontend_configure(w, h, pkg.MODE_LK, B)
+    pt_cap = max(1024, w * h // 64)
+    dots = _dots(B, h, w)  # ~ w * h / 16 corners per frame: four times the device's pt_cap
+    good_l, good_r = pkg.synth_sequence(3, 0, B, w, h)
+    out = pkg.FrontendBuffers(B, 1, pt_cap, fields=("n_fast", "n_seed", "fast_kps"))
+    with pytest.raises(pkg.SvoError) as e:
+        ctx.frontend_batch(dots, dots, out)
+    assert e.value.code == pkg.SVO_ERR_CAPACITY and "device capacity" in str(e.value)
+    # the flags are per run: a following good batch is delivered, and the overflowed run is gone from the queue
+    ctx.frontend_reset()
+    ctx.frontend_batch(good_l, good_r, out)
+    assert out.n_fast.min() > 50
+    # device-resident pipeline: the run is retired without a download; svo_frontend_check() must still see the overflow
+    ctx.frontend_reset()
+    ctx.frontend_upload(dots, dots)
+    ctx.frontend_run()
+    ctx.frontend_download(None)
+    ctx.frontend_upload(good_l, good_r)  # later good runs do not hide it
+    ctx.frontend_run()
+    ctx.frontend_download(None)
+    with pytest.raises(pkg.SvoError) as e:
+        ctx.frontend_check()
+    assert e.value.code == pkg.SVO_ERR_CAPACITY
+    ctx.frontend_check()  # reported once, then clear
+    ctx.close()
+
+
+def test_download_with_small_caller_buffers_can_be_retried(pkg):
+    w, h, B = 640, 200, 2
+    left, right = pkg.synth_sequence(5, 0, 2 * B, w, h)
+    ctx = pkg.Context(0, w, h, 2 * (2 * B + 1))
+    ctx.orb_configure(300, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    kp_cap, pt_cap = ctx.orb_capacity(w, h), max(1024, w * h // 64)
+    ref = pkg.FrontendBuffers(B, kp_cap, pt_cap)
+    ctx.frontend_batch(np.ascontiguousarray(left[:B]), np.ascontiguousarray(right[:B]), ref)
+    ctx.frontend_reset()
+    ctx.frontend_upload(np.ascontiguousarray(left[:B]), np.ascontiguousarray(right[:B]))
+    ctx.frontend_run()
+    for bad in (pkg.FrontendBuffers(B, kp_cap - 1, pt_cap), pkg.FrontendBuffers(B, kp_cap, 8)):
+        with pytest.raises(pkg.SvoError) as e:
+            ctx.frontend_download(bad)
+        assert e.value.code == pkg.SVO_ERR_CAPACITY and "kept queued" in str(e.value)
+        assert bad.n_left.sum() == 0 and bad.kps_left["x"].sum() == 0  # nothing was written
+    again = pkg.FrontendBuffers(B, kp_cap, pt_cap)
+    ctx.frontend_download(again)  # the same run, delivered now
+    for name in ("kps_left", "desc_left", "n_left", "stereo_idx", "fast_kps", "lk_p1", "lk_status", "n_lk_matched", "lk_err"):
+        assert np.array_equal(getattr(ref, name), getattr(again, name)), name
+    with pytest.raises(pkg.SvoError):
+        ctx.frontend_download(again)  # nothing left
+    ctx.frontend_upload(np.ascontiguousarray(left[B:]), np.ascontiguousarray(right[B:]))
+    ctx.frontend_run()
+    ctx.frontend_discard()
+    with pytest.raises(pkg.SvoError):
+        ctx.frontend_download(again)
+    ctx.close()
+
+
+def test_standalone_calls_between_batches(pkg, orc):
+    """svo_fast_detect with a cap above the front-end's pt_cap re-allocates the point buffers; the context must not
+    keep using the stale throughput-mode layout, and a standalone call must not leave a clobbered `last frame` behind."""
+    w, h, B = 640, 200, 2
+    left, right = pkg.synth_sequence(9, 0, 2 * B, w, h)
+    ctx = pkg.Context(0, w, h, 2 * (B + 1))
+    ctx.orb_configure(300, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    kp_cap, pt_cap = ctx.orb_capacity(w, h), max(1024, w * h // 64)
+    a = pkg.FrontendBuffers(B, kp_cap, pt_cap)
+    ctx.frontend_batch(np.ascontiguousarray(left[:B]), np.ascontiguousarray(right[:B]), a)
+    # a standalone call with the SAME capacity: allowed, drops the carried frame
+    k = ctx.fast_detect(left[0], 20, True, cap=pt_cap)
+    assert np.array_equal(k, orc.fast9(left[0], 20))
+    b = pkg.FrontendBuffers(B, kp_cap, pt_cap)
+    ctx.frontend_batch(np.ascontiguousarray(left[B:]), np.ascontiguousarray(right[B:]), b)
+    assert b.n_query[0] == 0 and b.n_seed[0] == 0 and b.n_query[1] == b.n_left[0]  # like after a reset
+    # a standalone call that grows the point buffers: the throughput mode must be configured again
+    k = ctx.fast_detect(left[1], 20, True, cap=w * h // 16)
+    assert np.array_equal(k, orc.fast9(left[1], 20))
+    with pytest.raises(pkg.SvoError):
+        ctx.frontend_upload(np.ascontiguousarray(left[:B]), np.ascontiguousarray(right[:B]))
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    c = pkg.FrontendBuffers(B, kp_cap, max(1024, w * h // 16))
+    ctx.frontend_batch(np.ascontiguousarray(left[:B]), np.ascontiguousarray(right[:B]), c)
+    for name in ("kps_left", "desc_left", "n_left", "stereo_idx", "n_fast", "n_lk_matched"):
+        assert np.array_equal(getattr(a, name), getattr(c, name)), name
+    ns = int(a.n_seed[1])
+    assert np.array_equal(a.lk_p1[1, :ns], c.lk_p1[1, :ns]) and np.array_equal(a.lk_status[1, :, :ns], c.lk_status[1, :, :ns])
+    # undelivered runs block standalone calls instead of being clobbered
+    ctx.frontend_upload(np.ascontiguousarray(left[B:]), np.ascontiguousarray(right[B:]))
+    ctx.frontend_run()
+    with pytest.raises(pkg.SvoError):
+        ctx.orb_extract(left[0])
+    ctx.frontend_download(c)
+    ctx.orb_extract(left[0])
+    ctx.close()
+
+
+def test_lk_chain_err_equals_oracle(pkg, orc):
+    w, h, B = 640, 200, 3
+    left, right = pkg.synth_sequence(1000, 14, B, w, h)
+    ctx = pkg.Context(0, w, h, 2 * (B + 1))
+    ctx.frontend_configure(w, h, pkg.MODE_LK, B)
+    pt_cap = max(1024, w * h // 64)
+    out = pkg.FrontendBuffers(B, 1, pt_cap)
+    ctx.frontend_batch(left, right, out)
+    checked = 0
+    for f in range(1, B):
+        seeds = orc.fast9(left[f - 1], 20)
+        pts = np.stack([seeds["x"], seeds["y"]], 1)
+        ns = int(out.n_seed[f])
+        assert ns == len(pts)
+        chain = ((left[f - 1], right[f - 1]), (right[f - 1], right[f]), (right[f], left[f]), (left[f], left[f - 1]))
+        cum = np.ones(ns, bool)
+        src = pts
+        for k, (a, b) in enumerate(chain):
+            p, s, e = orc.lk_track(a, b, src)
+            ok = cum & (s == 1)
+            ge = out.lk_err[f, k, :ns]
+            assert np.abs(ge[ok] - e[ok]).max() <= 0.02, f"err of call {k + 1}"  # mean absolute window difference / 32
+            assert np.all(ge[cum & (s == 0)] == 0)
+            cum = ok
+            src = p
+            checked += int(ok.sum())
+    assert checked > 500
+    # switched off: the field is left alone
+    ctx.frontend_set_lk_err(False)
+    ctx.frontend_reset()
+    out2 = pkg.FrontendBuffers(B, 1, pt_cap)
+    ctx.frontend_batch(left, right, out2)
+    assert out2.lk_err.sum() == 0 and np.array_equal(out2.lk_p1, out.lk_p1) and np.array_equal(out2.lk_status, out.lk_status)
+    ctx.close()
+
+
+def test_match_4000_by_4000(pkg, orc):
+    """BASELINE.json configs[3]: both brute-force matches at 4000 features."""
+    rng = np.random.default_rng(4000)
+    t = rng.integers(0, 256, (4000, 32), dtype=np.uint8)
+    q = t[rng.permutation(4000)].copy()
+    flip = rng.integers(0, 256, (4000, 32), dtype=np.uint8) & rng.integers(0, 256, (4000, 32), dtype=np.uint8) & rng.integers(0, 256, (4000, 32), dtype=np.uint8)
+    q ^= flip  # ~12 % of the bits flipped: distances well below random pairs, many near-ties among the 4000 candidates
+    q[:50] = t[7]  # 50 queries with several exact minima: first-index tie-break
+    t[100:110] = t[7]
+    ctx = pkg.Context(0, 64, 64, 2)
+    gi, gd = ctx.match_hamming(q, t)
+    oi, od = orc.match_hamming(q, t)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    assert np.all(gi[:50] == 7)
+    ctx.close()
+
+
+def test_right_image_at_4k(pkg, orc):
+    """The right image of the 3840x2160 pair (tests/test_orb_gpu.py checks the left one against the oracle)."""
+    w, h, nfeat = 3840, 2160, 4000
+    left, right = pkg.synth_stereo_frame(3000, 0, w, h)
+    ctx = pkg.Context(0, w, h, 2)
+    ctx.orb_configure(nfeat, 1.2, 8, 20, 7)
+    kps, desc = ctx.orb_extract_batch([left, right])
+    o = orc.OrbOracle(nfeat, 1.2, 8, 20, 7)
+    ok, od = o.extract(right)
+    assert len(kps[1]) == len(ok) and np.array_equal(kps[1], ok)
+    assert int(np.unpackbits(desc[1] ^ od).sum()) <= 10
+    for l in (0, 3, 7):
+        assert np.array_equal(ctx.orb_read_level(1, l), o.level(l))
+    ctx.close()
