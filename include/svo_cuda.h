@@ -212,6 +212,28 @@ int svo_frontend_discard(svo_ctx* ctx);
 int svo_frontend_batch(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride,
                        svo_frontend_out* out);
 
+/* ---- frame source (host code; replaces System::NextFrame_kitti, System.cpp:75-104) ----------------------------------- */
+/* Reads <dir>/image_0/%06d.png (left) and <dir>/image_1/%06d.png (right) from index first_index on, like the reference's
+ * cv::imread(..., IMREAD_GRAYSCALE); the run ends at the first missing pair (the reference returns a null frame there).
+ * 8-bit greyscale non-interlaced PNG (the KITTI odometry grey sequences) and binary PGM (%06d.pgm) are decoded; any other
+ * format or a size other than w x h is an error.  `threads` decoder threads fill a ring of `ring_batches` (>= 2) batches of
+ * `batch` frames in PINNED host memory ahead of the consumer. */
+typedef struct svo_source svo_source;
+int svo_source_open(svo_source** src, const char* dir, int first_index, int w, int h, int batch, int ring_batches, int threads);
+/* Number of consecutive stereo pairs found from first_index on. */
+int svo_source_frame_count(const svo_source* src);
+/* 1 if the ring is pinned (page-locked) memory; 0 on a host without a CUDA device (ordinary memory: decoder tests / tools). */
+int svo_source_is_pinned(const svo_source* src);
+/* Next batch in sequence order: *left / *right point at *n_frames contiguous w x h images (stride w), valid until the next call
+ * (pass them to svo_frontend_upload and call svo_frontend_run before asking for the next batch).  *n_frames == 0: end of the run.
+ * Blocks until the batch is decoded.  SVO_ERR_INVALID on a decode error (svo_source_error). */
+int svo_source_next(svo_source* src, const uint8_t** left, const uint8_t** right, int* n_frames);
+const char* svo_source_error(const svo_source* src);
+void svo_source_close(svo_source* src);
+/* Writers for tests and benchmarks (synthetic sequences on disk in the reference's dataset layout). */
+int svo_write_pgm(const char* path, const uint8_t* img, int w, int h, size_t stride);
+int svo_write_png(const char* path, const uint8_t* img, int w, int h, size_t stride, int zlib_level);
+
 /* ---- deterministic synthetic stereo sequences (bench / tests input; host code, needs no GPU) --------------------- */
 /* Frame `frame` of sequence `seed`: textured canvas, 8-px disparity, 2-px/frame motion, canvas
  * re-seeded every 16 frames.  left/right: h rows of `stride` bytes.  Lives in its own host-only library, libsvo_synth.so

@@ -35,7 +35,8 @@ ABI_SYMBOLS = [
     "svo_orb_read_candidates", "svo_fast_detect", "svo_match_hamming", "svo_lk_track", "svo_frontend_configure",
     "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_overlap", "svo_frontend_set_lk_err", "svo_frontend_set_projection",
     "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_check",
-    "svo_frontend_discard", "svo_frontend_batch",
+    "svo_frontend_discard", "svo_frontend_batch", "svo_source_open", "svo_source_frame_count", "svo_source_is_pinned", "svo_source_next",
+    "svo_source_error", "svo_source_close", "svo_write_pgm", "svo_write_png",
 ]
 SYNTH_SYMBOLS = ["svo_synth_stereo_frame"]  # exported by libsvo_synth.so
 
@@ -88,6 +89,16 @@ def lib():
         L.svo_ctx_stage_ms.restype = C.c_float
         L.svo_ctx_stage_ms.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.svo_orb_configure.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.svo_source_open.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.svo_source_frame_count.argtypes = [C.c_void_p]
+        L.svo_source_is_pinned.argtypes = [C.c_void_p]
+        L.svo_source_next.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        L.svo_source_error.restype = C.c_char_p
+        L.svo_source_error.argtypes = [C.c_void_p]
+        L.svo_source_close.argtypes = [C.c_void_p]
+        L.svo_source_close.restype = None
+        L.svo_write_pgm.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+        L.svo_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int]
         L.svo_lk_track.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         _lib = L
@@ -116,6 +127,63 @@ def synth_sequence(seed, first, count, w, h):
         if rc != 0:
             raise SvoError(rc, "svo_synth_stereo_frame")
     return left, right
+
+
+def write_sequence(directory, left, right, first_index=0, fmt="png", zlib_level=1):
+    """left / right (n, h, w) uint8 -> <directory>/image_0|1/%06d.<fmt> (the reference's dataset layout, System.cpp:77)."""
+    L = lib()
+    n, h, w = left.shape
+    for side, imgs in ((0, left), (1, right)):
+        os.makedirs(os.path.join(directory, f"image_{side}"), exist_ok=True)
+        for i in range(n):
+            path = os.path.join(directory, f"image_{side}", f"{first_index + i:06d}.{fmt}").encode()
+            img = np.ascontiguousarray(imgs[i])
+            rc = L.svo_write_png(path, _p(img), w, h, w, zlib_level) if fmt == "png" else L.svo_write_pgm(path, _p(img), w, h, w)
+            if rc != 0:
+                raise SvoError(rc, f"cannot write {path.decode()}")
+
+
+class FrameSource:
+    """svo_source: decoder threads filling a pinned ring of batches from a KITTI-layout directory (System::NextFrame_kitti)."""
+
+    def __init__(self, directory, w, h, batch, ring_batches=3, threads=8, first_index=0):
+        self._L = lib()
+        hnd = C.c_void_p()
+        rc = self._L.svo_source_open(C.byref(hnd), directory.encode(), first_index, w, h, batch, ring_batches, threads)
+        if rc != 0:
+            raise SvoError(rc, "svo_source_open failed")
+        self._h, self.w, self.h, self.batch = hnd, w, h, batch
+
+    def frame_count(self):
+        return int(self._L.svo_source_frame_count(self._h))
+
+    def is_pinned(self):
+        return bool(self._L.svo_source_is_pinned(self._h))
+
+    def next_ptr(self):
+        """-> (left address, right address, n_frames); n_frames == 0 at the end of the run"""
+        l, r, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        rc = self._L.svo_source_next(self._h, C.byref(l), C.byref(r), C.byref(n))
+        if rc != 0:
+            raise SvoError(rc, self._L.svo_source_error(self._h).decode())
+        return l.value, r.value, n.value
+
+    def next(self):
+        """-> (left, right) numpy views (n, h, w) into the ring, valid until the next call; None at the end of the run"""
+        l, r, n = self.next_ptr()
+        if n == 0:
+            return None
+        shape = (n, self.h, self.w)
+        mk = lambda a: np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_uint8)), shape=shape)
+        return mk(l), mk(r)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.svo_source_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 class Context:

@@ -181,3 +181,39 @@ def test_right_image_at_4k(pkg, orc):
     for l in (0, 3, 7):
         assert np.array_equal(ctx.orb_read_level(1, l), o.level(l))
     ctx.close()
+
+
+def test_frame_source_feeds_the_frontend(pkg, tmp_path):
+    """System::NextFrame_kitti replacement: PNG files on disk -> decoder threads -> pinned ring -> svo_frontend_upload; the results
+    equal those of the same frames handed over from memory."""
+    w, h, B, F = 640, 200, 4, 10
+    left, right = pkg.synth_sequence(21, 0, F, w, h)
+    pkg.write_sequence(str(tmp_path), left, right, fmt="png")
+    ctx = pkg.Context(0, w, h, 2 * (2 * B + 1))
+    ctx.orb_configure(300, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    kp_cap, pt_cap = ctx.orb_capacity(w, h), max(1024, w * h // 64)
+    ref = []
+    for f0 in range(0, F, B):
+        n = min(B, F - f0)
+        o = pkg.FrontendBuffers(n, kp_cap, pt_cap)
+        ctx.frontend_batch(np.ascontiguousarray(left[f0:f0 + n]), np.ascontiguousarray(right[f0:f0 + n]), o)
+        ref.append(o)
+    ctx.frontend_reset()
+    src = pkg.FrameSource(str(tmp_path), w, h, B, ring_batches=2, threads=3)
+    assert src.is_pinned() and src.frame_count() == F
+    i = 0
+    while True:
+        l, r, n = src.next_ptr()
+        if n == 0:
+            break
+        o = pkg.FrontendBuffers(n, kp_cap, pt_cap)
+        ctx.frontend_upload_ptr(l, r, n, w)
+        ctx.frontend_run()
+        ctx.frontend_download(o)
+        for name in ("kps_left", "desc_right", "n_left", "stereo_idx", "temporal_idx", "fast_kps", "lk_p3", "lk_status", "n_lk_matched", "n_orb_matched"):
+            assert np.array_equal(getattr(o, name), getattr(ref[i], name)), (i, name)
+        i += 1
+    assert i == len(ref)
+    src.close()
+    ctx.close()

@@ -1,6 +1,6 @@
 # quick GPU check: parity tests, then a short bench summary
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -${TAIL:-6}
 python bench.py --no-cpu-baseline ${BENCH_ARGS:-} 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench_last.json
 python - <<'PY'
 import json
