@@ -10,10 +10,17 @@
 #include <memory>
 #include <vector>
 
+// the type codes are macros in OpenCV; same values here
+#ifndef CV_8U
+#define CV_8U 0
+#define CV_8UC1 0
+#define CV_32F 5
+#define CV_32FC1 5
+#endif
+
 namespace cv {
 
 typedef unsigned char uchar;
-enum { CV_8U = 0, CV_8UC1 = 0, CV_32F = 5, CV_32FC1 = 5 };
 
 template <typename T>
 struct Point_ {
@@ -82,6 +89,8 @@ public:
         step = 0;
     }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    // cv::_InputArray::getMat() / cv::_OutputArray::getMat(): here the array types ARE Mat references, so this is the identity
+    Mat getMat() const { return *this; }
     int type() const { return type_; }
     size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
     bool isContinuous() const { return step == (size_t)cols * elemSize(); }

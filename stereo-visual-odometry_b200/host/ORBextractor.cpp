@@ -58,30 +58,31 @@ void ORBextractor::fill_pyramid(int w, int h) {
     for (int l = 0; l < nlevels; ++l) {
         int lw = 0, lh = 0;
         if (svo_orb_level_size(ctx_, w, h, l, &lw, &lh) != SVO_OK) return;
-        cv::Mat whole(lh + 2 * kEdge, lw + 2 * kEdge, cv::CV_8UC1);
-        unsigned char* inner = whole.data + (size_t)kEdge * whole.step + kEdge;
-        if (svo_orb_read_level(ctx_, 0, l, inner, whole.step, &lw, &lh) != SVO_OK) return;
+        cv::Mat whole(lh + 2 * kEdge, lw + 2 * kEdge, CV_8UC1);
+        unsigned char* inner = whole.ptr(kEdge) + kEdge;
+        if (svo_orb_read_level(ctx_, 0, l, inner, (size_t)whole.step, &lw, &lh) != SVO_OK) return;
         auto refl = [](int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); };
         for (int y = 0; y < lh; ++y) {
-            unsigned char* row = inner + (size_t)y * whole.step;
+            unsigned char* row = inner + (size_t)y * (size_t)whole.step;
             for (int x = 1; x <= kEdge; ++x) {
                 row[-x] = row[refl(-x, lw)];
                 row[lw - 1 + x] = row[refl(lw - 1 + x, lw)];
             }
         }
         for (int y = 1; y <= kEdge; ++y) {
-            std::memcpy(whole.data + (size_t)(kEdge - y) * whole.step, whole.data + (size_t)(kEdge + refl(-y, lh)) * whole.step, whole.step);
-            std::memcpy(whole.data + (size_t)(kEdge + lh - 1 + y) * whole.step, whole.data + (size_t)(kEdge + refl(lh - 1 + y, lh)) * whole.step, whole.step);
+            std::memcpy(whole.ptr(kEdge - y), whole.ptr(kEdge + refl(-y, lh)), (size_t)whole.step);
+            std::memcpy(whole.ptr(kEdge + lh - 1 + y), whole.ptr(kEdge + refl(lh - 1 + y, lh)), (size_t)whole.step);
         }
         // the reference stores the ROI without the border (temp(Rect(19,19,w,h)), :1069); keep that view semantics
-        mvImagePyramid[l] = cv::Mat(lh, lw, cv::CV_8UC1, inner, whole.step);
+        mvImagePyramid[l] = cv::Mat(lh, lw, CV_8UC1, inner, (size_t)whole.step);
         pyramid_store_[l] = whole;
     }
 }
 
-void ORBextractor::operator()(cv::InputArray image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors) {
-    if (image.empty()) return;
-    assert(image.type() == cv::CV_8UC1);
+void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray _descriptors) {
+    if (_image.empty()) return;
+    const cv::Mat image = _image.getMat();  // ORBextractor.cpp:996
+    assert(image.type() == CV_8UC1);
     const int w = image.cols, h = image.rows;
     svo_ctx* c = context(w, h);
     const int cap = svo_orb_capacity(c, w, h);
@@ -89,12 +90,13 @@ void ORBextractor::operator()(cv::InputArray image, cv::InputArray /*mask*/, std
     desc_buf_.resize((size_t)std::max(cap, 1) * 32);
     int n = 0;
     static_assert(sizeof(cv::KeyPoint) == sizeof(svo_keypoint), "cv::KeyPoint layout");
-    const int rc = svo_orb_extract(c, image.data, w, h, image.step, reinterpret_cast<svo_keypoint*>(kp_buf_.data()), desc_buf_.data(), cap, &n);
+    const int rc = svo_orb_extract(c, image.data, w, h, (size_t)image.step, reinterpret_cast<svo_keypoint*>(kp_buf_.data()), desc_buf_.data(), cap, &n);
     if (rc != SVO_OK) throw std::runtime_error(std::string("svo_orb_extract: ") + svo_last_error(c));
     if (n == 0) {
-        descriptors.release();
+        _descriptors.release();
     } else {
-        descriptors.create(n, 32, cv::CV_8U);
+        _descriptors.create(n, 32, CV_8U);  // ORBextractor.cpp:1017
+        cv::Mat descriptors = _descriptors.getMat();
         for (int i = 0; i < n; ++i) std::memcpy(descriptors.ptr(i), desc_buf_.data() + (size_t)i * 32, 32);
     }
     keypoints.assign(kp_buf_.begin(), kp_buf_.begin() + n);

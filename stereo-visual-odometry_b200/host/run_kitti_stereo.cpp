@@ -1,0 +1,122 @@
+// host/run_kitti_stereo.cpp -- the front-end of app/run_kitti_stereo.cpp (reference: app/run_kitti_stereo.cpp:5-19 -> System::Init /
+// Run / Step, System.cpp:28-104) on the B200 path: a KITTI-layout dataset directory is decoded by the frame source
+// (svo_source, System::NextFrame_kitti) and pushed through the throughput mode in batches; per frame it prints what
+// Tracking::ORB_StereoF2F_PnP_Track / LK_StereoF2F_PnP_Track hand to the pose back-end (number of matched / tracked points).
+// The pose back-end itself (solvePnPRansac, g2o, Pangolin viewer) is the reference's host code and is not part of this binary.
+//
+//   run_kitti_stereo <dataset_dir> [--mode orb|lk|both] [--batch 64] [--threads 8] [--width W --height H] [--nfeatures 1000] [--quiet]
+// The image size is taken from the first left image unless given.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "svo_cuda.h"
+
+static bool probe_size(const std::string& dir, int* w, int* h) {
+    for (const char* ext : {"png", "pgm"}) {
+        const std::string p = dir + "/image_0/000000." + ext;
+        FILE* f = fopen(p.c_str(), "rb");
+        if (!f) continue;
+        unsigned char b[32] = {0};
+        const size_t n = fread(b, 1, sizeof b, f);
+        fclose(f);
+        if (!strcmp(ext, "png") && n >= 24) {
+            *w = (b[16] << 24) | (b[17] << 16) | (b[18] << 8) | b[19];
+            *h = (b[20] << 24) | (b[21] << 16) | (b[22] << 8) | b[23];
+            return true;
+        }
+        if (!strcmp(ext, "pgm") && sscanf((const char*)b, "P5 %d %d", w, h) == 2) return true;
+    }
+    return false;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) {
+        fprintf(stderr, "usage: %s <dataset_dir> [--mode orb|lk|both] [--batch N] [--threads N] [--width W --height H] [--nfeatures N] [--quiet]\n", argv[0]);
+        return 2;
+    }
+    const std::string dir = argv[1];
+    int mode = SVO_MODE_ORB | SVO_MODE_LK, batch = 64, threads = 8, w = 0, h = 0, nfeatures = 1000;
+    bool quiet = false;
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto val = [&]() { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--mode") {
+            const std::string m = val();
+            mode = m == "orb" ? SVO_MODE_ORB : (m == "lk" ? SVO_MODE_LK : (SVO_MODE_ORB | SVO_MODE_LK));
+        } else if (a == "--batch") batch = atoi(val());
+        else if (a == "--threads") threads = atoi(val());
+        else if (a == "--width") w = atoi(val());
+        else if (a == "--height") h = atoi(val());
+        else if (a == "--nfeatures") nfeatures = atoi(val());
+        else if (a == "--quiet") quiet = true;
+    }
+    if ((w <= 0 || h <= 0) && !probe_size(dir, &w, &h)) {
+        fprintf(stderr, "cannot read %s/image_0/000000.png|pgm\n", dir.c_str());
+        return 1;
+    }
+    svo_source* src = nullptr;
+    if (svo_source_open(&src, dir.c_str(), 0, w, h, batch, 3, threads) != SVO_OK) {
+        fprintf(stderr, "svo_source_open failed\n");
+        return 1;
+    }
+    const int total = svo_source_frame_count(src);
+    printf("dataset %s: %d stereo pairs of %dx%d, batch %d, %d decoder threads\n", dir.c_str(), total, w, h, batch, threads);
+    svo_ctx* c = nullptr;
+    if (svo_ctx_create(&c, 0, w, h, 2 * (2 * batch + 1)) != SVO_OK) {
+        fprintf(stderr, "no CUDA device (there is no CPU fallback)\n");
+        return 1;
+    }
+    auto die = [&](const char* what) {
+        fprintf(stderr, "%s: %s\n", what, svo_last_error(c));
+        exit(1);
+    };
+    if (svo_orb_configure(c, nfeatures, 1.2f, 8, 20, 7) != SVO_OK) die("svo_orb_configure");  // config/default.yaml ORBextractor.*
+    if (svo_frontend_configure(c, w, h, mode, batch) != SVO_OK) die("svo_frontend_configure");
+    std::vector<int32_t> n_orb(batch), n_lk(batch), n_left(batch), n_fast(batch);
+    svo_frontend_out out;
+    memset(&out, 0, sizeof out);
+    out.kp_cap = svo_orb_capacity(c, w, h);
+    out.pt_cap = 1 << 20;
+    out.n_orb_matched = n_orb.data();
+    out.n_lk_matched = n_lk.data();
+    out.n_left = n_left.data();
+    out.n_fast = n_fast.data();
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint8_t *l = nullptr, *r = nullptr;
+    int n = 0, frame = 0, pending = 0;
+    long long sum_orb = 0, sum_lk = 0;
+    auto report = [&](int k) {
+        for (int i = 0; i < k; ++i, ++frame) {
+            sum_orb += n_orb[i];
+            sum_lk += n_lk[i];
+            if (!quiet)
+                printf("frame %06d: keypoints %d, ORB matches %d, FAST corners %d, LK tracks %d\n", frame, (mode & SVO_MODE_ORB) ? n_left[i] : 0,
+                       (mode & SVO_MODE_ORB) ? n_orb[i] : 0, (mode & SVO_MODE_LK) ? n_fast[i] : 0, (mode & SVO_MODE_LK) ? n_lk[i] : 0);
+        }
+    };
+    // pipelined: run(k + 1) is issued before download(k); the source's ring slot of batch k is recycled by the next svo_source_next
+    if (svo_source_next(src, &l, &r, &n) != SVO_OK) { fprintf(stderr, "%s\n", svo_source_error(src)); return 1; }
+    while (n > 0) {
+        if (svo_frontend_upload(c, l, r, n, (size_t)w) != SVO_OK) die("svo_frontend_upload");
+        if (svo_frontend_run(c) != SVO_OK) die("svo_frontend_run");
+        if (pending) {
+            if (svo_frontend_download(c, &out) != SVO_OK) die("svo_frontend_download");
+            report(pending);
+        }
+        pending = n;
+        if (svo_source_next(src, &l, &r, &n) != SVO_OK) { fprintf(stderr, "%s\n", svo_source_error(src)); return 1; }
+    }
+    if (pending) {
+        if (svo_frontend_download(c, &out) != SVO_OK) die("svo_frontend_download");
+        report(pending);
+    }
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("done: %d stereo pairs in %.3f s (%.1f pairs/s incl. decoding), ORB matches %lld, LK tracks %lld\n", frame, s, frame / s, sum_orb, sum_lk);
+    svo_source_close(src);
+    svo_ctx_destroy(c);
+    return frame == total ? 0 : 1;
+}

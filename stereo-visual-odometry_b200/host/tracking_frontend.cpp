@@ -90,7 +90,7 @@ int Tracking::Detect_OpenCVFASTFeatures() {  // tracking.cpp:94-113
     std::vector<cv::KeyPoint> keypoints((size_t)cap);
     int n = 0;
     const int fast_threshold = 20;
-    if (svo_fast_detect(c, img.data, img.cols, img.rows, img.step, fast_threshold, 1, reinterpret_cast<svo_keypoint*>(keypoints.data()), cap, &n) != SVO_OK)
+    if (svo_fast_detect(c, img.data, img.cols, img.rows, (size_t)img.step, fast_threshold, 1, reinterpret_cast<svo_keypoint*>(keypoints.data()), cap, &n) != SVO_OK)
         throw std::runtime_error(std::string("svo_fast_detect: ") + svo_last_error(c));
     Feature::wrap_keypoints(current_frame_, keypoints.data(), (size_t)n, true, current_frame_->features_left_);  // one block, not n `new`s
     return n;
@@ -154,8 +154,8 @@ static void lk_call(svo_ctx* c, const cv::Mat& prev, const cv::Mat& next, const 
     status.assign(p.size(), 0);
     if (p.empty()) return;
     std::vector<float> err(p.size());
-    if (prev.step != next.step) throw std::runtime_error("stereo images must share a row stride");
-    if (svo_lk_track(c, prev.data, next.data, prev.cols, prev.rows, prev.step, reinterpret_cast<const float*>(p.data()), (int)p.size(),
+    if ((size_t)prev.step != (size_t)next.step) throw std::runtime_error("stereo images must share a row stride");
+    if (svo_lk_track(c, prev.data, next.data, prev.cols, prev.rows, (size_t)prev.step, reinterpret_cast<const float*>(p.data()), (int)p.size(),
                      reinterpret_cast<float*>(q.data()), status.data(), err.data(), 21, 3, 30, 0.01, 0.001) != SVO_OK)
         throw std::runtime_error(std::string("svo_lk_track: ") + svo_last_error(c));
 }

@@ -21,8 +21,8 @@ using namespace lzb_vio;
 
 static Frame::Ptr make_frame(uint64_t seed, int t, int w, int h) {
     Frame::Ptr f = Frame::CreateFrame();
-    f->left_img_.create(h, w, cv::CV_8UC1);
-    f->right_img_.create(h, w, cv::CV_8UC1);
+    f->left_img_.create(h, w, CV_8UC1);
+    f->right_img_.create(h, w, CV_8UC1);
     svo_synth_stereo_frame(seed, t, w, h, f->left_img_.data, f->right_img_.data, f->left_img_.step);
     return f;
 }
@@ -60,7 +60,7 @@ int main() {
         std::vector<cv::KeyPoint> k2 = kps;
         ex(none, cv::Mat(), k2, desc);  // empty image: silent return, outputs untouched
         CHECK(k2.size() == kps.size());
-        cv::Mat flat(h, w, cv::CV_8UC1);
+        cv::Mat flat(h, w, CV_8UC1);
         std::memset(flat.data, 90, (size_t)h * flat.step);
         ex(flat, cv::Mat(), k2, desc);
         CHECK(k2.empty() && desc.empty());

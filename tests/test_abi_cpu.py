@@ -62,3 +62,12 @@ def test_synth_is_deterministic_and_stereo(pkg):
     l16, _ = pkg.synth_stereo_frame(1000, 16, 1241, 376)  # canvas re-seeded every 16 frames
     assert np.abs(l0.astype(int) - l16.astype(int)).mean() > 10
     assert pkg.synth_lib().svo_synth_stereo_frame(1, 0, 0, 10, None, None, 0) == pkg.SVO_ERR_INVALID
+
+
+def test_host_sources_typecheck_against_the_opencv_api():
+    """INTEGRATION.md route A builds host/*.cpp with -DSVO_USE_REAL_OPENCV.  This image has no OpenCV C++, so the sources are
+    type-checked (g++ -fsyntax-only) against tests/opencv_api_stub: declarations of the OpenCV classes they touch with the REAL
+    proxy types (cv::_InputArray / _OutputArray / MatStep), not the Mat-reference shim the in-repo build uses."""
+    for src in ("ORBextractor.cpp", "tracking_frontend.cpp"):
+        __import__('subprocess').check_call(["g++", "-std=c++17", "-fsyntax-only", "-DSVO_USE_REAL_OPENCV", "-I" + os.path.join(ROOT, "tests", "opencv_api_stub"),
+                               "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "stereo-visual-odometry_b200", "host", src)])

@@ -19,3 +19,30 @@ def test_cpp_dropin(pkg, orc, tmp_path):
                            "-Wl,-rpath," + pkgdir, "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-pthread"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "DROPIN PASS" in out.stdout, out.stdout + out.stderr
+
+
+def test_run_kitti_stereo_app(pkg, tmp_path):
+    """The front-end of app/run_kitti_stereo.cpp: dataset directory -> svo_source -> throughput mode, as a plain C-ABI binary."""
+    import numpy as np
+    pkgdir = os.path.join(ROOT, "stereo-visual-odometry_b200")
+    exe = os.path.join(pkgdir, "run_kitti_stereo")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(pkgdir, "host"), "-s"])
+    w, h, F = 640, 200, 9
+    left, right = pkg.synth_sequence(31, 0, F, w, h)
+    pkg.write_sequence(str(tmp_path), left, right, fmt="png")
+    out = subprocess.run([exe, str(tmp_path), "--mode", "both", "--batch", "4", "--threads", "3", "--nfeatures", "400"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("frame ")]
+    assert len(lines) == F and "done: 9 stereo pairs" in out.stdout
+    # the same numbers through the Python binding
+    ctx = pkg.Context(0, w, h, 2 * (F + 1))
+    ctx.orb_configure(400, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, F)
+    o = pkg.FrontendBuffers(F, ctx.orb_capacity(w, h), max(1024, w * h // 64), fields=("n_left", "n_orb_matched", "n_fast", "n_lk_matched"))
+    ctx.frontend_batch(left, right, o)
+    for i, l in enumerate(lines):
+        nums = [int(t.strip(",")) for t in l.replace(":", " ").split() if t.strip(",").isdigit()]
+        assert nums[1:] == [int(o.n_left[i]), int(o.n_orb_matched[i]), int(o.n_fast[i]), int(o.n_lk_matched[i])], l
+    ctx.close()
