@@ -63,8 +63,14 @@ def test_download_with_small_caller_buffers_can_be_retried(pkg):
         assert bad.n_left.sum() == 0 and bad.kps_left["x"].sum() == 0  # nothing was written
     again = pkg.FrontendBuffers(B, kp_cap, pt_cap)
     ctx.frontend_download(again)  # the same run, delivered now
-    for name in ("kps_left", "desc_left", "n_left", "stereo_idx", "fast_kps", "lk_p1", "lk_status", "n_lk_matched", "lk_err"):
+    for name in ("n_left", "n_query", "n_fast", "n_seed", "n_lk_matched"):
         assert np.array_equal(getattr(ref, name), getattr(again, name)), name
+    for i in range(B):  # entries beyond the per-frame counts are unspecified
+        nl, nq, nf, ns = int(ref.n_left[i]), int(ref.n_query[i]), int(ref.n_fast[i]), int(ref.n_seed[i])
+        assert np.array_equal(ref.kps_left[i, :nl], again.kps_left[i, :nl]) and np.array_equal(ref.desc_left[i, :nl], again.desc_left[i, :nl])
+        assert np.array_equal(ref.stereo_idx[i, :nq], again.stereo_idx[i, :nq]) and np.array_equal(ref.fast_kps[i, :nf], again.fast_kps[i, :nf])
+        assert np.array_equal(ref.lk_p1[i, :ns], again.lk_p1[i, :ns]) and np.array_equal(ref.lk_status[i, :, :ns], again.lk_status[i, :, :ns])
+        assert np.array_equal(ref.lk_err[i, :, :ns], again.lk_err[i, :, :ns])
     with pytest.raises(pkg.SvoError):
         ctx.frontend_download(again)  # nothing left
     ctx.frontend_upload(np.ascontiguousarray(left[B:]), np.ascontiguousarray(right[B:]))
@@ -100,8 +106,12 @@ def test_standalone_calls_between_batches(pkg, orc):
     ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
     c = pkg.FrontendBuffers(B, kp_cap, max(1024, w * h // 16))
     ctx.frontend_batch(np.ascontiguousarray(left[:B]), np.ascontiguousarray(right[:B]), c)
-    for name in ("kps_left", "desc_left", "n_left", "stereo_idx", "n_fast", "n_lk_matched"):
+    for name in ("n_left", "n_query", "n_fast", "n_lk_matched", "n_seed"):
         assert np.array_equal(getattr(a, name), getattr(c, name)), name
+    for i in range(B):  # entries beyond the per-frame counts are unspecified
+        nl, nq = int(a.n_left[i]), int(a.n_query[i])
+        assert np.array_equal(a.kps_left[i, :nl], c.kps_left[i, :nl]) and np.array_equal(a.desc_left[i, :nl], c.desc_left[i, :nl])
+        assert np.array_equal(a.stereo_idx[i, :nq], c.stereo_idx[i, :nq])
     ns = int(a.n_seed[1])
     assert np.array_equal(a.lk_p1[1, :ns], c.lk_p1[1, :ns]) and np.array_equal(a.lk_status[1, :, :ns], c.lk_status[1, :, :ns])
     # undelivered runs block standalone calls instead of being clobbered
@@ -211,8 +221,15 @@ def test_frame_source_feeds_the_frontend(pkg, tmp_path):
         ctx.frontend_upload_ptr(l, r, n, w)
         ctx.frontend_run()
         ctx.frontend_download(o)
-        for name in ("kps_left", "desc_right", "n_left", "stereo_idx", "temporal_idx", "fast_kps", "lk_p3", "lk_status", "n_lk_matched", "n_orb_matched"):
-            assert np.array_equal(getattr(o, name), getattr(ref[i], name)), (i, name)
+        q = ref[i]
+        for name in ("n_left", "n_right", "n_query", "n_fast", "n_seed", "n_lk_matched", "n_orb_matched"):
+            assert np.array_equal(getattr(o, name), getattr(q, name)), (i, name)
+        for j in range(n):  # entries beyond the per-frame counts are unspecified
+            nl, nr, nq, nf, ns = int(q.n_left[j]), int(q.n_right[j]), int(q.n_query[j]), int(q.n_fast[j]), int(q.n_seed[j])
+            assert np.array_equal(o.kps_left[j, :nl], q.kps_left[j, :nl]) and np.array_equal(o.desc_right[j, :nr], q.desc_right[j, :nr])
+            assert np.array_equal(o.stereo_idx[j, :nq], q.stereo_idx[j, :nq]) and np.array_equal(o.temporal_idx[j, :nq], q.temporal_idx[j, :nq])
+            assert np.array_equal(o.fast_kps[j, :nf], q.fast_kps[j, :nf]) and np.array_equal(o.lk_p3[j, :ns], q.lk_p3[j, :ns])
+            assert np.array_equal(o.lk_status[j, :, :ns], q.lk_status[j, :, :ns])
         i += 1
     assert i == len(ref)
     src.close()
