@@ -112,6 +112,21 @@ int svo_lk_track(svo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int w, 
                  const float* prev_xy, int n, float* next_xy, uint8_t* status, float* err, int win, int max_level,
                  int max_iter, double eps, double min_eig);
 
+/* ---- the Tracking post-filters (device; the same kernels the throughput mode runs) ----------------------------------------- */
+/* The tail of Tracking::ORB_Robust_Find_MuliImage_MatchedFeatures after the two match() calls (tracking.cpp:546-577): of the first
+ * des_index = min(n_last_left, n_last_right, n_cur_left) queries (quirk Q3) those with both distances <= max(2 * min_dist, 30) and
+ * |y_left - y_right| < feature_match_error are accepted, in query order.  idx1/dist1: match(last_left, last_right), idx2/dist2:
+ * match(last_left, cur_left).  Outputs: cap x 2 floats each (what the reference push_backs), *n_out accepted matches. */
+int svo_orb_match_filter(svo_ctx* ctx, const svo_keypoint* last_left, int n_last_left, const svo_keypoint* last_right, int n_last_right,
+                         const svo_keypoint* cur_left, int n_cur_left, const int32_t* idx1, const int32_t* dist1, const int32_t* idx2,
+                         const int32_t* dist2, double feature_match_error, float* t2_left, float* t1_left, float* t1_right, int cap,
+                         int* n_out);
+/* Tracking::deleteBadmatchFeatures (tracking.cpp:623-660): a track is dropped if one of its five points has a negative coordinate,
+ * one of its four status bytes is 0, or |p0.y - p1.y| or |p2.y - p3.y| exceeds feature_match_error.  The five n x 2 lists are
+ * compacted IN PLACE (order kept), *n_out survivors. */
+int svo_lk_chain_filter(svo_ctx* ctx, int n, float* p0, float* p1, float* p2, float* p3, float* p0_return, const uint8_t* status0,
+                        const uint8_t* status1, const uint8_t* status2, const uint8_t* status3, double feature_match_error, int* n_out);
+
 /* ---- triangulation ------------------------------------------------------------------------------------------- */
 /* Replaces cv::triangulatePoints(P1, P2, pts1, pts2, points4D) + cv::convertPointsFromHomogeneous (tracking.cpp:190-192,
  * 292-294).  proj1/proj2: 3x4 row-major doubles; pts: n x 2 floats; points4d (may be NULL): n x 4 floats (column i of

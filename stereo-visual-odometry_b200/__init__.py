@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_overlap", "svo_frontend_set_lk_err", "svo_frontend_set_projection",
     "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_check",
     "svo_frontend_discard", "svo_frontend_batch", "svo_source_open", "svo_source_frame_count", "svo_source_is_pinned", "svo_source_next",
-    "svo_source_error", "svo_source_close", "svo_write_pgm", "svo_write_png",
+    "svo_source_error", "svo_source_close", "svo_write_pgm", "svo_write_png", "svo_orb_match_filter", "svo_lk_chain_filter",
 ]
 SYNTH_SYMBOLS = ["svo_synth_stereo_frame"]  # exported by libsvo_synth.so
 
@@ -321,6 +321,26 @@ class Context:
         self._check(self._L.svo_lk_track(self._h, _p(prev), _p(nxt), w, h, prev.strides[0], _p(pts), n, _p(out), _p(status), _p(err),
                                          win, max_level, max_iter, eps, min_eig))
         return out, status, err
+
+    # ---- the Tracking post-filters on the device (tracking.cpp:546-577, 623-660)
+    def orb_match_filter(self, last_left, last_right, cur_left, idx1, dist1, idx2, dist2, fme=3.0):
+        """-> (t2_left, t1_left, t1_right) point lists [n, 2]"""
+        ll, lr, cl = (np.ascontiguousarray(a, KP_DTYPE) for a in (last_left, last_right, cur_left))
+        i1, d1, i2, d2 = (np.ascontiguousarray(a, np.int32) for a in (idx1, dist1, idx2, dist2))
+        cap = max(1, min(len(ll), len(lr), len(cl)))
+        o = [np.zeros((cap, 2), np.float32) for _ in range(3)]
+        n = C.c_int()
+        self._check(self._L.svo_orb_match_filter(self._h, _p(ll), len(ll), _p(lr), len(lr), _p(cl), len(cl), _p(i1), _p(d1), _p(i2), _p(d2),
+                                                 C.c_double(fme), _p(o[0]), _p(o[1]), _p(o[2]), cap, C.byref(n)))
+        return tuple(a[:n.value].copy() for a in o)
+
+    def lk_chain_filter(self, p0, p1, p2, p3, p0r, s0, s1, s2, s3, fme=3.0):
+        """-> the five compacted point lists"""
+        pts = [np.ascontiguousarray(a, np.float32).reshape(-1, 2).copy() for a in (p0, p1, p2, p3, p0r)]
+        st = [np.ascontiguousarray(a, np.uint8).ravel() for a in (s0, s1, s2, s3)]
+        n = C.c_int()
+        self._check(self._L.svo_lk_chain_filter(self._h, len(pts[0]), *[_p(a) for a in pts], *[_p(a) for a in st], C.c_double(fme), C.byref(n)))
+        return tuple(a[:n.value] for a in pts)
 
     # ---- throughput mode
     def frontend_configure(self, w, h, mode, max_frames):

@@ -127,24 +127,36 @@ int Tracking::ORB_Robust_Find_MuliImage_MatchedFeatures(std::vector<cv::Point2f>
     std::vector<cv::DMatch>& match2 = last_match2_;
     bf_match(c, last_frame_->left_Descriptors_, last_frame_->right_Descriptors_, match1);
     bf_match(c, last_frame_->left_Descriptors_, current_frame_->left_Descriptors_, match2);
-    const int des_index =
-        std::min(std::min(last_frame_->left_Descriptors_.rows, last_frame_->right_Descriptors_.rows), current_frame_->left_Descriptors_.rows);
-    if ((int)match1.size() < des_index || (int)match2.size() < des_index) return 0;
-    double min_dist = 10000, max_dist = 0;
-    for (int i = 0; i < des_index; i++) {
-        double dist = std::max(match1[i].distance, match2[i].distance);
-        if (dist < min_dist) min_dist = dist;
-        if (dist > max_dist) max_dist = dist;
+    // the association filter (tracking.cpp:546-577) runs on the device: the same kernel (K10) as in the throughput mode
+    auto kps_of = [](const std::vector<Feature::Ptr>& f) {
+        std::vector<cv::KeyPoint> k;
+        k.reserve(f.size());
+        for (const auto& p : f) k.push_back(p->position_);
+        return k;
+    };
+    const std::vector<cv::KeyPoint> kll = kps_of(last_frame_->features_left_), klr = kps_of(last_frame_->features_right_),
+                                    kcl = kps_of(current_frame_->features_left_);
+    const int nq = std::min((int)match1.size(), (int)match2.size());
+    std::vector<int32_t> i1((size_t)nq), d1((size_t)nq), i2((size_t)nq), d2((size_t)nq);
+    for (int i = 0; i < nq; ++i) {
+        i1[i] = match1[i].trainIdx;
+        d1[i] = (int32_t)match1[i].distance;
+        i2[i] = match2[i].trainIdx;
+        d2[i] = (int32_t)match2[i].distance;
     }
-    for (int i = 0; i < des_index; i++) {
-        if ((match1[i].distance <= std::max(2 * min_dist, 30.0)) && (match2[i].distance <= std::max(2 * min_dist, 30.0)) &&
-            (std::abs((last_frame_->features_left_[match1[i].queryIdx]->position_.pt.y) -
-                      (last_frame_->features_right_[match1[i].trainIdx]->position_.pt.y)) < feature_match_error_)) {
-            points_t2_left.push_back((current_frame_->features_left_)[match2[i].trainIdx]->position_.pt);
-            points_t1_left.push_back((last_frame_->features_left_)[match1[i].queryIdx]->position_.pt);
-            points_t1_right.push_back((last_frame_->features_right_)[match1[i].trainIdx]->position_.pt);
-        }
-    }
+    // queries beyond the matches' length cannot be filtered (an empty train set yields no matches): same early-out as the batch path
+    const int n_ll = std::min((int)kll.size(), nq);
+    const int cap = std::max(1, n_ll);
+    std::vector<cv::Point2f> t2((size_t)cap), t1l((size_t)cap), t1r((size_t)cap);
+    int n = 0;
+    if (svo_orb_match_filter(c, reinterpret_cast<const svo_keypoint*>(kll.data()), n_ll, reinterpret_cast<const svo_keypoint*>(klr.data()), (int)klr.size(),
+                             reinterpret_cast<const svo_keypoint*>(kcl.data()), (int)kcl.size(), i1.data(), d1.data(), i2.data(), d2.data(),
+                             feature_match_error_, reinterpret_cast<float*>(t2.data()), reinterpret_cast<float*>(t1l.data()),
+                             reinterpret_cast<float*>(t1r.data()), cap, &n) != SVO_OK)
+        throw std::runtime_error(std::string("svo_orb_match_filter: ") + svo_last_error(c));
+    points_t2_left.insert(points_t2_left.end(), t2.begin(), t2.begin() + n);
+    points_t1_left.insert(points_t1_left.end(), t1l.begin(), t1l.begin() + n);
+    points_t1_right.insert(points_t1_right.end(), t1r.begin(), t1r.begin() + n);
     return (int)points_t2_left.size();
 }
 
@@ -178,28 +190,25 @@ void Tracking::deleteBadmatchFeatures(std::vector<cv::Point2f>& points0, std::ve
                                       std::vector<cv::Point2f>& points3, std::vector<cv::Point2f>& points0_return,
                                       std::vector<unsigned char>& status0, std::vector<unsigned char>& status1,
                                       std::vector<unsigned char>& status2, std::vector<unsigned char>& status3) {
-    // tracking.cpp:623-660.  Same keep/drop rule; the reference erases in place (O(n^2)), here survivors are compacted.
-    size_t w = 0;
-    for (size_t i = 0; i < status3.size(); i++) {
-        const cv::Point2f pt0 = points0[i], pt1 = points1[i], pt2 = points2[i], pt3 = points3[i], pt0_r = points0_return[i];
-        const bool outsideframe = (pt3.x < 0) || (pt3.y < 0) || (pt2.x < 0) || (pt2.y < 0) || (pt1.x < 0) || (pt1.y < 0) || (pt0.x < 0) ||
-                                  (pt0.y < 0) || (pt0_r.x < 0) || (pt0_r.y < 0);
-        const bool badstatus = (status2[i] == 0) || (status1[i] == 0) || (status0[i] == 0) || (status3[i] == 0);
-        const bool NoStereoEpipolarConstrain =
-            (std::abs(pt0.y - pt1.y) > feature_match_error_) || (std::abs(pt2.y - pt3.y) > feature_match_error_);
-        if (outsideframe || badstatus || NoStereoEpipolarConstrain) continue;
-        points0[w] = pt0;
-        points1[w] = pt1;
-        points2[w] = pt2;
-        points3[w] = pt3;
-        points0_return[w] = pt0_r;
-        ++w;
-    }
-    points0.resize(w);
-    points1.resize(w);
-    points2.resize(w);
-    points3.resize(w);
-    points0_return.resize(w);
+    // tracking.cpp:623-660 on the device: the same kernel (K11) as in the throughput mode; the five lists are compacted in place
+    const size_t n = status3.size();
+    if (n == 0) return;
+    if (points0.size() < n || points1.size() < n || points2.size() < n || points3.size() < n || points0_return.size() < n || status0.size() < n ||
+        status1.size() < n || status2.size() < n)
+        throw std::runtime_error("deleteBadmatchFeatures: lists shorter than status3");
+    if (!current_frame_) throw std::runtime_error("deleteBadmatchFeatures: no current frame");
+    svo_ctx* c = mpORBextractorLeft_->context(current_frame_->left_img_.cols, current_frame_->left_img_.rows);
+    int kept = 0;
+    if (svo_lk_chain_filter(c, (int)n, reinterpret_cast<float*>(points0.data()), reinterpret_cast<float*>(points1.data()),
+                            reinterpret_cast<float*>(points2.data()), reinterpret_cast<float*>(points3.data()),
+                            reinterpret_cast<float*>(points0_return.data()), status0.data(), status1.data(), status2.data(), status3.data(),
+                            feature_match_error_, &kept) != SVO_OK)
+        throw std::runtime_error(std::string("svo_lk_chain_filter: ") + svo_last_error(c));
+    points0.resize((size_t)kept);
+    points1.resize((size_t)kept);
+    points2.resize((size_t)kept);
+    points3.resize((size_t)kept);
+    points0_return.resize((size_t)kept);
 }
 
 }  // namespace lzb_vio

@@ -234,3 +234,44 @@ def test_frame_source_feeds_the_frontend(pkg, tmp_path):
     assert i == len(ref)
     src.close()
     ctx.close()
+
+
+def test_standalone_device_filters_equal_oracle(pkg, orc):
+    """svo_orb_match_filter / svo_lk_chain_filter (K10 / K11 on caller arrays; what the drop-in Tracking class calls) against the
+    oracle's restatements of tracking.cpp:546-577 and :623-660."""
+    w, h = 640, 200
+    l0, r0 = pkg.synth_stereo_frame(55, 2, w, h)
+    l1, r1 = pkg.synth_stereo_frame(55, 3, w, h)
+    ctx = pkg.Context(0, w, h, 2)
+    ctx.orb_configure(500, 1.2, 8, 20, 7)
+    ks, ds = ctx.orb_extract_batch([l0, r0])
+    kl0, kr0, dl0, dr0 = ks[0], ks[1], ds[0], ds[1]
+    ks, ds = ctx.orb_extract_batch([l1, r1])
+    kl1, dl1 = ks[0], ds[0]
+    i1, d1 = ctx.match_hamming(dl0, dr0)
+    i2, d2 = ctx.match_hamming(dl0, dl1)
+    for fme in (3.0, 0.5):
+        acc = orc.orb_match_filter(i1, d1, i2, d2, len(kr0), len(kl1), kl0, kr0, fme)
+        t2, t1l, t1r = ctx.orb_match_filter(kl0, kr0, kl1, i1, d1, i2, d2, fme)
+        assert len(t2) == len(acc) and len(acc) > (20 if fme > 1 else 0)
+        xy = lambda k: np.stack([k["x"], k["y"]], 1)
+        assert np.array_equal(t1l, xy(kl0)[acc[:, 0]]) and np.array_equal(t1r, xy(kr0)[acc[:, 1]]) and np.array_equal(t2, xy(kl1)[acc[:, 2]])
+    # quirk Q3: fewer current keypoints than queries -> only the first des_index queries are considered
+    m = 40
+    t2, _, _ = ctx.orb_match_filter(kl0, kr0, kl1[:m], i1, d1, np.minimum(i2, m - 1), d2, 3.0)
+    acc = orc.orb_match_filter(i1, d1, np.minimum(i2, m - 1), d2, len(kr0), m, kl0, kr0, 3.0)
+    assert len(t2) == len(acc) and (len(acc) == 0 or acc[:, 0].max() < m)
+    # LK chain filter
+    seeds = orc.fast9(l0, 20)
+    p0 = np.stack([seeds["x"], seeds["y"]], 1)
+    p1, s1, _ = ctx.lk_track(l0, r0, p0)
+    p2, s2, _ = ctx.lk_track(r0, r1, p1)
+    p3, s3, _ = ctx.lk_track(r1, l1, p2)
+    p0r, s4, _ = ctx.lk_track(l1, l0, p3)
+    p2[5] = (-1.0, 4.0)  # a negative coordinate drops the track
+    keep = orc.lk_chain_filter(p0, p1, p2, p3, p0r, s1, s2, s3, s4, 3.0)
+    out = ctx.lk_chain_filter(p0, p1, p2, p3, p0r, s1, s2, s3, s4, 3.0)
+    assert len(out[0]) == keep.sum() and 0 < keep.sum() < len(p0) and not keep[5]
+    for g, o in zip(out, (p0, p1, p2, p3, p0r)):
+        assert np.array_equal(g, o[keep])
+    ctx.close()
