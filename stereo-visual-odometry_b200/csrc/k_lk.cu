@@ -356,10 +356,9 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             const uint8_t* tp = tile + pair_off(ccol);
             int p0 = tb[0], p1 = tb[row_off(1)];
             int top = 0, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;
-#pragma unroll
-            for (int r = 0; r < 22; ++r) {
-                const int p2 = tb[row_off(r + 2)];
-                // Scharr gradient at (X, Y = ipy + r) (tile row r + 1)
+            // one row of the general form: the Scharr gradient at (X, Y = ipy + r) (tile row r + 1) from tile rows r .. r + 2, and -- for
+            // r >= 1 -- the template entry of window row r - 1 from the gradients / pixels of rows r - 1 and r
+            auto grow = [&](int r, int p2, uint32_t pr, uint2* trow) {
                 const int V = 3 * (p0 + p2) + 10 * p1, Dv = p2 - p0;
                 const int Vl = __shfl_up_sync(0xFFFFFFFFu, V, 1), Vr = __shfl_down_sync(0xFFFFFFFFu, V, 1);
                 const int Dl = __shfl_up_sync(0xFFFFFFFFu, Dv, 1), Dr = __shfl_down_sync(0xFFFFFFFFu, Dv, 1);
@@ -368,12 +367,11 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 const int gx = in ? Vr - Vl : 0;
                 const int gy = in ? 3 * (Dl + Dr) + 10 * Dv : 0;
                 const int gxn = __shfl_down_sync(0xFFFFFFFFu, gx, 1), gyn = __shfl_down_sync(0xFFFFFFFFu, gy, 1);
-                const uint32_t pr = lds_u16(tp + row_off(r + 1));
-                if (r >= 1) {
+                if (trow) {
                     const int iv = (dp2(Wbot, pr, top) + 256) >> 9;
                     const int ixv = descale(tgx * iw00 + tgxn * iw01 + gx * iw10 + gxn * iw11, 14);
                     const int iyv = descale(tgy * iw00 + tgyn * iw01 + gy * iw10 + gyn * iw11, 14);
-                    if (wlane) tmpl[tbase[(r - 1) / SEG] + ((r - 1) % SEG) * 32] = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
+                    if (wlane) *trow = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
@@ -382,6 +380,18 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 tgx = gx; tgxn = gxn; tgy = gy; tgyn = gyn;
                 p0 = p1;
                 p1 = p2;
+            };
+            grow(0, tb[row_off(2)], lds_u16(tp + row_off(1)), nullptr);
+            // rows 1 .. 21 = three segments of 7: the segment loop stays rolled (this form runs for ~1 setup in 5; unrolling all 22
+            // rows made the kernel's executed code outgrow the instruction cache once the err pass ran too)
+#pragma unroll 1
+            for (int sg = 0; sg < 3; ++sg) {
+                const uint8_t* tbs = tb + sg * (row_off(SEG) - row_off(0));
+                const uint8_t* tps = tp + sg * (row_off(SEG) - row_off(0));
+                const int g = 3 * (lane - 1) + sg;
+                uint2* trow = tmpl + (g >> 5) * SEG * 32 + (g & 31);
+#pragma unroll
+                for (int jj = 0; jj < SEG; ++jj) grow(1 + SEG * sg + jj, tbs[row_off(3 + jj)], lds_u16(tps + row_off(2 + jj)), trow + jj * 32);
             }
         }
         const long long sA11 = warp_sum64(wlane ? a11 : 0), sA12 = warp_sum64(wlane ? a12 : 0), sA22 = warp_sum64(wlane ? a22 : 0);
@@ -470,19 +480,21 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                     __syncwarp();
                 }
                 int e = 0;
-#pragma unroll
+#pragma unroll 1  // (rolled: the err pass runs once per call; its code must stay small)
                 for (int sr = 0; sr < NROUND; ++sr) {
-                    const uint8_t* tp = tile + offJ[sr];
+                    const uint8_t* tp = tile + (sr ? offJ[1] : offJ[0]);
+                    const uint2* tls = tl + sr * SEG * 32;
                     uint32_t pa = lds_u16(tp);
+                    int es = 0;
 #pragma unroll
                     for (int j = 0; j < SEG; ++j) {
                         const uint32_t pb = lds_u16(tp + (row_off(j + 1) - row_off(0)));
-                        const int diff = dp2(Wbot, pb, dp2(Wtop, pa, (int)tl[(sr * SEG + j) * 32].x)) >> 9;
-                        if (lane + 32 * sr < 63) e += abs(diff);
+                        es += abs(dp2(Wbot, pb, dp2(Wtop, pa, (int)tls[j * 32].x)) >> 9);
                         pa = pb;
                     }
+                    if (lane + 32 * sr < 63) e += es;
                 }
-                const long long se = warp_sum64(e);
+                const int se = __reduce_add_sync(0xFFFFFFFFu, e);  // <= 441 * 255
                 err = __fdiv_rn((float)se, (float)(32 * WIN * WIN));
             }
         }
