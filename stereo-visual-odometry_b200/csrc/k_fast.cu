@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastT
     const FastLevel fl = P.lv[t.level];
     uint8_t* pix = smem;
     uint8_t* sc = smem + P.sc_off;
-    uint32_t* hit = reinterpret_cast<uint32_t*>(smem + P.hit_off);  // [row][MC4] 64-bit
+    uint32_t* hit = reinterpret_cast<uint32_t*>(smem + P.hit_off);  // [row][MC4] 64-bit; aliases the queues (dead once the scores exist)
     uint16_t* queues = reinterpret_cast<uint16_t*>(smem + P.q_off);
     int* ctl = reinterpret_cast<int*>(smem + P.ctl_off);  // [0] pooled leftovers, [1..8] queue fills, [16..23] cell totals
     uint16_t* tail = reinterpret_cast<uint16_t*>(smem + P.tail_off);
@@ -499,6 +499,10 @@ __global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastT
             any_strong |= __ballot_sync(0xFFFFFFFFu, strong);
         }
         const int need = any_strong ? 0xC000 : 0x4000;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)  // this cell's column of the survivor map (the queues' memory: nobody reads them any more)
+            if (32 * ch + lane < th) *reinterpret_cast<unsigned long long*>(hit + (((32 * ch + lane) * MC4 + cidx) << 1)) = 0ull;
+        __syncwarp();
         for (int i = lane; i < n; i += 32) {
             const int e = cl[i];
             if ((e & need) == need) {
@@ -831,9 +835,9 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
             P.minTh = g.minTh;
             P.iniTh = g.iniTh;
             P.sc_off = (int)svo_align((size_t)PW4 * PH, 128);
-            P.hit_off = P.sc_off + PW4 * (TH + 2);
-            P.ctl_off = P.hit_off + TH * MC4 * 8;
+            P.ctl_off = P.sc_off + PW4 * (TH + 2);
             P.q_off = P.ctl_off + 32 * (int)sizeof(int);
+            P.hit_off = P.q_off;  // the survivor map reuses the queues' memory after the score stage (TH * 64 <= FW * QCAP4 * 2 bytes)
             P.zero16 = (P.q_off - P.sc_off) / 16;
             P.tail_off = P.q_off + FW * QCAP4 * 2;
             P.cl_off = P.tail_off + FT * 2;
