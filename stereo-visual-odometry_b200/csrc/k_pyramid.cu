@@ -141,11 +141,10 @@ __global__ void __launch_bounds__(256) k_repitch(const uint8_t* __restrict__ lef
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256, 5) k_pyramid_fused(const __grid_constant__ CUtensorMap tmap, PyrGeom g, SlotMap map,
+__global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ CUtensorMap tmap, PyrGeom g, SlotMap map,
                                                        const PyrTile* __restrict__ tiles, int bufB_off) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long mbar;
-    __shared__ __align__(16) PyrTile sT;  // the tile's rectangles and thread layouts: read once, not once per level from L2
     const int slot = map.slot(blockIdx.y);
     const PyrTile& T = tiles[blockIdx.x];
     uint8_t* bufA = smem;             // level-0 box (SVO_PYR_BOX_H x SVO_PYR_BOX_W), later the even levels
@@ -156,39 +155,14 @@ __global__ void __launch_bounds__(256, 5) k_pyramid_fused(const __grid_constant_
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(SVO_PYR_BOX_W * SVO_PYR_BOX_H) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(bufA)),
                      "l"(&tmap), "r"((int)r0.x0 & ~15), "r"(slot * g.lvl[0].h + (int)r0.y0), "r"(smem_u32(&mbar))
                      : "memory");
     }
-    static_assert(sizeof(PyrTile) % 4 == 0 && sizeof(PyrTile) / 4 <= 256, "PyrTile is copied by one word per thread");
-    if (threadIdx.x < sizeof(PyrTile) / 4) reinterpret_cast<uint32_t*>(&sT)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(&T) + threadIdx.x);
-    __syncthreads();  // the mbarrier is initialised for everybody, the tile descriptor is in shared memory
-
-    // thread layout and column coefficients of a level: (row lane, 4-pixel group), the group's table entry (2 x 16 bytes).  Level
-    // l + 1's are fetched while level l is computed, so that no level starts with a dependent chain of L2 round trips.
-    struct Cols {
-        int rl, gi;
-        int4 m0, m1;
-    };
-    auto fetch_cols = [&](int l) {
-        Cols c;
-        c.rl = 0;
-        c.gi = 0;
-        c.m0 = c.m1 = make_int4(0, 0, 0, 0);
-        if (l >= g.nlevels) return c;
-        const PyrRect& r = sT.lv[l];
-        if (r.ng <= 0) return c;
-        c.rl = ((int)threadIdx.x * r.magic) >> 16;
-        c.gi = (int)threadIdx.x - c.rl * r.ng;
-        if (c.rl < r.nrl) {
-            const int gx = (r.x0 & ~3) + 4 * c.gi;
-            c.m0 = __ldg(g.lvl[l].xmeta + (gx >> 1));
-            c.m1 = __ldg(g.lvl[l].xmeta + (gx >> 1) + 1);
-        }
-        return c;
-    };
-    Cols cols = fetch_cols(1);
     {  // every thread waits for the TMA bytes (phase 0)
         uint32_t done = 0;
         while (!done) {
@@ -200,15 +174,14 @@ __global__ void __launch_bounds__(256, 5) k_pyramid_fused(const __grid_constant_
     int s_orgx = r0.x0 & ~15, s_orgy = r0.y0, s_pitch = SVO_PYR_BOX_W;  // the box starts at a 16-byte aligned column
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& D = g.lvl[l];
-        const PyrRect r = sT.lv[l];
+        const PyrRect r = T.lv[l];
         if (r.ng <= 0) break;  // deeper levels of this tile are empty too (CTA-uniform)
         uint8_t* dbuf = (l & 1) ? bufB : bufA;
         const int d_orgx = (r.x0 & ~3) - 4;  // level x of byte 0 of a buffer row (one group of front margin)
-        const int rl = cols.rl, gi = cols.gi;  // row lane, 4-pixel group
-        const int4 m0 = cols.m0, m1 = cols.m1;
-        cols = fetch_cols(l + 1);
+        const int rl = ((int)threadIdx.x * r.magic) >> 16, gi = (int)threadIdx.x - rl * r.ng;  // row lane, 4-pixel group
         if (rl < r.nrl) {
             const int gx = d_orgx + 4 + 4 * gi;  // level x of the group's first pixel
+            const int4 m0 = __ldg(D.xmeta + (gx >> 1)), m1 = __ldg(D.xmeta + (gx >> 1) + 1);
             const int rel0 = m0.x - s_orgx;  // >= 0 (host-checked): source byte of pixel 0's left tap in the buffer row
             const unsigned woff = (unsigned)rel0 & ~3u, sh0 = ((unsigned)rel0 & 3u) * 8u;
             const uint32_t sel1 = (uint32_t)m0.y, sel2 = sel1 >> 8, sel3 = sel1 >> 16;
