@@ -151,7 +151,9 @@ def run_b200(a):
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, in front of the one JSON line
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))  # barrier / max-reduce / signature gather only
     torch.cuda.set_device(local)
     w, h, B, K, W = a.width, a.height, a.frames, a.steps, a.warmup
     strong = a.cfg["scaling"] == "strong"
