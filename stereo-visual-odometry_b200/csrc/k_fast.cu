@@ -561,24 +561,23 @@ __global__ void __launch_bounds__(FT) k_fast_cells(const __grid_constant__ FastT
     }
 }
 
-// K2b: one CTA per (level, image): exclusive scan of the level's tile counts, gather into the candidate array.
-__global__ void __launch_bounds__(128) k_compact(PyrGeom g, SlotMap map, const FastTile* __restrict__ tiles,
-                                                 const uint32_t* __restrict__ tile_buf, const int* __restrict__ tile_cnt,
-                                                 uint32_t* __restrict__ cand, int* __restrict__ ncand, int* __restrict__ flags,
-                                                 uint32_t tile_buf_per_slot, uint32_t cand_per_slot, int n_tiles) {
-    __shared__ int off[129];
-    __shared__ int wsum[4];
+// K2b, two launches (one CTA per (level, image) doing both was 3 % of a 4K step: at 8 frames it is 128 CTAs walking ~100 k candidates each):
+//   k_compact_scan    one CTA per (level, image): exclusive scan of the level's tile counts -> tile_pos[], ncand, overflow flag
+//   k_compact_gather  one CTA per (tile, image): copies the tile's list to its position in the level's candidate array
+__global__ void __launch_bounds__(256) k_compact_scan(PyrGeom g, SlotMap map, const int* __restrict__ tile_cnt, int* __restrict__ tile_pos,
+                                                      int* __restrict__ ncand, int* __restrict__ flags, int n_tiles) {
+    __shared__ int wsum[8];
     __shared__ int running;
     const int l = blockIdx.x, slot = map.slot(blockIdx.y);
     const LevelGeom& G = g.lvl[l];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();
-    uint32_t* dst = cand + (size_t)slot * cand_per_slot + G.cand_off;
-    const uint32_t* src = tile_buf + (size_t)slot * tile_buf_per_slot;
-    for (int t0 = 0; t0 < G.tile_count; t0 += 128) {
+    const int* cnt = tile_cnt + (size_t)slot * n_tiles + G.tile_begin;
+    int* pos = tile_pos + (size_t)slot * n_tiles + G.tile_begin;
+    for (int t0 = 0; t0 < G.tile_count; t0 += 256) {
         const int ti = t0 + threadIdx.x;
-        const int v = ti < G.tile_count ? tile_cnt[(size_t)slot * n_tiles + G.tile_begin + ti] : 0;
+        const int v = ti < G.tile_count ? cnt[ti] : 0;
         int incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -587,29 +586,38 @@ __global__ void __launch_bounds__(128) k_compact(PyrGeom g, SlotMap map, const F
         }
         if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += wsum[w];
-        off[threadIdx.x] = wbase + incl - v;
-        if (threadIdx.x == 127) off[128] = wbase + incl;
-        __syncthreads();
-        const int chunk_total = off[128], base = running;
-        for (int e = threadIdx.x; e < chunk_total; e += 128) {
-            int lo = 0, hi = 127;  // last tile with off <= e
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (off[mid] <= e) lo = mid; else hi = mid - 1;
-            }
-            const int o = base + e;
-            if (o < G.cand_cap) dst[o] = src[tiles[G.tile_begin + t0 + lo].out_off + (e - off[lo])];
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int x = wsum[w];
+            if (w < warp) wbase += x;
+            total += x;
         }
+        const int base = running;
+        if (ti < G.tile_count) pos[ti] = base + wbase + incl - v;
         __syncthreads();
-        if (threadIdx.x == 0) running = base + chunk_total;
+        if (threadIdx.x == 0) running = base + total;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         ncand[slot * SVO_MAX_LEVELS + l] = min(running, G.cand_cap);
         if (running > G.cand_cap) atomicOr(flags + slot, SVO_FLAG_CAND_OVERFLOW);
     }
+}
+
+__global__ void __launch_bounds__(64) k_compact_gather(PyrGeom g, SlotMap map, const FastTile* __restrict__ tiles, const uint32_t* __restrict__ tile_buf,
+                                                       const int* __restrict__ tile_cnt, const int* __restrict__ tile_pos, uint32_t* __restrict__ cand,
+                                                       uint32_t tile_buf_per_slot, uint32_t cand_per_slot, int n_tiles) {
+    const int slot = map.slot(blockIdx.y);
+    const int n = tile_cnt[(size_t)slot * n_tiles + blockIdx.x];
+    if (n == 0) return;
+    const FastTile t = tiles[blockIdx.x];
+    const LevelGeom& G = g.lvl[t.level];
+    const int p0 = tile_pos[(size_t)slot * n_tiles + blockIdx.x];
+    const uint32_t* src = tile_buf + (size_t)slot * tile_buf_per_slot + t.out_off;
+    uint32_t* dst = cand + (size_t)slot * cand_per_slot + G.cand_off;
+    for (int e = threadIdx.x; e < n; e += 64)
+        if (p0 + e < G.cand_cap) dst[p0 + e] = src[e];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -854,10 +862,12 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img) {
     }
     {
         StageTimer t(c, 2);
-        dim3 grid(g.nlevels, n_img);
-        k_compact<<<grid, 128, 0, c->stream>>>(g, map, c->d_tiles, c->d_tile_buf, c->d_tile_cnt, c->d_cand, c->d_ncand, c->d_flags,
-                                               c->tile_buf_per_slot, c->cand_per_slot, c->n_tiles);
-        ++c->launches;
+        if (c->n_tiles > 0) {
+            k_compact_scan<<<dim3(g.nlevels, n_img), 256, 0, c->stream>>>(g, map, c->d_tile_cnt, c->d_tile_pos, c->d_ncand, c->d_flags, c->n_tiles);
+            k_compact_gather<<<dim3(c->n_tiles, n_img), 64, 0, c->stream>>>(g, map, c->d_tiles, c->d_tile_buf, c->d_tile_cnt, c->d_tile_pos, c->d_cand,
+                                                                            c->tile_buf_per_slot, c->cand_per_slot, c->n_tiles);
+            c->launches += 2;
+        }
     }
     SVO_CUDA_TRY(c, cudaGetLastError());
     return SVO_OK;

@@ -159,6 +159,7 @@ struct svo_ctx {
     void* d_tables = nullptr;  // resize tables
     uint32_t* d_tile_buf = nullptr;
     int* d_tile_cnt = nullptr;
+    int* d_tile_pos = nullptr;  // position of every tile's list in its level's candidate array (k_compact_scan)
     uint32_t* d_cand = nullptr;
     int* d_ncand = nullptr;     // slot * SVO_MAX_LEVELS + l
     uint16_t* d_knode = nullptr;  // octree scratch, same shape as cand

@@ -55,7 +55,7 @@ static void free_layout(svo_ctx* c) {
                      (void**)&c->d_ftile_buf, (void**)&c->d_ftile_cnt, (void**)&c->d_fast_kps, (void**)&c->d_nfast,
                      (void**)&c->d_lk_pts,   (void**)&c->d_lk_status, (void**)&c->d_lk_err,   (void**)&c->d_match,
                      (void**)&c->d_orb_pts,  (void**)&c->d_norb,      (void**)&c->d_lkf_pts,  (void**)&c->d_nlkf,
-                     (void**)&c->d_ptiles,   (void**)&c->d_orb_xyz,   (void**)&c->d_lkf_xyz};
+                     (void**)&c->d_ptiles,   (void**)&c->d_orb_xyz,   (void**)&c->d_lkf_xyz,   (void**)&c->d_tile_pos};
     for (void** p : ptrs) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -602,6 +602,7 @@ int svo_layout(svo_ctx* c, int w, int h) {
     }
     SVO_CUDA_TRY(c, cudaMalloc(&c->d_tile_buf, sizeof(uint32_t) * std::max<size_t>(1, (size_t)c->tile_buf_per_slot * S)));
     SVO_CUDA_TRY(c, cudaMalloc(&c->d_tile_cnt, sizeof(int) * std::max<size_t>(1, (size_t)c->n_tiles * S)));
+    SVO_CUDA_TRY(c, cudaMalloc(&c->d_tile_pos, sizeof(int) * std::max<size_t>(1, (size_t)c->n_tiles * S)));
     SVO_CUDA_TRY(c, cudaMalloc(&c->d_cand, sizeof(uint32_t) * std::max<size_t>(1, (size_t)c->cand_per_slot * S)));
     SVO_CUDA_TRY(c, cudaMalloc(&c->d_knode, sizeof(uint16_t) * std::max<size_t>(1, (size_t)c->cand_per_slot * S)));
     SVO_CUDA_TRY(c, cudaMalloc(&c->d_ncand, sizeof(int) * SVO_MAX_LEVELS * S));
