@@ -206,6 +206,8 @@ int svo_frontend_set_lk_err(svo_ctx* ctx, int enable);
 int svo_frontend_set_projection(svo_ctx* ctx, const double* proj_left, const double* proj_right);
 /* host images -> device (left/right: n_frames contiguous images of h rows, `stride` bytes per row) */
 int svo_frontend_upload(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride);
+/* blocks until the host-to-device copies of the last svo_frontend_upload() have completed (the host buffers may be reused) */
+int svo_frontend_wait_upload(svo_ctx* ctx);
 /* same, but left/right are DEVICE pointers (images already resident in HBM, e.g. written by a decoder or a torch tensor) */
 int svo_frontend_upload_dev(svo_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, int n_frames, size_t stride);
 /* all kernels for the uploaded frames; inputs and outputs stay in HBM */
@@ -231,7 +233,7 @@ int svo_frontend_batch(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, 
 /* Reads <dir>/image_0/%06d.png (left) and <dir>/image_1/%06d.png (right) from index first_index on, like the reference's
  * cv::imread(..., IMREAD_GRAYSCALE); the run ends at the first missing pair (the reference returns a null frame there).
  * 8-bit greyscale non-interlaced PNG (the KITTI odometry grey sequences) and binary PGM (%06d.pgm) are decoded; any other
- * format or a size other than w x h is an error.  `threads` decoder threads fill a ring of `ring_batches` (>= 2) batches of
+ * format or a size other than w x h is an error.  `threads` decoder threads fill a ring of `ring_batches` (>= 3) batches of
  * `batch` frames in PINNED host memory ahead of the consumer. */
 typedef struct svo_source svo_source;
 int svo_source_open(svo_source** src, const char* dir, int first_index, int w, int h, int batch, int ring_batches, int threads);
@@ -239,8 +241,10 @@ int svo_source_open(svo_source** src, const char* dir, int first_index, int w, i
 int svo_source_frame_count(const svo_source* src);
 /* 1 if the ring is pinned (page-locked) memory; 0 on a host without a CUDA device (ordinary memory: decoder tests / tools). */
 int svo_source_is_pinned(const svo_source* src);
-/* Next batch in sequence order: *left / *right point at *n_frames contiguous w x h images (stride w), valid until the next call
- * (pass them to svo_frontend_upload and call svo_frontend_run before asking for the next batch).  *n_frames == 0: end of the run.
+/* Next batch in sequence order: *left / *right point at *n_frames contiguous w x h images (stride w).  A batch stays valid until
+ * the SECOND following call: svo_frontend_upload() copies asynchronously, so the batch must outlive the request for the next one;
+ * a caller that has downloaded (or svo_frontend_wait_upload-ed) batch k before it asks for batch k + 2 is safe -- the pipelined
+ * loop upload(k+1), run(k+1), download(k), next() is.  *n_frames == 0: end of the run.
  * Blocks until the batch is decoded.  SVO_ERR_INVALID on a decode error (svo_source_error). */
 int svo_source_next(svo_source* src, const uint8_t** left, const uint8_t** right, int* n_frames);
 const char* svo_source_error(const svo_source* src);

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "svo_orb_capacity", "svo_orb_level_size", "svo_orb_extract", "svo_orb_extract_batch", "svo_orb_read_level",
     "svo_orb_read_candidates", "svo_fast_detect", "svo_match_hamming", "svo_lk_track", "svo_frontend_configure",
     "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_overlap", "svo_frontend_set_lk_err", "svo_frontend_set_projection",
-    "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_check",
+    "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_wait_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_check",
     "svo_frontend_discard", "svo_frontend_batch", "svo_source_open", "svo_source_frame_count", "svo_source_is_pinned", "svo_source_next",
     "svo_source_error", "svo_source_close", "svo_write_pgm", "svo_write_png", "svo_orb_match_filter", "svo_lk_chain_filter",
 ]
@@ -391,6 +391,9 @@ class Context:
     def frontend_upload_ptr(self, left_ptr, right_ptr, n_frames, stride):
         self._check(self._L.svo_frontend_upload(self._h, C.c_void_p(left_ptr), C.c_void_p(right_ptr), n_frames, C.c_size_t(stride)))
         self._n_frames = n_frames
+
+    def frontend_wait_upload(self):
+        self._check(self._L.svo_frontend_wait_upload(self._h))
 
     def frontend_upload_dev(self, left_ptr, right_ptr, n_frames, stride):
         """left_ptr / right_ptr: device addresses of n_frames contiguous images (rows of `stride` bytes)."""

@@ -290,6 +290,14 @@ extern "C" int svo_frontend_upload(svo_ctx* c, const uint8_t* left, const uint8_
     return frontend_upload_impl(c, left, right, n_frames, stride, cudaMemcpyHostToDevice);
 }
 
+extern "C" int svo_frontend_wait_upload(svo_ctx* c) {
+    if (!c) return SVO_ERR_INVALID;
+    if (!c->fe_configured || !c->copy_stream) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure() first");
+    cudaSetDevice(c->device);
+    SVO_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    return SVO_OK;
+}
+
 extern "C" int svo_frontend_upload_dev(svo_ctx* c, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride) {
     return frontend_upload_impl(c, left, right, n_frames, stride, cudaMemcpyDeviceToDevice);
 }

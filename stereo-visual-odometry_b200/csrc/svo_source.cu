@@ -152,7 +152,7 @@ struct svo_source {
     std::vector<int> slot_batch;  // which batch the slot holds
     int next_job = 0;             // next (frame, side) job to hand to a worker: job = 2 * frame + side
     int consumed_batches = 0;     // batches handed to the consumer so far
-    int held_slot = -1;           // slot lent to the consumer by the last svo_source_next()
+    int held_slot[2] = {-1, -1};  // slots lent to the consumer by the last two svo_source_next() calls ([0] = the older one)
     bool stop = false, failed = false;
     std::atomic<long long> decoded_bytes{0};
 
@@ -206,7 +206,7 @@ struct svo_source {
 extern "C" int svo_source_open(svo_source** out, const char* dir, int first_index, int w, int h, int batch, int ring_batches, int threads) {
     if (!out) return SVO_ERR_INVALID;
     *out = nullptr;
-    if (!dir || first_index < 0 || w <= 0 || h <= 0 || batch < 1 || ring_batches < 2 || threads < 1) return SVO_ERR_INVALID;
+    if (!dir || first_index < 0 || w <= 0 || h <= 0 || batch < 1 || ring_batches < 3 || threads < 1) return SVO_ERR_INVALID;
     svo_source* s = new svo_source();
     s->dir = dir;
     s->first = first_index;
@@ -253,12 +253,15 @@ extern "C" int svo_source_next(svo_source* s, const uint8_t** left, const uint8_
     *left = *right = nullptr;
     *n_frames = 0;
     std::unique_lock<std::mutex> lk(s->mu);
-    if (s->held_slot >= 0) {  // the batch lent by the previous call goes back to the decoders
-        s->remaining[s->held_slot] = -1;
-        s->slot_batch[s->held_slot] = -1;
-        s->held_slot = -1;
+    // A lent batch stays valid for TWO calls: its asynchronous host-to-device copy (svo_frontend_upload) may still be reading it when
+    // the next batch is asked for; one call later the pipelined caller has downloaded that batch's results, so its copy is complete.
+    if (s->held_slot[0] >= 0) {
+        s->remaining[s->held_slot[0]] = -1;
+        s->slot_batch[s->held_slot[0]] = -1;
         s->cv_free.notify_all();
     }
+    s->held_slot[0] = s->held_slot[1];
+    s->held_slot[1] = -1;
     const int b = s->consumed_batches;
     if (b * s->batch >= s->n_total) return s->failed ? SVO_ERR_INVALID : SVO_OK;  // end of the sequence: n_frames = 0
     const int slot = b % s->ring;
@@ -267,7 +270,7 @@ extern "C" int svo_source_next(svo_source* s, const uint8_t** left, const uint8_
     *left = s->slot_ptr(slot, 0);
     *right = s->slot_ptr(slot, 1);
     *n_frames = std::min(s->batch, s->n_total - b * s->batch);
-    s->held_slot = slot;
+    s->held_slot[1] = slot;
     ++s->consumed_batches;
     s->cv_free.notify_all();  // the window of claimable batches moved
     return SVO_OK;

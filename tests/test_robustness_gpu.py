@@ -213,7 +213,7 @@ def test_frame_source_feeds_the_frontend(pkg, tmp_path):
         ctx.frontend_batch(np.ascontiguousarray(left[f0:f0 + n]), np.ascontiguousarray(right[f0:f0 + n]), o)
         ref.append(o)
     ctx.frontend_reset()
-    src = pkg.FrameSource(str(tmp_path), w, h, B, ring_batches=2, threads=3)
+    src = pkg.FrameSource(str(tmp_path), w, h, B, ring_batches=3, threads=3)
     assert src.is_pinned() and src.frame_count() == F
     i = 0
     while True:

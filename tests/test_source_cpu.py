@@ -16,7 +16,7 @@ def test_source_roundtrip_own_writers(pkg, tmp_path, fmt):
     w, h, n, B = 333, 97, 11, 4
     left, right = _seq(pkg, n, w, h)
     pkg.write_sequence(str(tmp_path), left, right, first_index=5, fmt=fmt)
-    src = pkg.FrameSource(str(tmp_path), w, h, B, ring_batches=2, threads=3, first_index=5)
+    src = pkg.FrameSource(str(tmp_path), w, h, B, ring_batches=3, threads=3, first_index=5)
     assert src.frame_count() == n
     got_l, got_r = [], []
     while True:
@@ -64,15 +64,15 @@ def test_source_errors_are_loud(pkg, tmp_path):
     left, right = _seq(pkg, 3, w, h)
     pkg.write_sequence(str(tmp_path), left, right)
     cv2.imwrite(str(tmp_path / "image_0" / "000001.png"), np.zeros((h, w, 3), np.uint8))  # a colour PNG is not silently converted
-    src = pkg.FrameSource(str(tmp_path), w, h, 2, ring_batches=2, threads=2)
+    src = pkg.FrameSource(str(tmp_path), w, h, 2, ring_batches=3, threads=2)
     with pytest.raises(pkg.SvoError) as e:
         while src.next() is not None:
             pass
     assert "greyscale" in str(e.value)
     src.close()
-    src = pkg.FrameSource(str(tmp_path), w + 1, h, 2, ring_batches=2, threads=2)  # wrong size
+    src = pkg.FrameSource(str(tmp_path), w + 1, h, 2, ring_batches=3, threads=2)  # wrong size
     with pytest.raises(pkg.SvoError):
         src.next()
     src.close()
     with pytest.raises(pkg.SvoError):
-        pkg.FrameSource(str(tmp_path), w, h, 2, ring_batches=1, threads=2)  # ring needs >= 2 batches
+        pkg.FrameSource(str(tmp_path), w, h, 2, ring_batches=2, threads=2)  # ring needs >= 3 batches (two stay lent)
