@@ -208,6 +208,12 @@ struct svo_ctx {
 
     // ---- matches (frontend): per frame slot, kp_cap each
     int* d_match = nullptr;  // [frame slot][4][kp_cap]: stereo idx, stereo dist, temporal idx, temporal dist
+    // K6 on the int8 tensor-core path: descriptors expanded to one byte per bit in IMMA fragment order, their popcounts, slot list
+    uint32_t* d_xdesc = nullptr;  // [image slot][kp_cap][64 words]
+    int* d_xpop = nullptr;        // [image slot][kp_cap]
+    int* d_xslots = nullptr;
+    size_t xslots_cap = 0;
+    bool match_mma = true;        // SVO_MATCH_POPC=1 in the environment selects the POPC kernel (A/B measurements)
 
     // ---- frontend state
     int fe_mode = 0, fe_max_frames = 0, fe_ring = 0, fe_head = -1, fe_pending = 0, fe_first = 0;

@@ -73,6 +73,9 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
     if (c->d_pattern) cudaFree(c->d_pattern);
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_flag_accum) cudaFree(c->d_flag_accum);
+    if (c->d_xdesc) cudaFree(c->d_xdesc);
+    if (c->d_xpop) cudaFree(c->d_xpop);
+    if (c->d_xslots) cudaFree(c->d_xslots);
     if (c->d2h_stream) {
         cudaStreamSynchronize(c->d2h_stream);
         cudaStreamDestroy(c->d2h_stream);

@@ -6,6 +6,7 @@
 //                        previous frame (Tracking::last_frame_) carried in a ring of frame slots on the device.
 // No pixel arithmetic happens here; see k_*.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "svo_common.cuh"
@@ -188,9 +189,19 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     c->fe_depth = (2 * (2 * max_frames + 1) <= c->max_images) ? 2 : 1;
     c->fe_ring = c->fe_depth * max_frames + 1;
     if (mode & SVO_MODE_ORB) {
-        if (c->d_match) cudaFree(c->d_match);
-        c->d_match = nullptr;
+        void** ptrs[] = {(void**)&c->d_match, (void**)&c->d_xdesc, (void**)&c->d_xpop, (void**)&c->d_xslots};
+        for (void** p : ptrs) {
+            if (*p) cudaFree(*p);
+            *p = nullptr;
+        }
         SVO_CUDA_TRY(c, cudaMalloc(&c->d_match, sizeof(int) * 4 * (size_t)c->kp_cap * c->fe_ring));
+        c->match_mma = getenv("SVO_MATCH_POPC") == nullptr;
+        if (c->match_mma) {
+            SVO_CUDA_TRY(c, cudaMalloc(&c->d_xdesc, (size_t)256 * c->kp_cap * c->max_images));
+            SVO_CUDA_TRY(c, cudaMalloc(&c->d_xpop, sizeof(int) * (size_t)c->kp_cap * c->max_images));
+            c->xslots_cap = (size_t)2 * max_frames;
+            SVO_CUDA_TRY(c, cudaMalloc(&c->d_xslots, sizeof(int) * c->xslots_cap));
+        }
     }
     if (!c->copy_stream) {
         SVO_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
