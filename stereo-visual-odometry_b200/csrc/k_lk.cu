@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) k_pyr_down(LkLevelGeom S, LkLevelGeom D, 
 
 struct LkParams {
     LkLevelGeom lv[SVO_LK_LEVELS];  // padded planes (REFLECT_101 border of SVO_LK_PADX / SVO_LK_PADY materialised)
+    LkLevelGeom dv[SVO_LK_LEVELS];  // Scharr planes (Ix | Iy << 16 per pixel, 4 bytes; ZERO border: OpenCV's derivI), DERIV form only
     int levels;      // pyramid levels available (maxLevel + 1)
     int first, ring, skip_first;
     LkCall calls[4];  // the chain: the output list of call k is the source list of call k + 1
@@ -152,6 +153,45 @@ __global__ void __launch_bounds__(128) k_lk_pad(LkPadParams P, SlotMap map) {
     }
 }
 
+// K7c: Scharr derivatives of an LK level (cv::calcScharrDeriv as calcOpticalFlowPyrLK runs it per level): Ix | Iy << 16 per pixel.
+//   V = 3 (I(x, y-1) + I(x, y+1)) + 10 I(x, y), W = I(x, y+1) - I(x, y-1);  Ix = V(x+1) - V(x-1),  Iy = 3 (W(x-1) + W(x+1)) + 10 W(x)
+// Taps beyond the image read the REFLECT_101 border of the padded image plane; the derivative plane's own border stays ZERO
+// (OpenCV pads derivI with BORDER_CONSTANT), which is what makes windows across the image border need no special case.
+// One thread = 4 pixels of one row: 9 aligned words in, one 16-byte store out.
+__global__ void __launch_bounds__(256) k_lk_deriv(LkLevelGeom S, LkLevelGeom D, SlotMap map) {
+    const int slot = map.slot(blockIdx.z);
+    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x0 >= S.w || y >= S.h) return;
+    const uint8_t* __restrict__ src = S.base + (size_t)slot * S.plane + (ptrdiff_t)y * S.pitch + x0;  // 4-byte aligned: PADX % 4 == 0
+    int v[6], w[6];  // columns x0 - 1 .. x0 + 4
+    {
+        uint32_t r[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (ptrdiff_t)(k - 1) * S.pitch);
+            r[k][0] = __ldg(p - 1);
+            r[k][1] = __ldg(p);
+            r[k][2] = __ldg(p + 1);
+        }
+        auto px = [&](int k, int c) -> int {  // c = -1 .. 4
+            return c < 0 ? (int)(r[k][0] >> 24) : (c < 4 ? (int)((r[k][1] >> (8 * c)) & 0xFFu) : (int)(r[k][2] & 0xFFu));
+        };
+#pragma unroll
+        for (int c = -1; c <= 4; ++c) {
+            const int up = px(0, c), mid = px(1, c), dn = px(2, c);
+            v[c + 1] = 3 * (up + dn) + 10 * mid;
+            w[c + 1] = dn - up;
+        }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ix = v[i + 2] - v[i], iy = 3 * (w[i] + w[i + 2]) + 10 * w[i + 1];
+        o[i] = x0 + i < S.w ? (((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16)) : 0u;  // the border of the plane stays zero
+    }
+    *reinterpret_cast<uint4*>(D.base + (size_t)slot * D.plane + (ptrdiff_t)y * D.pitch + (size_t)x0 * 4) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
 // exact warp-wide sum of one int32 per lane as a 64-bit value: two hardware reductions (REDUX.SUM) on the 16-bit halves
@@ -188,7 +228,12 @@ constexpr int TROW = 64, TROWS = 24, TILE_BYTES = TROW * TROWS + 64;
 __host__ __device__ constexpr int row_off(int r) { return r * TROW + (r / 7) * 16; }
 constexpr int SEG = 7;           // iteration form: the window is cut into 21 columns x 3 segments of 7 rows = 63 strips; a lane
 constexpr int NROUND = 2;        // owns strips (lane) and (lane + 32): 14 pixels, 2 x 8 pair loads (vertical reuse inside a strip)
-constexpr int WARP_SMEM = TILE_BYTES + 32 * NROUND * SEG * 8;
+// derivative tile of the setup (DERIV form): 22 rows x 22 words (Ix | Iy << 16 per pixel), rows 24 words apart, every 7-row segment
+// skewed by 3 words so that the three segments a warp reads at once fall into different banks; it shares the image tile's memory
+__host__ __device__ constexpr int drow_off(int r) { return r * 24 + (r / 7) * 3; }
+constexpr int DTILE_BYTES = (drow_off(21) + 24) * 4;
+constexpr int TILE_AREA = DTILE_BYTES > TILE_BYTES ? ((DTILE_BYTES + 63) / 64) * 64 : TILE_BYTES;
+constexpr int WARP_SMEM = TILE_AREA + 32 * NROUND * SEG * 8;
 
 __device__ __forceinline__ int pair_off(int c) {  // byte offset in a tile row of the aligned u16 holding tile bytes (c, c+1)
     const int e = c & ~1;
@@ -223,6 +268,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restr
 //  iterations (next image): the window is cut into 63 strips (21 columns x 3 segments of 7 rows), two per lane: 8 pair loads
 //    per strip (vertical reuse), and per pixel one 64-bit template load, 2 IDP.2A, one shift, two sign extensions, two IMAD.
 // All window sums are exact integers; float expressions follow OpenCV's scalar order with _rn intrinsics.
+template <bool DERIV>
 __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
                                                       float* __restrict__ lk_pts, uint8_t* __restrict__ lk_status, float* __restrict__ lk_err) {
     __shared__ __align__(16) uint8_t s_mem[LW * WARP_SMEM];
@@ -236,7 +282,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
     const int pt = blockIdx.x * LW + warp;
     if (pt >= n) return;  // warp-uniform; most warps of the fixed-size grid leave here
     uint8_t* tile = s_mem + warp * WARP_SMEM;
-    uint2* tmpl = reinterpret_cast<uint2*>(tile + TILE_BYTES);  // [pixel y * 21 + x] = (256 - 512 * I, Ix | Iy << 16)
+    uint2* tmpl = reinterpret_cast<uint2*>(tile + TILE_AREA);  // [pixel y * 21 + x] = (256 - 512 * I, Ix | Iy << 16)
     // template layout: entry (round s, row-in-strip j, lane) at tmpl[(s * 7 + j) * 32 + lane]; strip g = 3 x + y / 7 of window
     // pixel (x, y) belongs to lane g & 31 in round g >> 5.  Strip 63 (lane 31, round 1) does not exist: zero gradient, never
     // rewritten, so it contributes nothing to the sums.
@@ -310,11 +356,79 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
         weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
         uint32_t Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16), Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
 
+        int a11 = 0, a12 = 0, a22 = 0;
+        if (DERIV) {
+            // ---- MEASURED ALTERNATIVE (SVO_LK_DERIV=1; off by default): template from the image plane and a precomputed Scharr plane
+            // (OpenCV's own order: derivI first, then the bilinear interpolation of I, Ix, Iy), in the iterations' strip layout: all 32
+            // lanes, 14 pixels each, one code path for windows inside and across the image border (the Scharr plane has a zero border,
+            // the image plane a REFLECT_101 one).  Parity-green (all GPU tests) and 18 % fewer SASS instructions, but the tracker is
+            // co-limited by the L1 / shared-memory pipe: the 1.9 KB Scharr tile per level and call more than doubles its L1 / L2 traffic
+            // (4.86 vs 4.82 ms) and the Scharr planes cost 0.24 ms per step to write -- 7.42 vs 7.14 ms per step, so the default stays the
+            // commuted form below (Scharr of the interpolated image in registers, no derivative plane anywhere).
+            // phase 1: I.  tile byte 0 = column ipx, row 0 = image row ipy (the same staging as the next image's tiles)
+            __syncwarp();
+            stage_tile(tile, I, G.pitch, ipx, ipy, lane);
+            __syncwarp();
+#pragma unroll
+            for (int sr = 0; sr < NROUND; ++sr) {
+                const uint8_t* tp = tile + offJ[sr];
+                uint32_t pa = lds_u16(tp);
+                const bool real = lane + 32 * sr < 63;
+#pragma unroll
+                for (int j = 0; j < SEG; ++j) {
+                    const uint32_t pb = lds_u16(tp + (row_off(j + 1) - row_off(0)));
+                    const int iv = dp2(Wbot, pb, dp2(Wtop, pa, 256)) >> 9;
+                    if (real) tmpl[(sr * SEG + j) * 32 + lane].x = (uint32_t)(256 - 512 * iv);
+                    pa = pb;
+                }
+            }
+            // phase 2: Ix, Iy.  22 x 22 words of the Scharr plane from (ipx, ipy) on; lane c loads column c
+            __syncwarp();
+            {
+                const LkLevelGeom& GD = P.dv[level];
+                const uint32_t* __restrict__ dsrc = reinterpret_cast<const uint32_t*>(GD.base + (size_t)prev_slot * GD.plane + (ptrdiff_t)ipy * GD.pitch) + ipx + lane;
+                uint32_t* dt = reinterpret_cast<uint32_t*>(tile);
+                if (lane < 22) {
+#pragma unroll
+                    for (int r = 0; r < 22; ++r) dt[drow_off(r) + lane] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(dsrc) + (ptrdiff_t)r * GD.pitch));
+                }
+            }
+            __syncwarp();
+            {
+                const uint32_t* dt = reinterpret_cast<const uint32_t*>(tile);
+#pragma unroll
+                for (int sr = 0; sr < NROUND; ++sr) {
+                    const int g = min(lane + 32 * sr, 62), x = g / 3, sg = g - 3 * x;
+                    const uint32_t* dp = dt + drow_off(SEG * sg) + x;
+                    const bool real = lane + 32 * sr < 63;
+                    int ptx = 0, pty = 0;  // top-row combinations of the previous tile row
+#pragma unroll
+                    for (int j = 0; j <= SEG; ++j) {
+                        const int ro = drow_off(j);  // relative to the strip's first row: 24 words per row, row 7 carries the next segment's skew
+                        const uint32_t wA = dp[ro], wB = dp[ro + 1];
+                        const int ixA = (int)(short)(wA & 0xFFFFu), iyA = (int)wA >> 16, ixB = (int)(short)(wB & 0xFFFFu), iyB = (int)wB >> 16;
+                        if (j >= 1) {
+                            const int ixv = (ptx + ixA * iw10 + ixB * iw11 + (1 << 13)) >> 14;
+                            const int iyv = (pty + iyA * iw10 + iyB * iw11 + (1 << 13)) >> 14;
+                            if (real) {
+                                tmpl[(sr * SEG + j - 1) * 32 + lane].y = ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16);
+                                a11 += ixv * ixv;
+                                a12 += ixv * iyv;
+                                a22 += iyv * iyv;
+                            }
+                        }
+                        if (j < SEG) {
+                            ptx = ixA * iw00 + ixB * iw01;
+                            pty = iyA * iw00 + iyB * iw01;
+                        }
+                    }
+                }
+            }
+        } else {
         // ---- previous image: tile byte 0 = column ipx - 1, tile row 0 = image row ipy - 1
         __syncwarp();
         stage_tile(tile, I, G.pitch, ipx - 1, ipy - 1, lane);
         __syncwarp();
-        int a11 = 0, a12 = 0, a22 = 0;
         // every gradient tap (columns ipx .. ipx+21, rows ipy .. ipy+21) inside the image?  (warp-uniform)
         const bool inside = ipx >= 0 && ipx + WIN < G.w && ipy >= 0 && ipy + WIN < G.h;
         if (inside) {
@@ -394,7 +508,9 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 for (int jj = 0; jj < SEG; ++jj) grow(1 + SEG * sg + jj, tbs[row_off(3 + jj)], lds_u16(tps + row_off(2 + jj)), trow + jj * 32);
             }
         }
-        const long long sA11 = warp_sum64(wlane ? a11 : 0), sA12 = warp_sum64(wlane ? a12 : 0), sA22 = warp_sum64(wlane ? a22 : 0);
+        }  // !DERIV
+        const bool alane = DERIV || wlane;  // DERIV: every lane holds window pixels
+        const long long sA11 = warp_sum64(alane ? a11 : 0), sA12 = warp_sum64(alane ? a12 : 0), sA22 = warp_sum64(alane ? a22 : 0);
         const float FLT_SCALE = 1.f / (1 << 20);
         const float A11 = __fmul_rn((float)sA11, FLT_SCALE), A12 = __fmul_rn((float)sA12, FLT_SCALE), A22 = __fmul_rn((float)sA22, FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -532,6 +648,13 @@ int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
     }
     k_lk_pad<<<dim3(P.row0[c->lk_levels], n_img), 128, 0, c->stream>>>(P, map);
     ++c->launches;
+    if (c->lk_deriv) {  // Scharr planes of all levels (the tracker's setup interpolates them)
+        for (int l = 0; l < c->lk_levels; ++l) {
+            const LkLevelGeom& S = P.lv[l];
+            k_lk_deriv<<<dim3((S.w + 255) / 256, (S.h + 3) / 4, n_img), 256, 0, c->stream>>>(S, c->lkd[l], map);
+            ++c->launches;
+        }
+    }
     SVO_CUDA_TRY(c, cudaGetLastError());
     return SVO_OK;
 }
@@ -539,6 +662,7 @@ int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
 static void fill_params(svo_ctx* c, LkParams& P, int max_level, int max_iter, double eps, double min_eig) {
     P.lv[0] = c->lkp0;
     for (int l = 1; l < SVO_LK_LEVELS; ++l) P.lv[l] = c->lk[l];
+    for (int l = 0; l < SVO_LK_LEVELS; ++l) P.dv[l] = c->lkd[l];
     P.levels = std::min(c->lk_levels, max_level + 1);
     P.max_iter = std::min(std::max(max_iter, 0), 100);
     eps = std::min(std::max(eps, 0.), 10.);
@@ -563,7 +687,8 @@ int launch_lk_chain(svo_ctx* c, int first, int ring, int n_frames, int skip_firs
     P.standalone = 0;
     P.want_err = want_err;
     dim3 grid((c->pt_cap + LW - 1) / LW, n_frames);
-    k_lk_track<<<grid, LW * 32, 0, c->stream>>>(P, c->d_fast_kps, c->d_nfast, c->d_lk_pts, c->d_lk_status, want_err ? c->d_lk_err : nullptr);
+    auto kern = c->lk_deriv ? k_lk_track<true> : k_lk_track<false>;
+    kern<<<grid, LW * 32, 0, c->stream>>>(P, c->d_fast_kps, c->d_nfast, c->d_lk_pts, c->d_lk_status, want_err ? c->d_lk_err : nullptr);
     ++c->launches;
     SVO_CUDA_TRY(c, cudaGetLastError());
     return SVO_OK;
@@ -583,7 +708,8 @@ int launch_lk_standalone(svo_ctx* c, int n, int max_level, int max_iter, double 
     P.n_fixed = n;
     P.want_err = want_err;
     dim3 grid((n + LW - 1) / LW, 1);
-    k_lk_track<<<grid, LW * 32, 0, c->stream>>>(P, c->d_fast_kps, c->d_nfast, c->d_lk_pts, c->d_lk_status, c->d_lk_err);
+    auto kern = c->lk_deriv ? k_lk_track<true> : k_lk_track<false>;
+    kern<<<grid, LW * 32, 0, c->stream>>>(P, c->d_fast_kps, c->d_nfast, c->d_lk_pts, c->d_lk_status, c->d_lk_err);
     ++c->launches;
     SVO_CUDA_TRY(c, cudaGetLastError());
     return SVO_OK;

@@ -181,6 +181,10 @@ struct svo_ctx {
     LkLevelGeom lkp0;               // padded copy of level 0 (written by k_lk_pad)
     int lk_levels = 0;
     uint8_t* d_lkpyr = nullptr;  // padded planes: level-0 copy + levels 1..3
+    // Scharr planes of the 4 LK levels (Ix | Iy << 16, zero border): the tracker's template setup interpolates them (K7c k_lk_deriv)
+    LkLevelGeom lkd[SVO_LK_LEVELS];
+    uint8_t* d_lkderiv = nullptr;
+    bool lk_deriv = false;  // SVO_LK_DERIV=1 in the environment: template setup from Scharr planes (parity-green, but 4 % slower: more L1 / L2 traffic)
     std::vector<FastTile> ftiles;
     FastTile* d_ftiles = nullptr;
     int n_ftiles = 0;

@@ -55,7 +55,7 @@ static void free_layout(svo_ctx* c) {
                      (void**)&c->d_ftile_buf, (void**)&c->d_ftile_cnt, (void**)&c->d_fast_kps, (void**)&c->d_nfast,
                      (void**)&c->d_lk_pts,   (void**)&c->d_lk_status, (void**)&c->d_lk_err,   (void**)&c->d_match,
                      (void**)&c->d_orb_pts,  (void**)&c->d_norb,      (void**)&c->d_lkf_pts,  (void**)&c->d_nlkf,
-                     (void**)&c->d_ptiles,   (void**)&c->d_orb_xyz,   (void**)&c->d_lkf_xyz,   (void**)&c->d_tile_pos};
+                     (void**)&c->d_ptiles,   (void**)&c->d_orb_xyz,   (void**)&c->d_lkf_xyz,   (void**)&c->d_tile_pos,  (void**)&c->d_lkderiv};
     for (void** p : ptrs) {
         if (*p) cudaFree(*p);
         *p = nullptr;

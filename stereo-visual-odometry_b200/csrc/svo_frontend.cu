@@ -36,7 +36,7 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
     if (c->aux_ready && c->pt_cap >= pt_cap) return SVO_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    void** ptrs[] = {(void**)&c->d_lkpyr,    (void**)&c->d_ftiles,  (void**)&c->d_ftile_buf, (void**)&c->d_ftile_cnt, (void**)&c->d_fast_kps,
+    void** ptrs[] = {(void**)&c->d_lkderiv,  (void**)&c->d_lkpyr,    (void**)&c->d_ftiles,  (void**)&c->d_ftile_buf, (void**)&c->d_ftile_cnt, (void**)&c->d_fast_kps,
                      (void**)&c->d_nfast,    (void**)&c->d_lk_pts,  (void**)&c->d_lk_status, (void**)&c->d_lk_err};
     for (void** p : ptrs) {
         if (*p) cudaFree(*p);
@@ -74,6 +74,27 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_lkpyr, 0, total + 4096, c->stream));
     c->lkp0.base = c->d_lkpyr + off[0] + (size_t)SVO_LK_PADY * c->lkp0.pitch + SVO_LK_PADX;
     for (int l = 1; l < c->lk_levels; ++l) c->lk[l].base = c->d_lkpyr + off[l] + (size_t)SVO_LK_PADY * c->lk[l].pitch + SVO_LK_PADX;
+
+    // Scharr planes: 4 bytes per pixel, the same padding as the image planes, border zero (set once here: the kernel writes the interior)
+    c->lk_deriv = getenv("SVO_LK_DERIV") != nullptr;  // measured alternative, off by default (see k_lk.cu / DESIGN.md)
+    if (c->lk_deriv) {
+        size_t dtotal = 0;
+        std::vector<size_t> doff(SVO_LK_LEVELS, 0);
+        for (int l = 0; l < c->lk_levels; ++l) {
+            const LkLevelGeom& G = l == 0 ? c->lkp0 : c->lk[l];
+            LkLevelGeom d{};
+            d.w = G.w;
+            d.h = G.h;
+            d.pitch = 4 * (int)svo_align(G.w + 2 * SVO_LK_PADX, 16);
+            d.plane = (uint32_t)d.pitch * (uint32_t)(G.h + 2 * SVO_LK_PADY);
+            doff[l] = dtotal;
+            dtotal += svo_align((size_t)d.plane * S, 256);
+            c->lkd[l] = d;
+        }
+        SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkderiv, dtotal + 4096));
+        SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_lkderiv, 0, dtotal + 4096, c->stream));
+        for (int l = 0; l < c->lk_levels; ++l) c->lkd[l].base = c->d_lkderiv + doff[l] + (size_t)SVO_LK_PADY * c->lkd[l].pitch + (size_t)SVO_LK_PADX * 4;
+    }
 
     // full-frame FAST strips over the inner domain [3, w-3) x [3, h-3)
     c->ftiles.clear();
