@@ -75,7 +75,11 @@ int svo_orb_capacity(const svo_ctx* ctx, int w, int h);
 /* Level geometry for a w x h input (ORBextractor::ComputePyramid, ORBextractor.cpp:1065-1066). */
 int svo_orb_level_size(const svo_ctx* ctx, int w, int h, int level, int* lw, int* lh);
 
-/* Replaces ORBextractor::operator()(image, mask, keypoints, descriptors) (ORBextractor.h:41-43,
+/* Note on the octree (ORBextractor.cpp:624-689): the reference breaks ties between equal-count nodes by heap ADDRESS; this library
+ * uses creation order, which is what the reference does under an allocator that hands out increasing addresses.  Under glibc
+ * malloc 1-3 % of the reference's own selected keypoints vary with the heap's history.
+ *
+ * Replaces ORBextractor::operator()(image, mask, keypoints, descriptors) (ORBextractor.h:41-43,
  * ORBextractor.cpp:990-1055).  img: 8-bit single channel, w x h, row stride in bytes.  kps/desc: caller arrays of
  * `cap` keypoints / cap*32 bytes; *n_out = number written.  An empty image (w==0||h==0||!img) returns SVO_OK with
  * *n_out = 0 (the reference returns silently, :993-994). */

@@ -9,6 +9,11 @@
 //       round B (:624-689)  nodes with > 1 key sorted by (count, address), walked from the back, stopping as soon as the
 //                           list reaches N nodes.  Address ties are canonicalised to creation order (the reference's
 //                           behaviour under a monotone allocator), i.e. descending count, then ascending list position.
+//                           LIMITATION: the reference sorts pair<count, ExtractorNode*> (:636), so with an allocator that reuses
+//                           freed blocks (glibc malloc after lNodes.erase) equal-count nodes can be split in a different order
+//                           and 1-3 % of the keypoints selected near the N cut-off differ -- between two runs of the reference
+//                           itself too (tests/test_reference_cpu.py prints the rate).  Bit-exactness against the compiled
+//                           reference is therefore defined, and tested, under a bump allocator (oracle/_ref, monotone = true).
 // So each round is: histogram keys into child quadrants -> (sort) -> prefix sums over parents -> rebuild the node
 // array in list order -> relabel keys.  The node array lives in shared memory in list order; keys stay in global
 // memory (L2-resident) with a 16-bit node position each.
