@@ -83,6 +83,14 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) nkp[slot] = total;
     if (level < 0) return;  // warp-uniform
+    // this lane's 8 pattern pairs (32 signed bytes) as two 16-byte loads (byte loads would be 32 warp instructions with 32 scattered
+    // sectors each); requested here, long before they are used, so that their L2 round trip hides behind the patch work
+    uint32_t pw[8];
+    {
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(pattern + lane * 32)), p1 = __ldg(reinterpret_cast<const uint4*>(pattern + lane * 32) + 1);
+        pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w;
+        pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
+    }
     const LevelGeom& G = g.lvl[level];
     const uint32_t c = lkp_all[(size_t)slot * lkp_per_slot + G.lkp_off + local];
     const int kx = cand_x(c) + SVO_MINB, ky = cand_y(c) + SVO_MINB;  // level pixel coordinates (:797-798)
@@ -173,14 +181,6 @@ __global__ void __launch_bounds__(DW * 32) k_describe(PyrGeom g, SlotMap map, Um
     double sd, cd;
     sincos((double)ang, &sd, &cd);
     const float a = (float)cd, b = (float)sd;
-    // this lane's 8 pattern pairs (32 signed bytes) as two 16-byte loads: byte loads here would be 32 warp instructions with
-    // 32 scattered sectors each -- as much L1 traffic as the whole shared-memory work of the keypoint
-    uint32_t pw[8];
-    {
-        const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(pattern + lane * 32)), p1 = __ldg(reinterpret_cast<const uint4*>(pattern + lane * 32) + 1);
-        pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w;
-        pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
-    }
     // vertical taps as packed u8 weights for even / odd first rows
     const uint32_t E0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), E1 = 48u | (34u << 8) | (18u << 16);
     const uint32_t O0 = (18u << 8) | (34u << 16) | (48u << 24), O1 = 56u | (48u << 8) | (34u << 16) | (18u << 24);

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
                                                        const PyrTile* __restrict__ tiles, int bufB_off) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) unsigned long long mbar;
+    __shared__ __align__(16) PyrTile sT;  // the tile's rectangles and thread layouts: read once, not once per level from L2
     const int slot = map.slot(blockIdx.y);
     const PyrTile& T = tiles[blockIdx.x];
     uint8_t* bufA = smem;             // level-0 box (SVO_PYR_BOX_H x SVO_PYR_BOX_W), later the even levels
@@ -156,6 +157,8 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    static_assert(sizeof(PyrTile) % 4 == 0 && sizeof(PyrTile) / 4 <= 256, "PyrTile is copied by one word per thread");
+    if (threadIdx.x < sizeof(PyrTile) / 4) reinterpret_cast<uint32_t*>(&sT)[threadIdx.x] = __ldg(reinterpret_cast<const uint32_t*>(&T) + threadIdx.x);
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(SVO_PYR_BOX_W * SVO_PYR_BOX_H) : "memory");
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
     int s_orgx = r0.x0 & ~15, s_orgy = r0.y0, s_pitch = SVO_PYR_BOX_W;  // the box starts at a 16-byte aligned column
     for (int l = 1; l < g.nlevels; ++l) {
         const LevelGeom& D = g.lvl[l];
-        const PyrRect r = T.lv[l];
+        const PyrRect r = sT.lv[l];
         if (r.ng <= 0) break;  // deeper levels of this tile are empty too (CTA-uniform)
         uint8_t* dbuf = (l & 1) ? bufB : bufA;
         const int d_orgx = (r.x0 & ~3) - 4;  // level x of byte 0 of a buffer row (one group of front margin)
