@@ -53,19 +53,20 @@ __device__ __forceinline__ void pyr_hpass4(const uint8_t* __restrict__ row, int 
     }
 }
 
-// cv::pyrDown: each thread produces 4 x 2 destination pixels (7 source rows, the middle 3 shared by both output rows)
+// cv::pyrDown: each thread produces 4 x 2 destination pixels (7 source rows, the middle 3 shared by both output rows).  The source is a
+// PADDED plane (REFLECT_101 border materialised by k_lk_pad, which is also pyrDown's border mode), so every tap is a plain aligned
+// load: no thread takes a border path (with an unpadded source the two border threads of every row made their warps run a ~200
+// instruction byte-wise path: 16.7 of 32 threads active per instruction).
 __global__ void __launch_bounds__(256) k_pyr_down(LkLevelGeom S, LkLevelGeom D, SlotMap map) {
     const int slot = map.slot(blockIdx.z);
     const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y0 = (blockIdx.y * 4 + (threadIdx.x >> 6)) * 2;
     if (x0 >= D.w || y0 >= D.h) return;
     const uint8_t* __restrict__ src = S.base + (size_t)slot * S.plane;
-    // all 4 pixels' taps inside the row and the 4 aligned words inside the pitch
-    const bool interior = 2 * x0 - 4 >= 0 && 2 * x0 + 12 <= S.w;
     int hr[7][4];
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
-        const int sy = reflect101(min(2 * y0 + i - 2, S.h + 1), S.h);  // rows beyond the second output row's taps are unused
-        pyr_hpass4(src + (size_t)sy * S.pitch, x0, S.w, interior, hr[i]);
+        const int sy = min(2 * y0 + i - 2, S.h + 1);  // rows beyond the second output row's taps are unused; -2 .. h + 1 lie in the border
+        pyr_hpass4(src + (ptrdiff_t)sy * S.pitch, x0, S.w, true, hr[i]);
     }
     uint8_t* dst = D.base + (size_t)slot * D.plane + (size_t)y0 * D.pitch + x0;
 #pragma unroll
@@ -104,6 +105,7 @@ struct LkPadParams {
     LkLevelGeom lv[SVO_LK_LEVELS];  // padded planes (base = interior origin)
     int row0[SVO_LK_LEVELS + 1];    // first CTA of every level (a CTA handles PAD_ROWS of the h + 2 * PADY padded rows)
     int levels;
+    int copy0;  // 1: entry 0 is level 0 and is copied whole from src0 (the unpadded ORB plane); else every entry is filled in place
 };
 
 __device__ __forceinline__ int reflect101_any(int i, int n) {
@@ -123,15 +125,16 @@ __global__ void __launch_bounds__(128) k_lk_pad(LkPadParams P, SlotMap map) {
     const int nrows = min(PAD_ROWS, D.h + SVO_LK_PADY - r0);
     uint8_t* dbase = D.base + (size_t)slot * D.plane;
     // source: level 0 comes from the (unpadded) ORB plane, the other levels from their own interior
-    const uint8_t* __restrict__ sbase = l == 0 ? P.src0.base + (size_t)slot * P.src0.plane : dbase;
-    const int spitch = l == 0 ? P.src0.pitch : D.pitch;
+    const bool from0 = l == 0 && P.copy0;
+    const uint8_t* __restrict__ sbase = from0 ? P.src0.base + (size_t)slot * P.src0.plane : dbase;
+    const int spitch = from0 ? P.src0.pitch : D.pitch;
     // 16 threads per row, 8 rows per CTA: no index divisions, 256 contiguous bytes per row and step
     const int rr = threadIdx.x >> 4, t16 = threadIdx.x & 15;
     if (rr >= nrows) return;
     const int yp = r0 + rr;
     const uint8_t* __restrict__ srow = sbase + (ptrdiff_t)reflect101_any(yp, D.h) * spitch;
     uint8_t* drow = dbase + (ptrdiff_t)yp * D.pitch;
-    if (l == 0 || yp < 0 || yp >= D.h) {
+    if (from0 || yp < 0 || yp >= D.h) {
         // interior columns (all rows of level 0, the top / bottom border rows of the others): 16-byte copies (rows are 16-byte
         // aligned), four independent loads in flight per thread, then the ragged end byte-wise
         const int nv = D.w >> 4;
@@ -630,24 +633,31 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
 
 int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img) {
     StageTimer t(c, 7);
+    // level 0: padded copy of the ORB level-0 plane; then level l = pyrDown(padded level l - 1), and its own border right after
+    // (the next level's taps read it)
+    auto pad = [&](int l) {
+        LkPadParams P{};
+        P.src0 = c->lk[0];
+        P.lv[0] = l == 0 ? c->lkp0 : c->lk[l];
+        P.levels = 1;
+        P.copy0 = l == 0;
+        P.row0[0] = 0;
+        P.row0[1] = (P.lv[0].h + 2 * SVO_LK_PADY + PAD_ROWS - 1) / PAD_ROWS;
+        k_lk_pad<<<dim3(P.row0[1], n_img), 128, 0, c->stream>>>(P, map);
+        ++c->launches;
+    };
+    pad(0);
     for (int l = 1; l < c->lk_levels; ++l) {
-        const LkLevelGeom& S = c->lk[l - 1];
+        const LkLevelGeom& S = l == 1 ? c->lkp0 : c->lk[l - 1];
         const LkLevelGeom& D = c->lk[l];
         dim3 grid((D.w + 255) / 256, (D.h + 7) / 8, n_img);
         k_pyr_down<<<grid, 256, 0, c->stream>>>(S, D, map);
         ++c->launches;
+        pad(l);
     }
-    LkPadParams P{};
-    P.src0 = c->lk[0];
+    LkPadParams P{};  // (geometry of all levels for the Scharr-plane alternative below)
     P.lv[0] = c->lkp0;
-    P.levels = c->lk_levels;
-    P.row0[0] = 0;
-    for (int l = 0; l < c->lk_levels; ++l) {
-        if (l) P.lv[l] = c->lk[l];
-        P.row0[l + 1] = P.row0[l] + (P.lv[l].h + 2 * SVO_LK_PADY + PAD_ROWS - 1) / PAD_ROWS;
-    }
-    k_lk_pad<<<dim3(P.row0[c->lk_levels], n_img), 128, 0, c->stream>>>(P, map);
-    ++c->launches;
+    for (int l = 1; l < c->lk_levels; ++l) P.lv[l] = c->lk[l];
     if (c->lk_deriv) {  // Scharr planes of all levels (the tracker's setup interpolates them)
         for (int l = 0; l < c->lk_levels; ++l) {
             const LkLevelGeom& S = P.lv[l];

@@ -209,12 +209,13 @@ __global__ void __launch_bounds__(256) k_pyramid_fused(const __grid_constant__ C
             uint8_t* sp = dbuf + 4 + 4 * gi + (ya - r.y0) * r.pitch;
             uint8_t* gp = D.base + (size_t)slot * D.plane + gx + (size_t)ya * D.pitch;
             const int4* ymp = D.ymeta + ya;
-            int4 ym = ya < yb ? __ldg(ymp) : make_int4(0, 0, 0, 0);  // {top tap row, bottom tap row, beta0, beta1}; next row prefetched
+            int4 ym = ya < yb ? __ldg(ymp) : make_int4(0, 0, 0, 0);  // {top tap row, bottom tap row, beta0, beta1}; the next row's is requested one iteration ahead (the table has a spare entry)
             int cached_row = -1;
             uint32_t Tc[4] = {0, 0, 0, 0};
+#pragma unroll 2
             for (int y = ya; y < yb; ++y) {
                 const int4 cur = ym;
-                if (y + 1 < yb) ym = __ldg(++ymp);
+                ym = __ldg(++ymp);
                 uint32_t T0[4], T1[4];
                 if (cur.x == cached_row) {
 #pragma unroll

@@ -344,7 +344,7 @@ int svo_layout(svo_ctx* c, int w, int h) {
             const int dw = g.lvl[l].w, dh = g.lvl[l].h;
             const int ngr = (dw + 3) / 4 + 2;
             off_xm[l] = reserve(sizeof(int) * 8 * ngr);
-            off_ym[l] = reserve(sizeof(int) * 4 * dh);
+            off_ym[l] = reserve(sizeof(int) * 4 * (dh + 1));  // + 1: the kernel requests row y + 1 unconditionally
             const int* xofs = (const int*)(host.data() + off_x[l]);
             const short* alpha = (const short*)(host.data() + off_a[l]);
             const int* yofs = (const int*)(host.data() + off_y[l]);
