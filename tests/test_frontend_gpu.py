@@ -13,6 +13,67 @@ def _oracle_chain(orc, l0, r0, l1, r1, seeds):
     return (p1, p2, p3, p0r), (s1, s2, s3, s4)
 
 
+def _check_unit(pkg, orc, oracle, out, i, lf, rf, prev):
+    """One unit of a batch (stereo frame i of `out`, images lf/rf) against the oracle; `prev` describes the frame before it (None for the
+    first of a sequence).  Returns the `prev` of the next frame."""
+    okl, odl = oracle.extract(lf)
+    okr, odr = oracle.extract(rf)
+    nl, nr = out.n_left[i], out.n_right[i]
+    assert nl == len(okl) and nr == len(okr)
+    assert np.array_equal(out.kps_left[i, :nl], okl) and np.array_equal(out.kps_right[i, :nr], okr)
+    assert np.unpackbits(out.desc_left[i, :nl] ^ odl).sum() <= 2
+    assert np.unpackbits(out.desc_right[i, :nr] ^ odr).sum() <= 2
+    ofast = orc.fast9(lf, 20)
+    assert out.n_fast[i] == len(ofast) and np.array_equal(out.fast_kps[i, :len(ofast)], ofast)
+    if prev is None:
+        assert out.n_query[i] == 0 and out.n_seed[i] == 0
+    else:
+        # K6 on the descriptors the GPU produced for the previous / current frame
+        nq = out.n_query[i]
+        assert nq == len(prev["dl"])
+        si, sd = orc.match_hamming(prev["dl"], prev["dr"])
+        ti, td = orc.match_hamming(prev["dl"], out.desc_left[i, :nl])
+        assert np.array_equal(out.stereo_idx[i, :nq], si) and np.array_equal(out.stereo_dist[i, :nq], sd)
+        assert np.array_equal(out.temporal_idx[i, :nq], ti) and np.array_equal(out.temporal_dist[i, :nq], td)
+        # the 4-call LK chain seeded with the previous frame's FAST corners
+        ns = out.n_seed[i]
+        seeds = np.stack([prev["fast"]["x"], prev["fast"]["y"]], 1)
+        assert ns == len(seeds)
+        (p1, p2, p3, p0r), sts = _oracle_chain(orc, prev["l"], prev["r"], lf, rf, seeds)
+        cum = np.ones(ns, bool)
+        for k, (gp, op) in enumerate(zip((out.lk_p1, out.lk_p2, out.lk_p3, out.lk_p0r), (p1, p2, p3, p0r))):
+            gs = out.lk_status[i, k, :ns]
+            # cumulative status: a failed point carries garbage into the next call (quirk Q5)
+            assert np.array_equal(gs[cum], sts[k][cum]), f"status of call {k + 1}"
+            cum &= sts[k] == 1
+            assert np.abs(gp[i, :ns] - op)[cum].max() <= 0.01, f"points of call {k + 1}"
+        keep_g = orc.lk_chain_filter(seeds, out.lk_p1[i, :ns], out.lk_p2[i, :ns], out.lk_p3[i, :ns], out.lk_p0r[i, :ns],
+                                     *[out.lk_status[i, k, :ns] for k in range(4)])
+        keep_o = orc.lk_chain_filter(seeds, p1, p2, p3, p0r, *sts)
+        assert np.array_equal(keep_g, keep_o)
+        # K11: deleteBadmatchFeatures on the device == the oracle filter applied to the device's own chain outputs
+        nk = out.n_lk_matched[i]
+        assert nk == keep_g.sum()
+        assert np.array_equal(out.lkf_t1_left[i, :nk], seeds[keep_g]) and np.array_equal(out.lkf_t1_right[i, :nk], out.lk_p1[i, :ns][keep_g])
+        assert np.array_equal(out.lkf_t2_right[i, :nk], out.lk_p2[i, :ns][keep_g]) and np.array_equal(out.lkf_t2_left[i, :nk], out.lk_p3[i, :ns][keep_g])
+        # K10: the ORB association filter (tracking.cpp:546-577)
+        acc = orc.orb_match_filter(si, sd, ti, td, len(prev["dr"]), nl, prev["kl"], prev["kr"], 3.0)
+        nm = out.n_orb_matched[i]
+        assert nm == len(acc) and nm > 20
+        cur_xy = np.stack([out.kps_left[i, :nl]["x"], out.kps_left[i, :nl]["y"]], 1)
+        pl_xy = np.stack([prev["kl"]["x"], prev["kl"]["y"]], 1)
+        pr_xy = np.stack([prev["kr"]["x"], prev["kr"]["y"]], 1)
+        assert np.array_equal(out.orb_t1_left[i, :nm], pl_xy[acc[:, 0]]) and np.array_equal(out.orb_t1_right[i, :nm], pr_xy[acc[:, 1]])
+        assert np.array_equal(out.orb_t2_left[i, :nm], cur_xy[acc[:, 2]])
+    return _prev_of(out, i, lf, rf, ofast)
+
+
+def _prev_of(out, i, lf, rf, ofast):
+    nl, nr = out.n_left[i], out.n_right[i]
+    return dict(l=lf, r=rf, dl=out.desc_left[i, :nl].copy(), dr=out.desc_right[i, :nr].copy(), fast=ofast,
+                kl=out.kps_left[i, :nl].copy(), kr=out.kps_right[i, :nr].copy())
+
+
 @pytest.mark.parametrize("w,h,nfeat,max_frames,n_total", [(640, 200, 500, 3, 7), (1241, 376, 1000, 4, 5)])
 def test_frontend_sequence(pkg, orc, w, h, nfeat, max_frames, n_total):
     seed = 1000
@@ -29,59 +90,28 @@ def test_frontend_sequence(pkg, orc, w, h, nfeat, max_frames, n_total):
         out = pkg.FrontendBuffers(n, kp_cap, pt_cap)
         ctx.frontend_batch(np.ascontiguousarray(left[f0:f0 + n]), np.ascontiguousarray(right[f0:f0 + n]), out)
         for i in range(n):
-            f = f0 + i
-            okl, odl = oracle.extract(left[f])
-            okr, odr = oracle.extract(right[f])
-            nl, nr = out.n_left[i], out.n_right[i]
-            assert nl == len(okl) and nr == len(okr)
-            assert np.array_equal(out.kps_left[i, :nl], okl) and np.array_equal(out.kps_right[i, :nr], okr)
-            assert np.unpackbits(out.desc_left[i, :nl] ^ odl).sum() <= 2
-            assert np.unpackbits(out.desc_right[i, :nr] ^ odr).sum() <= 2
-            ofast = orc.fast9(left[f], 20)
-            assert out.n_fast[i] == len(ofast) and np.array_equal(out.fast_kps[i, :len(ofast)], ofast)
-            if prev is None:
-                assert out.n_query[i] == 0 and out.n_seed[i] == 0
-            else:
-                # K6 on the descriptors the GPU produced for the previous / current frame
-                nq = out.n_query[i]
-                assert nq == len(prev["dl"])
-                si, sd = orc.match_hamming(prev["dl"], prev["dr"])
-                ti, td = orc.match_hamming(prev["dl"], out.desc_left[i, :nl])
-                assert np.array_equal(out.stereo_idx[i, :nq], si) and np.array_equal(out.stereo_dist[i, :nq], sd)
-                assert np.array_equal(out.temporal_idx[i, :nq], ti) and np.array_equal(out.temporal_dist[i, :nq], td)
-                # the 4-call LK chain seeded with the previous frame's FAST corners
-                ns = out.n_seed[i]
-                seeds = np.stack([prev["fast"]["x"], prev["fast"]["y"]], 1)
-                assert ns == len(seeds)
-                (p1, p2, p3, p0r), sts = _oracle_chain(orc, prev["l"], prev["r"], left[f], right[f], seeds)
-                cum = np.ones(ns, bool)
-                for k, (gp, op) in enumerate(zip((out.lk_p1, out.lk_p2, out.lk_p3, out.lk_p0r), (p1, p2, p3, p0r))):
-                    gs = out.lk_status[i, k, :ns]
-                    # cumulative status: a failed point carries garbage into the next call (quirk Q5)
-                    assert np.array_equal(gs[cum], sts[k][cum]), f"status of call {k + 1}"
-                    cum &= sts[k] == 1
-                    assert np.abs(gp[i, :ns] - op)[cum].max() <= 0.01, f"points of call {k + 1}"
-                keep_g = orc.lk_chain_filter(seeds, out.lk_p1[i, :ns], out.lk_p2[i, :ns], out.lk_p3[i, :ns], out.lk_p0r[i, :ns],
-                                             *[out.lk_status[i, k, :ns] for k in range(4)])
-                keep_o = orc.lk_chain_filter(seeds, p1, p2, p3, p0r, *sts)
-                assert np.array_equal(keep_g, keep_o)
-                # K11: deleteBadmatchFeatures on the device == the oracle filter applied to the device's own chain outputs
-                nk = out.n_lk_matched[i]
-                assert nk == keep_g.sum()
-                assert np.array_equal(out.lkf_t1_left[i, :nk], seeds[keep_g]) and np.array_equal(out.lkf_t1_right[i, :nk], out.lk_p1[i, :ns][keep_g])
-                assert np.array_equal(out.lkf_t2_right[i, :nk], out.lk_p2[i, :ns][keep_g]) and np.array_equal(out.lkf_t2_left[i, :nk], out.lk_p3[i, :ns][keep_g])
-                # K10: the ORB association filter (tracking.cpp:546-577)
-                acc = orc.orb_match_filter(si, sd, ti, td, len(prev["dr"]), nl, prev["kl"], prev["kr"], 3.0)
-                nm = out.n_orb_matched[i]
-                assert nm == len(acc) and nm > 20
-                cur_xy = np.stack([out.kps_left[i, :nl]["x"], out.kps_left[i, :nl]["y"]], 1)
-                pl_xy = np.stack([prev["kl"]["x"], prev["kl"]["y"]], 1)
-                pr_xy = np.stack([prev["kr"]["x"], prev["kr"]["y"]], 1)
-                assert np.array_equal(out.orb_t1_left[i, :nm], pl_xy[acc[:, 0]]) and np.array_equal(out.orb_t1_right[i, :nm], pr_xy[acc[:, 1]])
-                assert np.array_equal(out.orb_t2_left[i, :nm], cur_xy[acc[:, 2]])
-            prev = dict(l=left[f], r=right[f], dl=out.desc_left[i, :nl].copy(), dr=out.desc_right[i, :nr].copy(), fast=ofast,
-                        kl=out.kps_left[i, :nl].copy(), kr=out.kps_right[i, :nr].copy())
+            prev = _check_unit(pkg, orc, oracle, out, i, left[f0 + i], right[f0 + i], prev)
         f0 += n
+    ctx.close()
+
+
+def test_bench_step_against_oracle(pkg, orc):
+    """The batch bench.py times (config c1: 128 KITTI-sized frames of sequence seed 1000 from frame 0, nfeatures 1000) checked DIRECTLY
+    against the oracle on a spread of its units -- the first, one either side of the canvas re-seed, the middle, the last -- each
+    through every stage (ORB both eyes, both matches, FAST seeds, the 4-call LK chain, both filters)."""
+    w, h, B, nfeat = 1241, 376, 128, 1000
+    left, right = pkg.synth_sequence(1000, 0, B, w, h)
+    ctx = pkg.Context(0, w, h, 2 * (B + 1))
+    ctx.orb_configure(nfeat, 1.2, 8, 20, 7)
+    ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
+    kp_cap, pt_cap = ctx.orb_capacity(w, h), max(1024, w * h // 64)
+    out = pkg.FrontendBuffers(B, kp_cap, pt_cap)
+    ctx.frontend_batch(left, right, out)
+    ctx.frontend_check()
+    oracle = orc.OrbOracle(nfeat, 1.2, 8, 20, 7)
+    for f in (0, 15, 16, 64, 127):
+        prev = None if f == 0 else _prev_of(out, f - 1, left[f - 1], right[f - 1], orc.fast9(left[f - 1], 20))
+        _check_unit(pkg, orc, oracle, out, f, left[f], right[f], prev)
     ctx.close()
 
 
