@@ -438,22 +438,23 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             //   Ib(r) = interpolated image at tile row r (rows 0..22), exact and un-descaled
             //   Ix(y) = 3 (dH(y) + dH(y+2)) + 10 dH(y+1),  dH = Ib(x+1) - Ib(x-1)
             //   Iy(y) = S(y+2) - S(y),                       S  = 3 (Ib(x-1) + Ib(x+1)) + 10 Ib(x)
+            //   (Ib carries the rounding constant 256 of I's descale: it cancels in dH and in S(y+2) - S(y))
             const uint8_t* tp = tile + pair_off(ccol);
-            int top = dp2(Wtop, lds_u16(tp), 0);
+            int top = dp2(Wtop, lds_u16(tp), 256);
             int dH0 = 0, dH1 = 0, S0 = 0, S1 = 0, ibm = 0;
 #pragma unroll
             for (int r = 1; r < TROWS; ++r) {
                 const uint32_t pr = lds_u16(tp + row_off(r));
-                const int ib = dp2(Wbot, pr, top);  // Ib(r - 1)
-                top = dp2(Wtop, pr, 0);
+                const int ib = dp2(Wbot, pr, top);  // Ib(r - 1) + 256
+                top = dp2(Wtop, pr, 256);
                 const int ibL = __shfl_up_sync(0xFFFFFFFFu, ib, 1), ibR = __shfl_down_sync(0xFFFFFFFFu, ib, 1);
                 const int dH2 = ibR - ibL, S2 = 3 * (ibL + ibR) + 10 * ib;
                 if (r >= 3) {  // window row y = r - 3: Ib rows y, y+1, y+2 are complete
                     const int y = r - 3;
                     const int ixv = (3 * (dH0 + dH2) + 10 * dH1 + (1 << 13)) >> 14;
                     const int iyv = (S2 - S0 + (1 << 13)) >> 14;
-                    const int iv = (ibm + 256) >> 9;
-                    if (wlane) tmpl[tbase[y / SEG] + (y % SEG) * 32] = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
+                    // 256 - 512 * descale(Ib, 9) = 256 - ((Ib + 256) & ~511); (Ix, Iy) packed by one PRMT
+                    if (wlane) tmpl[tbase[y / SEG] + (y % SEG) * 32] = make_uint2((uint32_t)(256 - (ibm & ~511)), __byte_perm((uint32_t)ixv, (uint32_t)iyv, 0x5410));
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             const uint8_t* tb = tile + ((ccol >> 2) << 3) + (ccol & 3);  // T byte of this lane's column
             const uint8_t* tp = tile + pair_off(ccol);
             int p0 = tb[0], p1 = tb[row_off(1)];
-            int top = 0, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;
+            int top = 256, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;
             // one row of the general form: the Scharr gradient at (X, Y = ipy + r) (tile row r + 1) from tile rows r .. r + 2, and -- for
             // r >= 1 -- the template entry of window row r - 1 from the gradients / pixels of rows r - 1 and r
             auto grow = [&](int r, int p2, uint32_t pr, uint2* trow) {
@@ -485,15 +486,15 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 const int gy = in ? 3 * (Dl + Dr) + 10 * Dv : 0;
                 const int gxn = __shfl_down_sync(0xFFFFFFFFu, gx, 1), gyn = __shfl_down_sync(0xFFFFFFFFu, gy, 1);
                 if (trow) {
-                    const int iv = (dp2(Wbot, pr, top) + 256) >> 9;
+                    const int ib = dp2(Wbot, pr, top);  // interpolated pixel + 256
                     const int ixv = descale(tgx * iw00 + tgxn * iw01 + gx * iw10 + gxn * iw11, 14);
                     const int iyv = descale(tgy * iw00 + tgyn * iw01 + gy * iw10 + gyn * iw11, 14);
-                    if (wlane) *trow = make_uint2((uint32_t)(256 - 512 * iv), ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16));
+                    if (wlane) *trow = make_uint2((uint32_t)(256 - (ib & ~511)), __byte_perm((uint32_t)ixv, (uint32_t)iyv, 0x5410));
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
                 }
-                top = dp2(Wtop, pr, 0);
+                top = dp2(Wtop, pr, 256);
                 tgx = gx; tgxn = gxn; tgy = gy; tgyn = gyn;
                 p0 = p1;
                 p1 = p2;
@@ -563,9 +564,12 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                     pa = pb;
                 }
             }
-            // |diff| <= 255 and |Ix|, |Iy| <= 4080 (Scharr of 8-bit pixels): the window sums stay below 441 * 255 * 4080 < 2^31,
-            // so one 32-bit hardware reduction per sum is exact
-            const int sb1 = __reduce_add_sync(0xFFFFFFFFu, b1), sb2 = __reduce_add_sync(0xFFFFFFFFu, b2);
+            // |diff| <= 8160 (pixels carry 5 fraction bits) and |Ix|, |Iy| <= 4080 (Scharr of 8-bit pixels): a lane's 14 products stay
+            // below 2^29, but the window sum can reach 441 * 8160 * 4080 ~ 2^34 (sharp stripes one pixel out of register), so the
+            // exact sum takes three hardware reductions: the two high parts (b >> 8, |sum| < 2^26) and both low bytes packed in one
+            const int hb1 = __reduce_add_sync(0xFFFFFFFFu, b1 >> 8), hb2 = __reduce_add_sync(0xFFFFFFFFu, b2 >> 8);
+            const uint32_t lb = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(b1 & 255) | ((uint32_t)(b2 & 255) << 16));  // each <= 32 * 255
+            const long long sb1 = ((long long)hb1 << 8) + (long long)(lb & 0xFFFFu), sb2 = ((long long)hb2 << 8) + (long long)(lb >> 16);
             const float b1f = __fmul_rn((float)sb1, FLT_SCALE), b2f = __fmul_rn((float)sb2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2f), __fmul_rn(A22, b1f)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1f), __fmul_rn(A11, b2f)), D);
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                     }
                     if (lane + 32 * sr < 63) e += es;
                 }
-                const int se = __reduce_add_sync(0xFFFFFFFFu, e);  // <= 441 * 255
+                const int se = __reduce_add_sync(0xFFFFFFFFu, e);  // <= 441 * 8160
                 err = __fdiv_rn((float)se, (float)(32 * WIN * WIN));
             }
         }

@@ -91,6 +91,34 @@ def test_lk_levels_and_iterations(pkg, orc):
     ctx.close()
 
 
+def test_lk_sharp_patterns_one_pixel_out_of_register(pkg, orc):
+    """Binary stripes / checkerboards of period 4 shifted by one pixel: every window pixel carries the largest gradient (4080) and half
+    of them the largest difference (8160), so the first Gauss-Newton step's sums sum(diff * Ix) reach ~7e9 -- beyond 32 bits.  The
+    sums are exact integers in the oracle (64-bit); the device's must be too."""
+    w, h = 320, 240
+    yy, xx = np.mgrid[0:h, 0:w]
+    stripes = (((xx >> 1) & 1) * 255).astype(np.uint8)
+    checker = ((((xx >> 1) ^ (yy >> 1)) & 1) * 255).astype(np.uint8)
+    rng = np.random.default_rng(3)
+    pts = (rng.uniform(0, 1, (400, 2)) * [w, h]).astype(np.float32)
+    ctx = pkg.Context(0, w, h, 2)
+    big = 0
+    for img in (stripes, checker):
+        for sh in (1, -1):
+            nxt = np.ascontiguousarray(np.roll(img, sh, axis=1))
+            for max_level in (0, 3):
+                g = ctx.lk_track(img, nxt, pts, max_level=max_level)
+                o = orc.lk_track(img, nxt, pts, max_level=max_level)
+                assert np.array_equal(g[1], o[1])
+                ok = o[1] == 1
+                big += int(ok.sum())
+                if ok.any():
+                    assert np.abs(g[0] - o[0])[ok].max() <= LK_TOL
+                    assert np.abs(g[2] - o[2])[ok].max() <= 1e-3
+    assert big > 400
+    ctx.close()
+
+
 @pytest.mark.parametrize("gap", [3, 6, 11])
 def test_lk_large_motion_many_iterations(pkg, orc, gap):
     """Frames several steps apart (2 px of motion per step + the 8 px disparity): tracks need many Gauss-Newton steps, leave their
