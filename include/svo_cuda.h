@@ -45,6 +45,11 @@ int svo_ctx_create(svo_ctx** ctx, int device, int max_w, int max_h, int max_imag
 void svo_ctx_destroy(svo_ctx* ctx);
 const char* svo_last_error(const svo_ctx* ctx);
 int svo_abi_version(void);
+/* Debug: with SVO_GUARD=1 in the environment every device buffer of the library carries a 4 KB guard band on both sides; returns the
+ * number of band bytes overwritten so far (0 = no write overrun), -1 when the library runs without SVO_GUARD. */
+long long svo_guard_check(void);
+/* Debug: deliberately overruns a scratch buffer by 3 bytes and returns what svo_guard_check() reports for it (3; -1 without SVO_GUARD). */
+long long svo_guard_selftest(void);
 /* Run all work of this context on the caller's CUDA stream (a cudaStream_t); NULL restores the context's own. */
 int svo_ctx_set_stream(svo_ctx* ctx, void* cuda_stream);
 int svo_ctx_synchronize(svo_ctx* ctx);

@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "svo_frontend_reset", "svo_frontend_set_match_error", "svo_frontend_set_overlap", "svo_frontend_set_lk_err", "svo_frontend_set_projection",
     "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_wait_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_check",
     "svo_frontend_discard", "svo_frontend_batch", "svo_source_open", "svo_source_frame_count", "svo_source_is_pinned", "svo_source_next",
-    "svo_source_error", "svo_source_close", "svo_write_pgm", "svo_write_png", "svo_orb_match_filter", "svo_lk_chain_filter",
+    "svo_source_error", "svo_source_close", "svo_write_pgm", "svo_write_png", "svo_orb_match_filter", "svo_lk_chain_filter", "svo_guard_check", "svo_guard_selftest",
 ]
 SYNTH_SYMBOLS = ["svo_synth_stereo_frame"]  # exported by libsvo_synth.so
 
@@ -57,6 +57,16 @@ class FrontendOut(C.Structure):
 
 _lib = None
 _synth = None
+
+
+def guard_check():
+    """Debug (SVO_GUARD=1 in the environment before the library loads): guard-band bytes overwritten so far; -1 if guards are off."""
+    return int(lib().svo_guard_check())
+
+
+def guard_selftest():
+    """Debug: a deliberate 3-byte overrun of a scratch buffer as seen by the guard bands (3 with SVO_GUARD=1, -1 without)."""
+    return int(lib().svo_guard_selftest())
 
 
 def synth_lib():
@@ -84,6 +94,10 @@ def lib():
         L.svo_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
         L.svo_ctx_destroy.argtypes = [C.c_void_p]
         L.svo_ctx_destroy.restype = None
+        L.svo_guard_check.restype = C.c_longlong
+        L.svo_guard_check.argtypes = []
+        L.svo_guard_selftest.restype = C.c_longlong
+        L.svo_guard_selftest.argtypes = []
         L.svo_ctx_launch_count.restype = C.c_int64
         L.svo_ctx_launch_count.argtypes = [C.c_void_p]
         L.svo_ctx_stage_ms.restype = C.c_float

@@ -265,10 +265,10 @@ int launch_match_frontend(svo_ctx* c, int first, int ring, int n_frames, int ski
 
 int svo_ensure_scratch(svo_ctx* c, size_t bytes) {
     if (c->scratch_bytes >= bytes) return SVO_OK;
-    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_scratch) svo_dev_free(c->d_scratch);
     c->d_scratch = nullptr;
     c->scratch_bytes = 0;
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_scratch, bytes));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_scratch, bytes));
     c->scratch_bytes = bytes;
     return SVO_OK;
 }

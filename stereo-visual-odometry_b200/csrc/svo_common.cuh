@@ -303,6 +303,16 @@ int svo_check_flags(svo_ctx* c, const SlotMap& map, int n_img);
 int svo_ensure_scratch(svo_ctx* c, size_t bytes);
 int svo_standalone_guard(svo_ctx* c);
 
+// ---- device allocations -------------------------------------------------------------------------------------------------------
+// Every device buffer of the library comes from svo_dev_malloc.  With SVO_GUARD=1 in the environment each buffer gets a 4 KB band
+// of 0xA5 bytes on both sides and svo_guard_check() (C ABI, debug) counts the band bytes that changed: the write-overrun check the
+// GPU tests run (the pool's compute-sanitizer is closed).  Without the variable it is plain cudaMalloc / cudaFree.
+cudaError_t svo_dev_malloc_bytes(void** p, size_t bytes);
+cudaError_t svo_dev_free(void* p);
+template <class T>
+inline cudaError_t svo_dev_malloc(T** p, size_t bytes) { return svo_dev_malloc_bytes(reinterpret_cast<void**>(p), bytes); }
+
+
 // host helpers
 int svo_layout(svo_ctx* c, int w, int h);
 size_t svo_align(size_t v, size_t a);

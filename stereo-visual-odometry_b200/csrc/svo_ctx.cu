@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include <cuda.h>
 
@@ -20,6 +22,99 @@ static const int8_t kBriefPattern[1024] = {
 
 size_t svo_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+
+// ---- device allocator with optional guard bands (SVO_GUARD=1; see svo_common.cuh) ------------------------------------------------
+namespace {
+constexpr size_t kGuard = 4096;
+constexpr unsigned char kGuardByte = 0xA5;
+struct GuardedBuf { void* raw; size_t bytes; int device; };
+std::mutex g_guard_mu;
+std::map<void*, GuardedBuf> g_guarded;  // user pointer -> allocation
+bool guard_on() {
+    static const bool on = [] { const char* e = getenv("SVO_GUARD"); return e && *e && *e != '0'; }();
+    return on;
+}
+}  // namespace
+
+cudaError_t svo_dev_malloc_bytes(void** p, size_t bytes) {
+    if (!guard_on()) return cudaMalloc(p, bytes);
+    const size_t body = svo_align(std::max<size_t>(bytes, 1), 256);  // the rear band starts at the next 256-byte boundary behind the buffer
+    void* raw = nullptr;
+    cudaError_t e = cudaMalloc(&raw, body + 2 * kGuard);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemset(raw, kGuardByte, body + 2 * kGuard)) != cudaSuccess) {  // the slack between bytes and body counts as band too
+        cudaFree(raw);
+        return e;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *p = static_cast<unsigned char*>(raw) + kGuard;
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    g_guarded[*p] = GuardedBuf{raw, bytes, dev};
+    return cudaSuccess;
+}
+
+cudaError_t svo_dev_free(void* p) {
+    if (!guard_on() || !p) return cudaFree(p);
+    void* raw = p;
+    {
+        std::lock_guard<std::mutex> lk(g_guard_mu);
+        auto it = g_guarded.find(p);
+        if (it != g_guarded.end()) {
+            raw = it->second.raw;
+            g_guarded.erase(it);
+        }
+    }
+    return cudaFree(raw);
+}
+
+// Number of guard-band bytes (front band, slack behind the buffer, rear band) of all live buffers that no longer hold the fill
+// value; -1 when the library runs without SVO_GUARD.  Synchronises the devices it reads.
+extern "C" long long svo_guard_check(void) {
+    if (!guard_on()) return -1;
+    std::vector<std::pair<void*, GuardedBuf>> live;
+    {
+        std::lock_guard<std::mutex> lk(g_guard_mu);
+        live.assign(g_guarded.begin(), g_guarded.end());
+    }
+    int keep = 0;
+    cudaGetDevice(&keep);
+    long long bad = 0;
+    std::vector<unsigned char> h;
+    for (const auto& kv : live) {
+        const GuardedBuf& b = kv.second;
+        const size_t body = svo_align(std::max<size_t>(b.bytes, 1), 256);
+        cudaSetDevice(b.device);
+        cudaDeviceSynchronize();
+        const unsigned char* raw = static_cast<const unsigned char*>(b.raw);
+        const size_t rear = body - b.bytes + kGuard;
+        h.resize(kGuard + rear);
+        if (cudaMemcpy(h.data(), raw, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(h.data() + kGuard, raw + kGuard + b.bytes, rear, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -2;
+        long long n = 0;
+        for (unsigned char v : h) n += v != kGuardByte;
+        if (n) fprintf(stderr, "svo_guard_check: %lld guard bytes overwritten around a buffer of %zu bytes\n", n, b.bytes);
+        bad += n;
+    }
+    cudaSetDevice(keep);
+    return bad;
+}
+
+// Positive control of the guard bands: overruns a scratch buffer of 1000 bytes by one byte in front and two behind on purpose and
+// returns what svo_guard_check() sees for it (3 with SVO_GUARD=1, -1 without); the buffer is released again.
+extern "C" long long svo_guard_selftest(void) {
+    if (!guard_on()) return -1;
+    const long long before = svo_guard_check();
+    unsigned char* p = nullptr;
+    if (before < 0 || svo_dev_malloc(&p, 1000) != cudaSuccess) return -2;
+    cudaMemset(p - 1, 0, 1);
+    cudaMemset(p + 1000, 0, 2);
+    const long long after = svo_guard_check();
+    svo_dev_free(p);
+    return after < 0 ? after : after - before;
+}
 
 extern "C" int svo_abi_version(void) { return SVO_ABI_VERSION; }
 
@@ -57,7 +152,7 @@ static void free_layout(svo_ctx* c) {
                      (void**)&c->d_orb_pts,  (void**)&c->d_norb,      (void**)&c->d_lkf_pts,  (void**)&c->d_nlkf,
                      (void**)&c->d_ptiles,   (void**)&c->d_orb_xyz,   (void**)&c->d_lkf_xyz,   (void**)&c->d_tile_pos,  (void**)&c->d_lkderiv};
     for (void** p : ptrs) {
-        if (*p) cudaFree(*p);
+        if (*p) svo_dev_free(*p);
         *p = nullptr;
     }
     c->cur_w = c->cur_h = 0;
@@ -70,12 +165,12 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_layout(c);
-    if (c->d_pattern) cudaFree(c->d_pattern);
-    if (c->d_scratch) cudaFree(c->d_scratch);
-    if (c->d_flag_accum) cudaFree(c->d_flag_accum);
-    if (c->d_xdesc) cudaFree(c->d_xdesc);
-    if (c->d_xpop) cudaFree(c->d_xpop);
-    if (c->d_xslots) cudaFree(c->d_xslots);
+    if (c->d_pattern) svo_dev_free(c->d_pattern);
+    if (c->d_scratch) svo_dev_free(c->d_scratch);
+    if (c->d_flag_accum) svo_dev_free(c->d_flag_accum);
+    if (c->d_xdesc) svo_dev_free(c->d_xdesc);
+    if (c->d_xpop) svo_dev_free(c->d_xpop);
+    if (c->d_xslots) svo_dev_free(c->d_xslots);
     if (c->d2h_stream) {
         cudaStreamSynchronize(c->d2h_stream);
         cudaStreamDestroy(c->d2h_stream);
@@ -84,7 +179,7 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         for (int i = 0; i < 2; ++i) {
-            if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+            if (c->d_stage[i]) svo_dev_free(c->d_stage[i]);
             cudaEventDestroy(c->ev_copy[i]);
             cudaEventDestroy(c->ev_repitch[i]);
         }
@@ -210,7 +305,7 @@ int svo_orb_configure_impl(svo_ctx* c, int nfeatures, float scaleFactor, int nle
         }
     }
     if (!c->d_pattern) {
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_pattern, sizeof(kBriefPattern)));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_pattern, sizeof(kBriefPattern)));
         SVO_CUDA_TRY(c, cudaMemcpy(c->d_pattern, kBriefPattern, sizeof(kBriefPattern), cudaMemcpyHostToDevice));
     }
     c->configured = true;
@@ -293,7 +388,7 @@ int svo_layout(svo_ctx* c, int w, int h) {
         G.patch_size = (int)(31 * c->scale[l]);
     }
     c->pyr_bytes = total + 4096;  // slack: vector loads may run past the last row
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_pyr, c->pyr_bytes));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_pyr, c->pyr_bytes));
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_pyr, 0, c->pyr_bytes, c->stream));
     for (int l = 0; l < L; ++l) g.lvl[l].base = c->d_pyr + lvl_off[l];
 
@@ -380,7 +475,7 @@ int svo_layout(svo_ctx* c, int w, int h) {
             }
         }
         host.resize(svo_align(host.size() + 16, 16), 0);
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_tables, host.size()));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_tables, host.size()));
         SVO_CUDA_TRY(c, cudaMemcpy(c->d_tables, host.data(), host.size(), cudaMemcpyHostToDevice));
         for (int l = 1; l < L; ++l) {
             g.lvl[l].xofs = (const int*)((uint8_t*)c->d_tables + off_x[l]);
@@ -502,7 +597,7 @@ int svo_layout(svo_ctx* c, int w, int h) {
                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r == CUDA_SUCCESS) {
                     c->n_ptiles = (int)c->ptiles.size();
-                    SVO_CUDA_TRY(c, cudaMalloc(&c->d_ptiles, sizeof(PyrTile) * c->n_ptiles));
+                    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_ptiles, sizeof(PyrTile) * c->n_ptiles));
                     SVO_CUDA_TRY(c, cudaMemcpy(c->d_ptiles, c->ptiles.data(), sizeof(PyrTile) * c->n_ptiles, cudaMemcpyHostToDevice));
                     c->fused_pyr = true;
                 }
@@ -600,21 +695,21 @@ int svo_layout(svo_ctx* c, int w, int h) {
     if (c->octree_ncap > 4096) return c->fail(SVO_ERR_INVALID, "per-level feature quota above 4092 is not supported");
 
     if (c->n_tiles) {
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_tiles, sizeof(FastTile) * c->n_tiles));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_tiles, sizeof(FastTile) * c->n_tiles));
         SVO_CUDA_TRY(c, cudaMemcpy(c->d_tiles, c->tiles.data(), sizeof(FastTile) * c->n_tiles, cudaMemcpyHostToDevice));
     }
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_tile_buf, sizeof(uint32_t) * std::max<size_t>(1, (size_t)c->tile_buf_per_slot * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_tile_cnt, sizeof(int) * std::max<size_t>(1, (size_t)c->n_tiles * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_tile_pos, sizeof(int) * std::max<size_t>(1, (size_t)c->n_tiles * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_cand, sizeof(uint32_t) * std::max<size_t>(1, (size_t)c->cand_per_slot * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_knode, sizeof(uint16_t) * std::max<size_t>(1, (size_t)c->cand_per_slot * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_ncand, sizeof(int) * SVO_MAX_LEVELS * S));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkp, sizeof(uint32_t) * std::max<size_t>(1, (size_t)c->lkp_per_slot * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_nlkp, sizeof(int) * SVO_MAX_LEVELS * S));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_kps, sizeof(svo_keypoint) * std::max<size_t>(1, (size_t)c->kp_cap * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_desc, std::max<size_t>(1, (size_t)32 * c->kp_cap * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_nkp, sizeof(int) * S));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_flags, sizeof(int) * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_tile_buf, sizeof(uint32_t) * std::max<size_t>(1, (size_t)c->tile_buf_per_slot * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_tile_cnt, sizeof(int) * std::max<size_t>(1, (size_t)c->n_tiles * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_tile_pos, sizeof(int) * std::max<size_t>(1, (size_t)c->n_tiles * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_cand, sizeof(uint32_t) * std::max<size_t>(1, (size_t)c->cand_per_slot * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_knode, sizeof(uint16_t) * std::max<size_t>(1, (size_t)c->cand_per_slot * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_ncand, sizeof(int) * SVO_MAX_LEVELS * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_lkp, sizeof(uint32_t) * std::max<size_t>(1, (size_t)c->lkp_per_slot * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_nlkp, sizeof(int) * SVO_MAX_LEVELS * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_kps, sizeof(svo_keypoint) * std::max<size_t>(1, (size_t)c->kp_cap * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_desc, std::max<size_t>(1, (size_t)32 * c->kp_cap * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_nkp, sizeof(int) * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_flags, sizeof(int) * S));
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_ncand, 0, sizeof(int) * SVO_MAX_LEVELS * S, c->stream));
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nlkp, 0, sizeof(int) * SVO_MAX_LEVELS * S, c->stream));
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nkp, 0, sizeof(int) * S, c->stream));

@@ -39,7 +39,7 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
     void** ptrs[] = {(void**)&c->d_lkderiv,  (void**)&c->d_lkpyr,    (void**)&c->d_ftiles,  (void**)&c->d_ftile_buf, (void**)&c->d_ftile_cnt, (void**)&c->d_fast_kps,
                      (void**)&c->d_nfast,    (void**)&c->d_lk_pts,  (void**)&c->d_lk_status, (void**)&c->d_lk_err};
     for (void** p : ptrs) {
-        if (*p) cudaFree(*p);
+        if (*p) svo_dev_free(*p);
         *p = nullptr;
     }
     c->aux_ready = false;
@@ -70,7 +70,7 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
         c->lk[l] = padded(lw, lh, off[l]);
         c->lk_levels = l + 1;
     }
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkpyr, total + 4096));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_lkpyr, total + 4096));
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_lkpyr, 0, total + 4096, c->stream));
     c->lkp0.base = c->d_lkpyr + off[0] + (size_t)SVO_LK_PADY * c->lkp0.pitch + SVO_LK_PADX;
     for (int l = 1; l < c->lk_levels; ++l) c->lk[l].base = c->d_lkpyr + off[l] + (size_t)SVO_LK_PADY * c->lk[l].pitch + SVO_LK_PADX;
@@ -91,7 +91,7 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
             dtotal += svo_align((size_t)d.plane * S, 256);
             c->lkd[l] = d;
         }
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkderiv, dtotal + 4096));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_lkderiv, dtotal + 4096));
         SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_lkderiv, 0, dtotal + 4096, c->stream));
         for (int l = 0; l < c->lk_levels; ++l) c->lkd[l].base = c->d_lkderiv + doff[l] + (size_t)SVO_LK_PADY * c->lkd[l].pitch + (size_t)SVO_LK_PADX * 4;
     }
@@ -117,17 +117,17 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
     c->ftile_buf_per_slot = boff;
     c->pt_cap = std::max(pt_cap, 256);
     if (c->n_ftiles) {
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_ftiles, sizeof(FastTile) * c->n_ftiles));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_ftiles, sizeof(FastTile) * c->n_ftiles));
         SVO_CUDA_TRY(c, cudaMemcpy(c->d_ftiles, c->ftiles.data(), sizeof(FastTile) * c->n_ftiles, cudaMemcpyHostToDevice));
     }
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_ftile_buf, sizeof(uint32_t) * std::max<size_t>(1, (size_t)boff * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_ftile_cnt, sizeof(int) * std::max<size_t>(1, (size_t)c->n_ftiles * S)));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_fast_kps, sizeof(svo_keypoint) * (size_t)c->pt_cap * S));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_nfast, sizeof(int) * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_ftile_buf, sizeof(uint32_t) * std::max<size_t>(1, (size_t)boff * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_ftile_cnt, sizeof(int) * std::max<size_t>(1, (size_t)c->n_ftiles * S)));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_fast_kps, sizeof(svo_keypoint) * (size_t)c->pt_cap * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_nfast, sizeof(int) * S));
     SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nfast, 0, sizeof(int) * S, c->stream));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_pts, sizeof(float) * 2 * 5 * (size_t)c->pt_cap * S));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_status, (size_t)4 * c->pt_cap * S));
-    SVO_CUDA_TRY(c, cudaMalloc(&c->d_lk_err, sizeof(float) * 4 * (size_t)c->pt_cap * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_lk_pts, sizeof(float) * 2 * 5 * (size_t)c->pt_cap * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_lk_status, (size_t)4 * c->pt_cap * S));
+    SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_lk_err, sizeof(float) * 4 * (size_t)c->pt_cap * S));
     c->aux_ready = true;
     return SVO_OK;
 }
@@ -212,16 +212,16 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     if (mode & SVO_MODE_ORB) {
         void** ptrs[] = {(void**)&c->d_match, (void**)&c->d_xdesc, (void**)&c->d_xpop, (void**)&c->d_xslots};
         for (void** p : ptrs) {
-            if (*p) cudaFree(*p);
+            if (*p) svo_dev_free(*p);
             *p = nullptr;
         }
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_match, sizeof(int) * 4 * (size_t)c->kp_cap * c->fe_ring));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_match, sizeof(int) * 4 * (size_t)c->kp_cap * c->fe_ring));
         c->match_mma = getenv("SVO_MATCH_POPC") == nullptr;
         if (c->match_mma) {
-            SVO_CUDA_TRY(c, cudaMalloc(&c->d_xdesc, (size_t)256 * c->kp_cap * c->max_images));
-            SVO_CUDA_TRY(c, cudaMalloc(&c->d_xpop, sizeof(int) * (size_t)c->kp_cap * c->max_images));
+            SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_xdesc, (size_t)256 * c->kp_cap * c->max_images));
+            SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_xpop, sizeof(int) * (size_t)c->kp_cap * c->max_images));
             c->xslots_cap = (size_t)2 * max_frames;
-            SVO_CUDA_TRY(c, cudaMalloc(&c->d_xslots, sizeof(int) * c->xslots_cap));
+            SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_xslots, sizeof(int) * c->xslots_cap));
         }
     }
     if (!c->copy_stream) {
@@ -233,34 +233,34 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
     }
     SVO_CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
     for (int i = 0; i < 2; ++i) {
-        if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+        if (c->d_stage[i]) svo_dev_free(c->d_stage[i]);
         c->d_stage[i] = nullptr;
         c->ev_repitch_valid[i] = false;
     }
     c->stage_bytes = 2 * svo_align((size_t)max_frames * h * (2 * (size_t)w), 256);  // 2 sides, stride up to 2 x width
-    for (int i = 0; i < 2; ++i) SVO_CUDA_TRY(c, cudaMalloc(&c->d_stage[i], c->stage_bytes));
+    for (int i = 0; i < 2; ++i) SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_stage[i], c->stage_bytes));
     c->stage_idx = 0;
     {
         void** ptrs[] = {(void**)&c->d_orb_pts, (void**)&c->d_norb, (void**)&c->d_lkf_pts, (void**)&c->d_nlkf, (void**)&c->d_orb_xyz, (void**)&c->d_lkf_xyz};
         for (void** p : ptrs) {
-            if (*p) cudaFree(*p);
+            if (*p) svo_dev_free(*p);
             *p = nullptr;
         }
     }
     if (mode & SVO_MODE_ORB) {
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_orb_pts, sizeof(float) * 2 * 3 * (size_t)c->kp_cap * c->fe_ring));
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_norb, sizeof(int) * c->fe_ring));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_orb_pts, sizeof(float) * 2 * 3 * (size_t)c->kp_cap * c->fe_ring));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_norb, sizeof(int) * c->fe_ring));
         SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_norb, 0, sizeof(int) * c->fe_ring, c->stream));
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_orb_xyz, sizeof(float) * 3 * (size_t)c->kp_cap * c->fe_ring));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_orb_xyz, sizeof(float) * 3 * (size_t)c->kp_cap * c->fe_ring));
     }
     if (mode & SVO_MODE_LK) {
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkf_pts, sizeof(float) * 2 * 5 * (size_t)c->pt_cap * c->fe_ring));
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_nlkf, sizeof(int) * c->fe_ring));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_lkf_pts, sizeof(float) * 2 * 5 * (size_t)c->pt_cap * c->fe_ring));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_nlkf, sizeof(int) * c->fe_ring));
         SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_nlkf, 0, sizeof(int) * c->fe_ring, c->stream));
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_lkf_xyz, sizeof(float) * 3 * (size_t)c->pt_cap * c->fe_ring));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_lkf_xyz, sizeof(float) * 3 * (size_t)c->pt_cap * c->fe_ring));
     }
     if (!c->d_flag_accum) {
-        SVO_CUDA_TRY(c, cudaMalloc(&c->d_flag_accum, sizeof(int)));
+        SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_flag_accum, sizeof(int)));
         SVO_CUDA_TRY(c, cudaMemsetAsync(c->d_flag_accum, 0, sizeof(int), c->stream));
     }
     c->fe_mode = mode;

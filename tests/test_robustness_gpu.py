@@ -278,3 +278,18 @@ def test_standalone_device_filters_equal_oracle(pkg, orc):
     for g, o in zip(out, (p0, p1, p2, p3, p0r)):
         assert np.array_equal(g, o[keep])
     ctx.close()
+
+
+def test_no_kernel_writes_outside_its_buffers():
+    """SVO_GUARD=1: every device buffer of the library sits between two 4 KB guard bands (svo_dev_malloc); after the whole C ABI has
+    run at awkward sizes (tests/run_guarded.py) no band byte may have changed.  The write-overrun check of this suite (the pool's
+    compute-sanitizer is closed)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, SVO_GUARD="1")
+    r = subprocess.run([sys.executable, os.path.join(here, "run_guarded.py")], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    last = r.stdout.strip().splitlines()[-1].split()
+    assert last[0] == "GUARD" and int(last[1]) == 0 and int(last[2]) > 50
