@@ -93,6 +93,7 @@ struct LkParams {
     int n_fixed;
     int max_iter;
     double eps2;
+    float eps2_lo, eps2_hi;  // eps2 * (1 -/+ 1e-6): outside this band the float value of |delta|^2 decides like the double one
     float min_eig;
     int want_err;
     int pt_cap;
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
         }
         int iw00, iw01, iw10, iw11;
         weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), iw00, iw01, iw10, iw11);
-        uint32_t Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16), Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
+        uint32_t Wtop = __byte_perm((uint32_t)iw00, (uint32_t)iw01, 0x5410), Wbot = __byte_perm((uint32_t)iw10, (uint32_t)iw11, 0x5410);
 
         int a11 = 0, a12 = 0, a22 = 0;
         if (DERIV) {
@@ -534,13 +535,13 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
         int tx = INT_MIN, ty = INT_MIN;  // origin of the staged next-image tile (none yet: the tile holds the previous image)
         for (int j = 0; j < P.max_iter; ++j) {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
-            if (inx < -WIN || inx >= G.w || iny < -WIN || iny >= G.h) {
+            if ((unsigned)inx + (unsigned)WIN >= (unsigned)(G.w + WIN) || (unsigned)iny + (unsigned)WIN >= (unsigned)(G.h + WIN)) {  // outside [-WIN, size)
                 if (level == 0) status = 0;
                 break;
             }
             weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
-            Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16);
-            Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
+            Wtop = __byte_perm((uint32_t)iw00, (uint32_t)iw01, 0x5410);
+            Wbot = __byte_perm((uint32_t)iw10, (uint32_t)iw11, 0x5410);
             if (inx != tx || iny != ty) {  // sub-pixel steps usually stay in the same integer cell: the staged tile is still valid
                 __syncwarp();              // the previous tile (and, in the first iteration, the template stores) are complete
                 stage_tile(tile, J, G.pitch, inx, iny, lane);
@@ -577,8 +578,13 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             ny = __fadd_rn(ny, dy);
             outx = __fadd_rn(nx, half);
             outy = __fadd_rn(ny, half);
-            if ((double)dx * (double)dx + (double)dy * (double)dy <= P.eps2) break;
-            if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+            // OpenCV: delta.ddot(delta) <= epsilon in double.  The float value (three roundings, < 3e-7 relative) decides the same
+            // way unless it lies within 1e-6 of the threshold; only then the double expression is evaluated (NaN ends up there too)
+            const float d2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+            if (d2 < P.eps2_lo) break;
+            if (!(d2 > P.eps2_hi) && (double)dx * (double)dx + (double)dy * (double)dy <= P.eps2) break;
+            // (double)|v| < 0.01 for a float v  <=>  |v| <= 0.01f: 0.01f is the largest float below 0.01
+            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
                 outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f));
                 outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
                 break;
@@ -595,8 +601,8 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 status = 0;
             } else if (P.want_err) {
                 weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), iw00, iw01, iw10, iw11);
-                Wtop = ((uint32_t)iw00 & 0xFFFFu) | ((uint32_t)iw01 << 16);
-                Wbot = ((uint32_t)iw10 & 0xFFFFu) | ((uint32_t)iw11 << 16);
+                Wtop = __byte_perm((uint32_t)iw00, (uint32_t)iw01, 0x5410);
+                Wbot = __byte_perm((uint32_t)iw10, (uint32_t)iw11, 0x5410);
                 if (inx != tx || iny != ty) {
                     __syncwarp();
                     stage_tile(tile, J, G.pitch, inx, iny, lane);
@@ -681,6 +687,8 @@ static void fill_params(svo_ctx* c, LkParams& P, int max_level, int max_iter, do
     P.max_iter = std::min(std::max(max_iter, 0), 100);
     eps = std::min(std::max(eps, 0.), 10.);
     P.eps2 = eps * eps;
+    P.eps2_lo = (float)(P.eps2 * (1.0 - 1e-6));
+    P.eps2_hi = (float)(P.eps2 * (1.0 + 1e-6));
     P.min_eig = (float)min_eig;
     P.pt_cap = c->pt_cap;
 }
