@@ -24,6 +24,10 @@ namespace {
 
 constexpr int WIN = SVO_LK_WIN;  // 21
 constexpr int LW = 1;            // warps (points) per CTA
+#ifndef SVO_LK_TWO_PHASE
+#define SVO_LK_TWO_PHASE 1
+#endif
+constexpr bool INSIDE_TWO_PHASE = SVO_LK_TWO_PHASE != 0;  // setup of windows inside the image: two phases through shared memory (0: column-lane form)
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     // |offset| <= WIN beyond the image and n > WIN on every level, so one reflection suffices
@@ -236,7 +240,14 @@ constexpr int NROUND = 2;        // owns strips (lane) and (lane + 32): 14 pixel
 // skewed by 3 words so that the three segments a warp reads at once fall into different banks; it shares the image tile's memory
 __host__ __device__ constexpr int drow_off(int r) { return r * 24 + (r / 7) * 3; }
 constexpr int DTILE_BYTES = (drow_off(21) + 24) * 4;
-constexpr int TILE_AREA = DTILE_BYTES > TILE_BYTES ? ((DTILE_BYTES + 63) / 64) * 64 : TILE_BYTES;
+// interpolated-image array of the setup (inside form): 23 rows x 23 words, every 7-row segment skewed by 10 words (7 * 23 + 10 = 11 mod 32:
+// the strips (column x, rows 7 sg ..) a warp reads at once -- x = 0..10, sg = 0..2 -- fall into 32 different banks); it takes the
+// image tile's place while the previous image's own tile sits in the (still unused) template area
+__host__ __device__ constexpr int irow_off(int r) { return r * 23 + (r / 7) * 10; }
+constexpr int ITILE_BYTES = (irow_off(22) + 23) * 4;
+constexpr int TILE_MAX = DTILE_BYTES > ITILE_BYTES ? (DTILE_BYTES > TILE_BYTES ? DTILE_BYTES : TILE_BYTES) : (ITILE_BYTES > TILE_BYTES ? ITILE_BYTES : TILE_BYTES);
+constexpr int TILE_AREA = ((TILE_MAX + 63) / 64) * 64;
+static_assert(TILE_BYTES <= 32 * SEG * 8, "the previous image's tile must fit below the second round of the template area");
 constexpr int WARP_SMEM = TILE_AREA + 32 * NROUND * SEG * 8;
 
 __device__ __forceinline__ int pair_off(int c) {  // byte offset in a tile row of the aligned u16 holding tile bytes (c, c+1)
@@ -296,6 +307,12 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
     for (int sr = 0; sr < NROUND; ++sr) {
         const int g = min(lane + 32 * sr, 62), x = g / 3, sg = g - 3 * x;
         offJ[sr] = row_off(SEG * sg) + pair_off(x);
+    }
+    int offB[NROUND];  // setup, inside form: word offset of the strip's first entry (column x, row 7 * seg) in the interpolated-image array
+#pragma unroll
+    for (int sr = 0; sr < NROUND; ++sr) {
+        const int g = min(lane + 32 * sr, 62), x = g / 3, sg = g - 3 * x;
+        offB[sr] = irow_off(SEG * sg) + x;
     }
     // setup (column-lane form): where this lane's column x = lane - 1 stores row y: base of segment y / 7, plus (y % 7) * 32
     int tbase[3];
@@ -361,6 +378,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
         uint32_t Wtop = __byte_perm((uint32_t)iw00, (uint32_t)iw01, 0x5410), Wbot = __byte_perm((uint32_t)iw10, (uint32_t)iw11, 0x5410);
 
         int a11 = 0, a12 = 0, a22 = 0;
+        bool all_lanes = DERIV;
         if (DERIV) {
             // ---- MEASURED ALTERNATIVE (SVO_LK_DERIV=1; off by default): template from the image plane and a precomputed Scharr plane
             // (OpenCV's own order: derivI first, then the bilinear interpolation of I, Ix, Iy), in the iterations' strip layout: all 32
@@ -430,12 +448,65 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             }
         } else {
         // ---- previous image: tile byte 0 = column ipx - 1, tile row 0 = image row ipy - 1
-        __syncwarp();
-        stage_tile(tile, I, G.pitch, ipx - 1, ipy - 1, lane);
-        __syncwarp();
         // every gradient tap (columns ipx .. ipx+21, rows ipy .. ipy+21) inside the image?  (warp-uniform)
         const bool inside = ipx >= 0 && ipx + WIN < G.w && ipy >= 0 && ipy + WIN < G.h;
-        if (inside) {
+        const bool two_phase = INSIDE_TWO_PHASE && inside;
+        uint8_t* itile = two_phase ? reinterpret_cast<uint8_t*>(tmpl) : tile;  // (two-phase form: the tile area receives Ib)
+        __syncwarp();
+        stage_tile(itile, I, G.pitch, ipx - 1, ipy - 1, lane);
+        __syncwarp();
+        if (two_phase) {
+            all_lanes = true;
+            // Inside form in two phases through shared memory (all 32 lanes busy in the second):
+            //   A  lane = tile column c <= 22 walks down the rows: Ib(r, c) = interpolated image, un-descaled, + 256 (the rounding
+            //      constant of I's descale; it cancels in both Scharr sums)                              -> ibw[irow_off(r) + c]
+            //   B  the iterations' strip layout (lane = column x, 7 rows; two strips per lane): per row of Ib three loads (columns
+            //      x, x+1, x+2), dH = R - L, S = 3 (L + R) + 10 C; per pixel Ix = 3 (dH(y) + dH(y+2)) + 10 dH(y+1),
+            //      Iy = S(y+2) - S(y), I from C(y+1).  ~420 instead of ~540 warp-instructions of the column-lane form below, whose
+            //      24 active lanes spend 23 rows on 21 rows of output.
+            int* ibw = reinterpret_cast<int*>(tile);
+            {
+                const uint8_t* tp = itile + pair_off(min(lane, 22));
+                int* iw = ibw + min(lane, 22);
+                int top = dp2(Wtop, lds_u16(tp), 256);
+#pragma unroll
+                for (int r = 1; r < TROWS; ++r) {
+                    const uint32_t pr = lds_u16(tp + row_off(r));
+                    const int ib = dp2(Wbot, pr, top);
+                    top = dp2(Wtop, pr, 256);
+                    if (lane < 23) iw[irow_off(r - 1)] = ib;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int sr = 0; sr < NROUND; ++sr) {
+                const int* ip = ibw + offB[sr];
+                uint2* to = tmpl + sr * SEG * 32 + lane;
+                const bool real = lane + 32 * sr < 63;
+                int dHa = 0, dHb = 0, Sa = 0, Sb = 0, Cb = 0;
+#pragma unroll
+                for (int j = 0; j < SEG + 2; ++j) {
+                    const int o = irow_off(j);  // relative to the strip's first row (7 sg): 23 words per row, rows 7 and 8 carry the next segment's skew
+                    const int L = ip[o], C = ip[o + 1], R = ip[o + 2];
+                    const int dH = R - L, S = 3 * (L + R) + 10 * C;
+                    if (j >= 2) {  // window row 7 sg + j - 2
+                        const int ixv = (3 * (dHa + dH) + 10 * dHb + (1 << 13)) >> 14;
+                        const int iyv = (S - Sa + (1 << 13)) >> 14;
+                        if (real) {
+                            to[(j - 2) * 32] = make_uint2((uint32_t)(256 - (Cb & ~511)), __byte_perm((uint32_t)ixv, (uint32_t)iyv, 0x5410));
+                            a11 += ixv * ixv;
+                            a12 += ixv * iyv;
+                            a22 += iyv * iyv;
+                        }
+                    }
+                    dHa = dHb;
+                    dHb = dH;
+                    Sa = Sb;
+                    Sb = S;
+                    Cb = C;
+                }
+            }
+        } else if (inside) {
             //   Ib(r) = interpolated image at tile row r (rows 0..22), exact and un-descaled
             //   Ix(y) = 3 (dH(y) + dH(y+2)) + 10 dH(y+1),  dH = Ib(x+1) - Ib(x-1)
             //   Iy(y) = S(y+2) - S(y),                       S  = 3 (Ib(x-1) + Ib(x+1)) + 10 Ib(x)
@@ -514,7 +585,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             }
         }
         }  // !DERIV
-        const bool alane = DERIV || wlane;  // DERIV: every lane holds window pixels
+        const bool alane = all_lanes || wlane;  // strip forms: every lane holds window pixels
         const long long sA11 = warp_sum64(alane ? a11 : 0), sA12 = warp_sum64(alane ? a12 : 0), sA22 = warp_sum64(alane ? a22 : 0);
         const float FLT_SCALE = 1.f / (1 << 20);
         const float A11 = __fmul_rn((float)sA11, FLT_SCALE), A12 = __fmul_rn((float)sA12, FLT_SCALE), A22 = __fmul_rn((float)sA22, FLT_SCALE);
