@@ -24,10 +24,6 @@ namespace {
 
 constexpr int WIN = SVO_LK_WIN;  // 21
 constexpr int LW = 1;            // warps (points) per CTA
-#ifndef SVO_LK_TWO_PHASE
-#define SVO_LK_TWO_PHASE 1
-#endif
-constexpr bool INSIDE_TWO_PHASE = SVO_LK_TWO_PHASE != 0;  // setup of windows inside the image: two phases through shared memory (0: column-lane form)
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     // |offset| <= WIN beyond the image and n > WIN on every level, so one reflection suffices
@@ -275,11 +271,11 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restr
 }
 
 // One warp per point, all pyramid levels in one launch.
-//  setup (previous image): lane l owns column ipx - 1 + l of the staged 24 x 24 neighbourhood and walks down the rows; the
-//    Scharr gradient and the bilinear interpolation -- both linear with integer weights -- are commuted EXACTLY when every
-//    gradient tap lies inside the image: the image is interpolated once (Ib, un-descaled, 2 IDP.2A per row) and Scharr is
-//    applied to Ib with two shuffles per row.  Otherwise (window across the image border) the general form with OpenCV's
-//    constant-0 derivative outside the image runs.  The template (I, Ix, Iy) goes to shared memory in FLATTENED pixel order.
+//  setup (previous image): the Scharr gradient and the bilinear interpolation -- both linear with integer weights -- are commuted
+//    EXACTLY when every gradient tap lies inside the image: the staged 24 x 24 neighbourhood is interpolated once (Ib, un-descaled,
+//    2 IDP.2A per value, lane = column) into shared memory and Scharr is applied to Ib in the iterations' strip layout with all 32
+//    lanes.  Otherwise (window across the image border) the general form with OpenCV's constant-0 derivative outside the image
+//    runs (lane = column, neighbours by shuffle).  The template (I, Ix, Iy) goes to shared memory in FLATTENED pixel order.
 //  iterations (next image): the window is cut into 63 strips (21 columns x 3 segments of 7 rows), two per lane: 8 pair loads
 //    per strip (vertical reuse), and per pixel one 64-bit template load, 2 IDP.2A, one shift, two sign extensions, two IMAD.
 // All window sums are exact integers; float expressions follow OpenCV's scalar order with _rn intrinsics.
@@ -450,7 +446,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
         // ---- previous image: tile byte 0 = column ipx - 1, tile row 0 = image row ipy - 1
         // every gradient tap (columns ipx .. ipx+21, rows ipy .. ipy+21) inside the image?  (warp-uniform)
         const bool inside = ipx >= 0 && ipx + WIN < G.w && ipy >= 0 && ipy + WIN < G.h;
-        const bool two_phase = INSIDE_TWO_PHASE && inside;
+        const bool two_phase = inside;
         uint8_t* itile = two_phase ? reinterpret_cast<uint8_t*>(tmpl) : tile;  // (two-phase form: the tile area receives Ib)
         __syncwarp();
         stage_tile(itile, I, G.pitch, ipx - 1, ipy - 1, lane);
@@ -462,8 +458,8 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             //      constant of I's descale; it cancels in both Scharr sums)                              -> ibw[irow_off(r) + c]
             //   B  the iterations' strip layout (lane = column x, 7 rows; two strips per lane): per row of Ib three loads (columns
             //      x, x+1, x+2), dH = R - L, S = 3 (L + R) + 10 C; per pixel Ix = 3 (dH(y) + dH(y+2)) + 10 dH(y+1),
-            //      Iy = S(y+2) - S(y), I from C(y+1).  ~420 instead of ~540 warp-instructions of the column-lane form below, whose
-            //      24 active lanes spend 23 rows on 21 rows of output.
+            //      Iy = S(y+2) - S(y), I from C(y+1).  ~420 warp-instructions; the one-phase form it replaced (lane = column, neighbours by
+            //      shuffle: 24 active lanes spending 23 rows on 21 rows of output) took ~540 (LK chain 4.79 -> 4.68 ms).
             int* ibw = reinterpret_cast<int*>(tile);
             {
                 const uint8_t* tp = itile + pair_off(min(lane, 22));
@@ -505,37 +501,6 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                     Sb = S;
                     Cb = C;
                 }
-            }
-        } else if (inside) {
-            //   Ib(r) = interpolated image at tile row r (rows 0..22), exact and un-descaled
-            //   Ix(y) = 3 (dH(y) + dH(y+2)) + 10 dH(y+1),  dH = Ib(x+1) - Ib(x-1)
-            //   Iy(y) = S(y+2) - S(y),                       S  = 3 (Ib(x-1) + Ib(x+1)) + 10 Ib(x)
-            //   (Ib carries the rounding constant 256 of I's descale: it cancels in dH and in S(y+2) - S(y))
-            const uint8_t* tp = tile + pair_off(ccol);
-            int top = dp2(Wtop, lds_u16(tp), 256);
-            int dH0 = 0, dH1 = 0, S0 = 0, S1 = 0, ibm = 0;
-#pragma unroll
-            for (int r = 1; r < TROWS; ++r) {
-                const uint32_t pr = lds_u16(tp + row_off(r));
-                const int ib = dp2(Wbot, pr, top);  // Ib(r - 1) + 256
-                top = dp2(Wtop, pr, 256);
-                const int ibL = __shfl_up_sync(0xFFFFFFFFu, ib, 1), ibR = __shfl_down_sync(0xFFFFFFFFu, ib, 1);
-                const int dH2 = ibR - ibL, S2 = 3 * (ibL + ibR) + 10 * ib;
-                if (r >= 3) {  // window row y = r - 3: Ib rows y, y+1, y+2 are complete
-                    const int y = r - 3;
-                    const int ixv = (3 * (dH0 + dH2) + 10 * dH1 + (1 << 13)) >> 14;
-                    const int iyv = (S2 - S0 + (1 << 13)) >> 14;
-                    // 256 - 512 * descale(Ib, 9) = 256 - ((Ib + 256) & ~511); (Ix, Iy) packed by one PRMT
-                    if (wlane) tmpl[tbase[y / SEG] + (y % SEG) * 32] = make_uint2((uint32_t)(256 - (ibm & ~511)), __byte_perm((uint32_t)ixv, (uint32_t)iyv, 0x5410));
-                    a11 += ixv * ixv;
-                    a12 += ixv * iyv;
-                    a22 += iyv * iyv;
-                }
-                dH0 = dH1;
-                dH1 = dH2;
-                S0 = S1;
-                S1 = S2;
-                ibm = ib;
             }
         } else {
             // general form: Scharr gradient per image position, zero outside the image (OpenCV's constant-0 padded
