@@ -18,7 +18,7 @@ assert KP_DTYPE.itemsize == 28
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_prims.cpp", "oracle_orb.cpp", "oracle_capi.cpp", "oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_prims.cpp", "oracle_orb.cpp", "oracle_capi.cpp", "oracle_pnp.cpp", "oracle.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -353,3 +353,50 @@ def frontend_sequence(left, right, nfeatures=1000, scale_factor=1.2, nlevels=8, 
     return lib().orc_frontend_sequence(_p(left), _p(right), C.c_int(f), C.c_int(w), C.c_int(h), C.c_int(nfeatures),
                                        C.c_float(scale_factor), C.c_int(nlevels), C.c_int(ini_th), C.c_int(min_th), C.c_int(mode),
                                        C.c_int(threads))
+
+
+# ---- pose from points (oracle_pnp.cpp) -------------------------------------------------------------------------------
+def svd(a):
+    """cv2.SVDecomp for a square matrix up to 12 x 12 -> (w, u, vt)."""
+    a = np.ascontiguousarray(a, np.float64)
+    n = a.shape[0]
+    w, u, vt = np.zeros(n), np.zeros((n, n)), np.zeros((n, n))
+    lib().orc_svd(_p(a), C.c_int(n), _p(w), _p(u), _p(vt))
+    return w, u, vt
+
+
+def epnp(K, p3, p2):
+    """EPnP on all n points -> (ok, R 3x3, t 3)."""
+    K = np.ascontiguousarray(K, np.float64).reshape(9)
+    p3 = np.ascontiguousarray(p3, np.float32).reshape(-1, 3)
+    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+    R = np.zeros(9)
+    t = np.zeros(3)
+    ok = lib().orc_epnp(_p(K), _p(p3), _p(p2), C.c_int(len(p3)), _p(R), _p(t))
+    return bool(ok), R.reshape(3, 3), t
+
+
+def pnp_refine(K, p3, p2, rvec, tvec, mask=None):
+    """solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess=True) -> (rvec, tvec, LM iterations)."""
+    K = np.ascontiguousarray(K, np.float64).reshape(9)
+    p3 = np.ascontiguousarray(p3, np.float32).reshape(-1, 3)
+    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+    param = np.concatenate([np.asarray(rvec, np.float64).reshape(3), np.asarray(tvec, np.float64).reshape(3)])
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    it = lib().orc_pnp_refine(_p(K), _p(p3), _p(p2), C.c_int(len(p3)), None if m is None else _p(m), _p(param))
+    return param[:3].copy(), param[3:].copy(), it
+
+
+def pnp_ransac(K, p3, p2, iterations=500, reproj_err=0.5, confidence=0.99):
+    """cv::solvePnPRansac as called at tracking.cpp:486-488 -> dict(ok, rvec, tvec, R, mask, n_inliers, best_iter, iters)."""
+    K = np.ascontiguousarray(K, np.float64).reshape(9)
+    p3 = np.ascontiguousarray(p3, np.float32).reshape(-1, 3)
+    p2 = np.ascontiguousarray(p2, np.float32).reshape(-1, 2)
+    n = len(p3)
+    mask = np.zeros(max(n, 1), np.uint8)
+    out = np.zeros(15)
+    info = np.zeros(3, np.int32)
+    ok = lib().orc_pnp_ransac(_p(K), _p(p3), _p(p2), C.c_int(n), C.c_int(iterations), C.c_float(reproj_err), C.c_double(confidence), _p(mask),
+                              _p(out), _p(info))
+    return dict(ok=bool(ok), rvec=out[:3].copy(), tvec=out[3:6].copy(), R=out[6:].reshape(3, 3).copy(), mask=mask[:n].astype(bool),
+                n_inliers=int(info[0]), best_iter=int(info[1]), iters=int(info[2]))

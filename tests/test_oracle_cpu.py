@@ -192,3 +192,79 @@ def test_cv2_primitive_orb_equals_oracle(pkg, orc):
         k1, d1 = ref_pipeline.Cv2PrimitiveOrb(nfeat, 1.2, 8, 20, 7).extract(left)
         assert len(k0) == len(k1) and np.array_equal(k0, k1)
         assert np.array_equal(d0, d1)
+
+
+# ---- pose from points (oracle/oracle_pnp.cpp) against cv2 4.13 outputs (oracle/make_golden_pnp.py) ----------------------------
+@pytest.fixture(scope="module")
+def gold_pnp():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "cv2_pnp.npz"))
+
+
+def test_pnp_svd_matches_cv2(orc, gold_pnp):
+    g = gold_pnp
+    for i in range(6):
+        for kind in ("svd3", "svdg", "svd12"):
+            w, u, vt = orc.svd(g[f"{kind}_{i}_a"])
+            scale = g[f"{kind}_{i}_w"].max()
+            assert np.abs(w - g[f"{kind}_{i}_w"]).max() <= 1e-12 * scale, (kind, i)
+            assert np.abs(u - g[f"{kind}_{i}_u"]).max() <= 1e-9, (kind, i)   # signs and order included
+            if kind != "svd12":
+                assert np.abs(vt - g[f"{kind}_{i}_vt"]).max() <= 1e-9, (kind, i)
+
+
+def _rod(orc, r):
+    R = np.zeros(9)
+    orc.lib().orc_rodrigues(orc._p(np.ascontiguousarray(r, np.float64)), orc._p(R))
+    return R.reshape(3, 3)
+
+
+def test_pnp_epnp_matches_cv2(orc, gold_pnp):
+    g = gold_pnp
+    for k in range(int(g["epnp_count"])):
+        ok, R, t = orc.epnp(g["K"], g[f"epnp_{k}_p3"], g[f"epnp_{k}_p2"])
+        assert ok
+        assert np.abs(R - _rod(orc, g[f"epnp_{k}_r"])).max() <= 1e-9, k
+        assert np.abs(t - g[f"epnp_{k}_t"]).max() <= 1e-9, k
+    # the minimal case: the two-dimensional null space of M^T M makes about one case in seven depend on rounding noise inside
+    # the SVD (oracle_pnp.cpp header); the rest must agree
+    same = 0
+    for k in range(40):
+        ok, R, t = orc.epnp(g["K"], g[f"epnp5_{k}_p3"], g[f"epnp5_{k}_p2"])
+        same += bool(ok and np.abs(R - _rod(orc, g[f"epnp5_{k}_r"])).max() <= 1e-6 and np.abs(t - g[f"epnp5_{k}_t"]).max() <= 1e-6)
+    assert same >= 30, same
+
+
+def test_pnp_refine_matches_cv2(orc, gold_pnp):
+    g = gold_pnp
+    for k in range(6):
+        r, t, it = orc.pnp_refine(g["K"], g[f"lm_{k}_p3"], g[f"lm_{k}_p2"], np.zeros(3), np.zeros(3))
+        assert np.abs(r - g[f"lm_{k}_r"]).max() <= 1e-8 and np.abs(t - g[f"lm_{k}_t"]).max() <= 1e-8, k
+        assert 1 <= it <= 20
+
+
+def test_pnp_ransac_matches_cv2(orc, gold_pnp):
+    g = gold_pnp
+    n_scenes = int(g["ransac_count"])
+    exact = 0
+    for k in range(n_scenes):
+        res = orc.pnp_ransac(g["K"], g[f"ransac_{k}_p3"], g[f"ransac_{k}_p2"])
+        m = g[f"ransac_{k}_mask"].astype(bool)
+        assert res["ok"] == bool(g[f"ransac_{k}_ok"])
+        jac = (m & res["mask"]).sum() / max((m | res["mask"]).sum(), 1)
+        dp = max(np.abs(res["rvec"] - g[f"ransac_{k}_r"]).max(), np.abs(res["tvec"] - g[f"ransac_{k}_t"]).max())
+        if np.array_equal(m, res["mask"]):
+            exact += 1
+            assert dp <= 1e-8, (k, dp)       # same consensus set -> same refined pose
+        else:
+            assert jac >= 0.8 and dp <= 1e-2, (k, jac, dp)
+    assert exact >= n_scenes // 2, (exact, n_scenes)   # identical inlier set AND pose on the majority of the scenes
+
+
+def test_pnp_degenerate_inputs(orc, gold_pnp):
+    K = gold_pnp["K"]
+    res = orc.pnp_ransac(K, np.zeros((3, 3), np.float32), np.zeros((3, 2), np.float32))
+    assert not res["ok"] and res["n_inliers"] == 0
+    p3, p2 = gold_pnp["ransac_0_p3"][:5], gold_pnp["ransac_0_p2"][:5]
+    orc.pnp_ransac(K, p3, p2)  # n == model size: one hypothesis from points 0..4, no crash
+    res = orc.pnp_ransac(K, np.zeros((50, 3), np.float32), np.zeros((50, 2), np.float32))  # all points identical: nothing usable
+    assert not res["ok"] or res["n_inliers"] >= 5
