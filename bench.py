@@ -48,12 +48,19 @@ CONFIGS = {
 }
 
 
+KITTI_P1 = [718.856, 0, 607.1928, 0, 0, 718.856, 185.2157, 0, 0, 0, 1, 0]          # P0 / P1 of KITTI odometry sequence 00
+KITTI_P2 = [718.856, 0, 607.1928, -386.1448, 0, 718.856, 185.2157, 0, 0, 0, 1, 0]
+
+
 def workload_config(a):
     c = {"workload": f"{a.cfg['name']}: ORB({a.nfeatures} feats, 8 levels, FAST 20/7) on L+R + 2x BF-Hamming + full-frame FAST(20) + "
                      f"4-call pyrLK(21x21, 4 levels, 30 it, err computed like the reference's call), synthetic stereo sequence seed {a.seed}",
          "config": a.config, "width": a.width, "height": a.height, "frames_per_step_per_gpu": a.frames, "nfeatures": a.nfeatures,
          "l2_policy": "inputs larger than L2: each step streams a different batch of images (>= 59 MB at the smallest config) plus the "
                       "pyramid levels and scratch it writes (~250 MB per step at c1)"}
+    if getattr(a, "pnp", False):
+        c["workload"] += " + triangulation + PnP-RANSAC (500 it, 0.5 px, 0.99; EPnP hypotheses, LM refinement) on both filtered lists"
+        c["pnp"] = True
     if a.cfg["scaling"] == "strong":
         c["sweep_units"] = a.sweep_units
         c["frames_per_step_per_gpu"] = None
@@ -190,6 +197,9 @@ def run_b200(a):
     ctx.orb_configure(a.nfeatures, 1.2, 8, 20, 7)
     ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
     ctx.frontend_set_overlap(not a.no_overlap)
+    if a.pnp:  # the pose step of the reference loop (tracking.cpp:190-200): KITTI sequence-00 projection matrices
+        ctx.frontend_set_projection(KITTI_P1, KITTI_P2)
+        ctx.frontend_set_pnp(True, 500, 0.5)
     stream = torch.cuda.Stream()  # a real (non-null) stream shared by torch events and the library's kernels
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -253,6 +263,7 @@ def run_b200(a):
     # ---- e2e: host buffers in, host buffers out, through the public upload / run / download calls
     out = pkg.FrontendBuffers(B, kp_cap, pt_cap, alloc=lambda shape, dt: pinned_u8((int(np.prod(shape)) * np.dtype(dt).itemsize,)).numpy()
                               .view(dt).reshape(shape))
+    out.pnp_enabled = bool(a.pnp)
     d2h_total = [0]
     sigs = {}
 
@@ -477,6 +488,7 @@ def main():
     p.add_argument("--sweep-units", type=int, default=None, help="c5: units (stereo pairs) of the one sequence")
     p.add_argument("--sample-units", type=int, default=0, help="reference arm: stereo frames per step (0 = per-config default per core)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--pnp", action="store_true", help="also run triangulation + PnP-RANSAC on the filtered lists (SURVEY 8f rows 1-2)")
     p.add_argument("--no-overlap", action="store_true", help="run the ORB tail and the FAST + LK chain on one stream")
     a = p.parse_args()
     a.cfg = CONFIGS[a.config]

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SVO_ABI_VERSION 4
+#define SVO_ABI_VERSION 5
 
 typedef enum svo_status {
     SVO_OK = 0,
@@ -59,12 +59,12 @@ int64_t svo_ctx_launch_count(const svo_ctx* ctx);
  * svo_ctx_enable_stage_timing(ctx, 1).  Events are kept per timing slot (svo_ctx_set_timing_slot, 0..SVO_TIMING_SLOTS-1)
  * so that a bench can time K back-to-back steps without synchronising in between and read all of them afterwards.
  * stage: 0 pyramid(K1) 1 fast+cells(K2) 2 compact(K2b) 3 octree(K3) 4 angle+descriptor(K4/K5) 5 match(K6)
- *        6 fullframe-fast(K9) 7 lk-pyramid(K7) 8..11 lk-track calls 1..4 (K8).
+ *        6 fullframe-fast(K9) 7 lk-pyramid(K7) 8..11 lk-track calls 1..4 (K8) 12 pose (K13, both lists).
  * svo_ctx_stage_ms returns milliseconds, <0 if the stage did not run in that slot. */
 int svo_ctx_enable_stage_timing(svo_ctx* ctx, int on);
 int svo_ctx_set_timing_slot(svo_ctx* ctx, int slot);
 float svo_ctx_stage_ms(const svo_ctx* ctx, int slot, int stage);
-#define SVO_NUM_STAGES 12
+#define SVO_NUM_STAGES 13
 #define SVO_TIMING_SLOTS 64
 
 /* ---- ORB extractor ------------------------------------------------------------------------------------------- */
@@ -144,6 +144,21 @@ int svo_lk_chain_filter(svo_ctx* ctx, int n, float* p0, float* p1, float* p2, fl
 int svo_triangulate_points(svo_ctx* ctx, const double* proj1, const double* proj2, const float* pts1, const float* pts2,
                            int n, float* points4d, float* points3d);
 
+/* ---- pose from 3-D / 2-D correspondences ---------------------------------------------------------------------- */
+/* Replaces cv::solvePnPRansac(points3D, points2D, K, zeros(4), rvec, tvec, useExtrinsicGuess = true, iterations, reproj_error,
+ * confidence, inliers, SOLVEPNP_ITERATIVE) + cv::Rodrigues(rvec, rotation) at tracking.cpp:486-489 (OpenCV_EstimatePose_PnP), for
+ * n_problems independent lists in ONE launch (one CTA per list): 5-point EPnP hypotheses drawn with cv::RNG((uint64)-1), consensus
+ * at reproj_error pixels, RANSACUpdateNumIters, Levenberg-Marquardt refinement over the consensus set.  K: 3 x 3 row-major.
+ * Problem i: counts[i] points at pts3d + i*cap*3 / pts2d + i*cap*2.  Outputs per problem: rvec[3], tvec[3], rotation[9] (row-major,
+ * may be NULL), inlier_mask[cap] bytes (may be NULL; cv's `inliers` = the indices whose byte is 1), n_inliers (may be NULL),
+ * info[2] = {index of the winning hypothesis, hypotheses evaluated} (may be NULL), ok = solvePnPRansac's return value.
+ * ok = 0 (no model with more than 4 inliers, or fewer than 5 points): rvec = tvec = 0, rotation = identity, empty inlier set.
+ * Agreement with OpenCV: DESIGN.md section 5 (identical inlier sets and poses whenever the winning 5-point hypothesis is one whose
+ * EPnP solution does not depend on the basis OpenCV's SVD picks in an exactly singular subspace; else a close consensus set). */
+int svo_pnp_ransac(svo_ctx* ctx, const double* K, const float* pts3d, const float* pts2d, const int32_t* counts, int n_problems, int cap,
+                   int iterations, float reproj_error, double confidence, double* rvec, double* tvec, double* rotation,
+                   uint8_t* inlier_mask, int32_t* n_inliers, int32_t* info, int32_t* ok);
+
 /* ---- throughput mode: batches of consecutive stereo frames ------------------------------------------------------ */
 /* One unit of work = one new stereo frame t:
  *   SVO_MODE_ORB: operator() on left_t and right_t (Detect_MyORBFeatures, tracking.cpp:502-532), then
@@ -197,6 +212,15 @@ typedef struct svo_frontend_out {
     /* the `err` output of the four calcOpticalFlowPyrLK calls (tracking.cpp:593-618 pass it; unused by the reference afterwards):
      * 4 x pt_cap floats per frame (err1..err4), computed unless svo_frontend_set_lk_err(ctx, 0) */
     float* lk_err;
+    /* pose of frame f relative to frame f-1 from each filtered list (OpenCV_EstimatePose_PnP, tracking.cpp:464-501), filled only
+     * after svo_frontend_set_pnp(ctx, 1, ...): 16 doubles per frame = rvec[3], tvec[3], rotation[9] row-major, 1 spare;
+     * 4 ints per frame = {ok, inliers, winning hypothesis, hypotheses evaluated}; one byte per list entry = inlier flag */
+    double* orb_pose;
+    int32_t* orb_pnp_info;
+    uint8_t* orb_inlier_mask;  /* kp_cap per frame, n_orb_matched valid */
+    double* lk_pose;
+    int32_t* lk_pnp_info;
+    uint8_t* lk_inlier_mask;   /* pt_cap per frame, n_lk_matched valid */
 } svo_frontend_out;
 
 int svo_frontend_configure(svo_ctx* ctx, int w, int h, int mode, int max_frames);
@@ -213,6 +237,10 @@ int svo_frontend_set_lk_err(svo_ctx* ctx, int enable);
 /* Sensors::projMatr1_ / projMatr2_ (3x4, row-major doubles; sensors.cpp:8-24): enables the device-side triangulation of
  * the filtered lists.  Call after svo_frontend_configure(). */
 int svo_frontend_set_projection(svo_ctx* ctx, const double* proj_left, const double* proj_right);
+/* Tracking::iterationsCount_ / reprojectionError_ / confidence_ (parameter.cpp:57-59; config/default.yaml:80-82: 500, 0.5, 0.99):
+ * enables the device-side pose step on the triangulated lists (K = left 3 x 3 of proj_left, tracking.cpp:476-477).  Call after
+ * svo_frontend_set_projection(); a later svo_frontend_configure() switches it off again.  enable = 0 frees its buffers. */
+int svo_frontend_set_pnp(svo_ctx* ctx, int enable, int iterations, float reproj_error, double confidence);
 /* host images -> device (left/right: n_frames contiguous images of h rows, `stride` bytes per row) */
 int svo_frontend_upload(svo_ctx* ctx, const uint8_t* left, const uint8_t* right, int n_frames, size_t stride);
 /* blocks until the host-to-device copies of the last svo_frontend_upload() have completed (the host buffers may be reused) */

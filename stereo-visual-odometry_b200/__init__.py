@@ -24,7 +24,7 @@ assert KP_DTYPE.itemsize == 28
 SVO_OK, SVO_ERR_INVALID, SVO_ERR_CUDA, SVO_ERR_CAPACITY, SVO_ERR_NOT_CONFIGURED = 0, -1, -2, -3, -4
 MODE_ORB, MODE_LK = 1, 2
 STAGES = ["pyramid", "fast_cells", "compact", "octree", "describe", "match", "fast_full", "lk_pyramid", "lk_track1", "lk_track2",
-          "lk_track3", "lk_track4"]
+          "lk_track3", "lk_track4", "pnp"]
 TIMING_SLOTS = 64
 
 # every symbol include/svo_cuda.h declares (tests check the library exports all of them)
@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "svo_triangulate_points", "svo_frontend_upload", "svo_frontend_wait_upload", "svo_frontend_upload_dev", "svo_frontend_run", "svo_frontend_download", "svo_frontend_check",
     "svo_frontend_discard", "svo_frontend_batch", "svo_source_open", "svo_source_frame_count", "svo_source_is_pinned", "svo_source_next",
     "svo_source_error", "svo_source_close", "svo_write_pgm", "svo_write_png", "svo_orb_match_filter", "svo_lk_chain_filter", "svo_guard_check", "svo_guard_selftest",
+    "svo_pnp_ransac", "svo_frontend_set_pnp",
 ]
 SYNTH_SYMBOLS = ["svo_synth_stereo_frame"]  # exported by libsvo_synth.so
 
@@ -52,7 +53,8 @@ class FrontendOut(C.Structure):
         "kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
         "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status",
         "orb_t2_left", "orb_t1_left", "orb_t1_right", "n_orb_matched", "lkf_t1_left", "lkf_t1_right", "lkf_t2_right", "lkf_t2_left",
-        "n_lk_matched", "orb_points3d", "lk_points3d", "lk_err")]
+        "n_lk_matched", "orb_points3d", "lk_points3d", "lk_err", "orb_pose", "orb_pnp_info", "orb_inlier_mask", "lk_pose", "lk_pnp_info",
+        "lk_inlier_mask")]
 
 
 _lib = None
@@ -115,6 +117,8 @@ def lib():
         L.svo_write_png.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int]
         L.svo_lk_track.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.svo_pnp_ransac.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_float, C.c_double] + [C.c_void_p] * 7
+        L.svo_frontend_set_pnp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_double]
         _lib = L
     return _lib
 
@@ -382,6 +386,30 @@ class Context:
         p2 = np.ascontiguousarray(p2, np.float64).reshape(12)
         self._check(self._L.svo_frontend_set_projection(self._h, _p(p1), _p(p2)))
 
+    def frontend_set_pnp(self, enable=True, iterations=500, reproj_error=0.5, confidence=float(np.float32(0.99))):
+        """Tracking::iterationsCount_ / reprojectionError_ / confidence_ (config/default.yaml:80-82; confidence_ is a float there)."""
+        self._check(self._L.svo_frontend_set_pnp(self._h, int(bool(enable)), int(iterations), C.c_float(reproj_error), C.c_double(confidence)))
+
+    def pnp_ransac(self, K, pts3d, pts2d, counts=None, iterations=500, reproj_error=0.5, confidence=0.99):
+        """cv::solvePnPRansac (tracking.cpp:486-488) for one list ([n,3] / [n,2]) or a batch ([b,cap,3] / [b,cap,2] + counts[b]).
+        Returns dict(ok, rvec, tvec, R, mask, n_inliers, best_iter, iters); arrays carry a leading batch axis for batch input."""
+        K = np.ascontiguousarray(K, np.float64).reshape(9)
+        p3 = np.ascontiguousarray(pts3d, np.float32)
+        p2 = np.ascontiguousarray(pts2d, np.float32)
+        single = p3.ndim == 2
+        if single:
+            p3, p2 = p3[None], p2[None]
+        b, cap = p3.shape[0], p3.shape[1]
+        cnt = np.full(b, cap, np.int32) if counts is None else np.ascontiguousarray(counts, np.int32)
+        rvec, tvec, R = np.zeros((b, 3)), np.zeros((b, 3)), np.zeros((b, 9))  # noqa
+        mask = np.zeros((b, max(cap, 1)), np.uint8)
+        ninl, info, ok = np.zeros(b, np.int32), np.zeros((b, 2), np.int32), np.zeros(b, np.int32)
+        self._check(self._L.svo_pnp_ransac(self._h, _p(K), _p(p3), _p(p2), _p(cnt), b, cap, int(iterations), C.c_float(reproj_error),
+                                           C.c_double(confidence), _p(rvec), _p(tvec), _p(R), _p(mask), _p(ninl), _p(info), _p(ok)))
+        res = dict(ok=ok.astype(bool), rvec=rvec, tvec=tvec, R=R.reshape(b, 3, 3), mask=mask[:, :cap].astype(bool), n_inliers=ninl,
+                   best_iter=info[:, 0].copy(), iters=info[:, 1].copy())
+        return {k: v[0] for k, v in res.items()} if single else res
+
     def triangulate_points(self, p1, p2, pts1, pts2):
         """cv::triangulatePoints + convertPointsFromHomogeneous -> (points4d [n,4], points3d [n,3])"""
         p1 = np.ascontiguousarray(p1, np.float64).reshape(12)
@@ -431,7 +459,8 @@ class FrontendBuffers:
     ALL = ("kps_left", "desc_left", "n_left", "kps_right", "desc_right", "n_right", "n_query", "stereo_idx", "stereo_dist",
            "temporal_idx", "temporal_dist", "fast_kps", "n_fast", "n_seed", "lk_p1", "lk_p2", "lk_p3", "lk_p0r", "lk_status",
            "orb_t2_left", "orb_t1_left", "orb_t1_right", "n_orb_matched", "lkf_t1_left", "lkf_t1_right", "lkf_t2_right", "lkf_t2_left",
-           "n_lk_matched", "orb_points3d", "lk_points3d", "lk_err")
+           "n_lk_matched", "orb_points3d", "lk_points3d", "lk_err", "orb_pose", "orb_pnp_info", "orb_inlier_mask", "lk_pose", "lk_pnp_info",
+           "lk_inlier_mask")
 
     def __init__(self, n_frames, kp_cap, pt_cap, fields=None, alloc=None):
         fields = self.ALL if fields is None else fields
@@ -447,7 +476,10 @@ class FrontendBuffers:
                       orb_t2_left=((F, K, 2), np.float32), orb_t1_left=((F, K, 2), np.float32), orb_t1_right=((F, K, 2), np.float32),
                       n_orb_matched=((F,), np.int32), lkf_t1_left=((F, P, 2), np.float32), lkf_t1_right=((F, P, 2), np.float32),
                       lkf_t2_right=((F, P, 2), np.float32), lkf_t2_left=((F, P, 2), np.float32), n_lk_matched=((F,), np.int32),
-                      orb_points3d=((F, K, 3), np.float32), lk_points3d=((F, P, 3), np.float32), lk_err=((F, 4, P), np.float32))
+                      orb_points3d=((F, K, 3), np.float32), lk_points3d=((F, P, 3), np.float32), lk_err=((F, 4, P), np.float32),
+                      orb_pose=((F, 16), np.float64), orb_pnp_info=((F, 4), np.int32), orb_inlier_mask=((F, K), np.uint8),
+                      lk_pose=((F, 16), np.float64), lk_pnp_info=((F, 4), np.int32), lk_inlier_mask=((F, P), np.uint8))
+        self.pnp_enabled = False  # set by the caller when svo_frontend_set_pnp() is on (copied_bytes counts the pose outputs then)
         self.struct = FrontendOut()
         self.struct.kp_cap = kp_cap
         self.struct.pt_cap = pt_cap
@@ -480,4 +512,9 @@ class FrontendBuffers:
                             ("orb_points3d", mo * 12), ("lk_points3d", mk * 12), ("lk_err", ms * 16)):
             if getattr(self, name) is not None:
                 total += width * F
+        if self.pnp_enabled:
+            for name, width in (("orb_pose", 128), ("orb_pnp_info", 16), ("orb_inlier_mask", mo), ("lk_pose", 128), ("lk_pnp_info", 16),
+                                ("lk_inlier_mask", mk)):
+                if getattr(self, name) is not None:
+                    total += width * F
         return total + 3 * 4 * 2 * (F + 1)  # the count / flag arrays

@@ -210,6 +210,20 @@ struct svo_ctx {
     float* d_orb_xyz = nullptr;  // [frame slot][kp_cap][3]
     float* d_lkf_xyz = nullptr;  // [frame slot][pt_cap][3]
 
+    // K13: pose of every unit frame from its filtered lists (cv::solvePnPRansac, tracking.cpp:464-501); parameters as in
+    // config/default.yaml:80-82.  Results per list kind (0 ORB, 1 LK) and frame slot.
+    bool fe_pnp = false;
+    int pnp_iters = 500;
+    float pnp_reproj = 0.5f;
+    double pnp_conf = (double)0.99f;
+    uint32_t* d_pnp_rng = nullptr;   // the raw stream of cv::RNG((uint64)-1): the same for every problem
+    int pnp_rng_n = 0;
+    uint64_t pnp_rng_end = 0;
+    double* d_pnp_pose = nullptr;    // [kind][frame slot][16]: rvec, tvec, R row-major, spare
+    int* d_pnp_info = nullptr;       // [kind][frame slot][4]: ok, inliers, best hypothesis, hypotheses evaluated
+    uint8_t* d_pnp_mask_orb = nullptr;  // [frame slot][kp_cap]
+    uint8_t* d_pnp_mask_lk = nullptr;   // [frame slot][pt_cap]
+
     // ---- matches (frontend): per frame slot, kp_cap each
     int* d_match = nullptr;  // [frame slot][4][kp_cap]: stereo idx, stereo dist, temporal idx, temporal dist
     // K6 on the int8 tensor-core path: descriptors expanded to one byte per bit in IMMA fragment order, their popcounts, slot list
@@ -287,6 +301,8 @@ int launch_match_frontend(svo_ctx* c, int first, int ring, int n_frames, int ski
 int launch_orb_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_first);      // K10
 int launch_lk_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_first);       // K11
 int launch_triangulate_frontend(svo_ctx* c, int first, int ring, int n_frames);            // K12
+int launch_pnp_frontend(svo_ctx* c, int first, int ring, int n_frames);                    // K13
+int svo_pnp_free_frontend(svo_ctx* c);
 int launch_fast_full(svo_ctx* c, const SlotMap& map, int n_img, int threshold);      // K9 (+ ordered compaction)
 int launch_lk_pyramid(svo_ctx* c, const SlotMap& map, int n_img);                    // K7
 // the 4-call LK chain for n_frames unit frames in ONE launch (K8); see k_lk.cu

@@ -155,6 +155,7 @@ static void free_layout(svo_ctx* c) {
         if (*p) svo_dev_free(*p);
         *p = nullptr;
     }
+    svo_pnp_free_frontend(c);
     c->cur_w = c->cur_h = 0;
     c->aux_ready = false;
     c->fe_configured = false;
@@ -168,6 +169,7 @@ extern "C" void svo_ctx_destroy(svo_ctx* c) {
     if (c->d_pattern) svo_dev_free(c->d_pattern);
     if (c->d_scratch) svo_dev_free(c->d_scratch);
     if (c->d_flag_accum) svo_dev_free(c->d_flag_accum);
+    if (c->d_pnp_rng) svo_dev_free(c->d_pnp_rng);
     if (c->d_xdesc) svo_dev_free(c->d_xdesc);
     if (c->d_xpop) svo_dev_free(c->d_xpop);
     if (c->d_xslots) svo_dev_free(c->d_xslots);

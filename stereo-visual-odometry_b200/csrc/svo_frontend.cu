@@ -198,6 +198,7 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
         return c->fail(SVO_ERR_INVALID, "svo_frontend_configure: bad mode / size / max_frames");
     if (2 * (max_frames + 1) > c->max_images) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure: need max_images >= 2 * (max_frames + 1)");
     if (c->fe_configured) cudaStreamSynchronize(c->stream);
+    svo_pnp_free_frontend(c);  // sized by the ring and the capacities below: svo_frontend_set_pnp() must follow a (re)configure
     if ((mode & SVO_MODE_ORB) && !c->user_configured) return c->fail(SVO_ERR_NOT_CONFIGURED, "svo_orb_configure() first");
     cudaSetDevice(c->device);
     int rc;
@@ -427,6 +428,7 @@ extern "C" int svo_frontend_run(svo_ctx* c) {
     }
     if (overlap) SVO_CUDA_TRY(c, cudaStreamWaitEvent(main_stream, c->ev_join, 0));  // join before anything reads the ORB results
     if (c->have_proj && (rc = launch_triangulate_frontend(c, first, ring, n)) != SVO_OK) return rc;
+    if (c->have_proj && c->fe_pnp && (rc = launch_pnp_frontend(c, first, ring, n)) != SVO_OK) return rc;
     {  // completed-run queue (depth <= 2): what svo_frontend_download delivers, oldest first
         svo_ctx::DoneRun& d = c->fe_q[(c->fe_qhead + c->fe_nq) % 2];
         d.first = first;
@@ -587,6 +589,11 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
         for (int r = 0; r < 3; ++r)
             if (oh[r] && (rc = rcpy.copy(oh[r], hk * 8, c->d_orb_pts + (size_t)r * K * 2, (size_t)3 * K * 8, (size_t)maxM * 8))) return rc;
         if (out->orb_points3d && c->have_proj && (rc = rcpy.copy(out->orb_points3d, hk * 12, c->d_orb_xyz, (size_t)K * 12, (size_t)maxM * 12))) return rc;
+        if (c->fe_pnp) {
+            if (out->orb_pose && (rc = rcpy.copy(out->orb_pose, 128, c->d_pnp_pose, 128, 128))) return rc;
+            if (out->orb_pnp_info && (rc = rcpy.copy(out->orb_pnp_info, 16, c->d_pnp_info, 16, 16))) return rc;
+            if (out->orb_inlier_mask && (rc = rcpy.copy(out->orb_inlier_mask, hk, c->d_pnp_mask_orb, (size_t)K, (size_t)maxM))) return rc;
+        }
         int32_t* mh[4] = {out->stereo_idx, out->stereo_dist, out->temporal_idx, out->temporal_dist};
         for (int r = 0; r < 4; ++r)
             if (mh[r] && (rc = rcpy.copy(mh[r], hk * 4, c->d_match + (size_t)r * K, (size_t)4 * K * 4, (size_t)maxQ * 4))) return rc;
@@ -617,6 +624,11 @@ extern "C" int svo_frontend_download(svo_ctx* c, svo_frontend_out* out) {
         for (int r = 0; r < 4; ++r)
             if (fh[r] && (rc = rcpy.copy(fh[r], hp * 8, c->d_lkf_pts + (size_t)r * P * 2, (size_t)5 * P * 8, (size_t)maxK * 8))) return rc;
         if (out->lk_points3d && c->have_proj && (rc = rcpy.copy(out->lk_points3d, hp * 12, c->d_lkf_xyz, (size_t)P * 12, (size_t)maxK * 12))) return rc;
+        if (c->fe_pnp) {
+            if (out->lk_pose && (rc = rcpy.copy(out->lk_pose, 128, c->d_pnp_pose + (size_t)16 * ring, 128, 128))) return rc;
+            if (out->lk_pnp_info && (rc = rcpy.copy(out->lk_pnp_info, 16, c->d_pnp_info + (size_t)4 * ring, 16, 16))) return rc;
+            if (out->lk_inlier_mask && (rc = rcpy.copy(out->lk_inlier_mask, hp, c->d_pnp_mask_lk, (size_t)P, (size_t)maxK))) return rc;
+        }
         if (out->lk_status)
             for (int r = 0; r < 4; ++r)
                 if ((rc = rcpy.copy(out->lk_status + (size_t)r * hp, 4 * hp, c->d_lk_status + (size_t)r * P, (size_t)4 * P, (size_t)maxS))) return rc;

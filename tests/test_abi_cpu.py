@@ -25,7 +25,7 @@ def test_exports_every_declared_symbol(pkg):
     assert not missing, missing
     assert sorted(pkg.ABI_SYMBOLS + pkg.SYNTH_SYMBOLS) == declared
     assert not any(hasattr(L, s) for s in pkg.SYNTH_SYMBOLS), "the generator must not be linked into the CUDA library"
-    assert L.svo_abi_version() == 4
+    assert L.svo_abi_version() == 5
 
 
 def test_keypoint_layout(pkg):
