@@ -438,13 +438,13 @@ def run_reference(a):
     speeds = {}
     for name, v in variants.items():
         n = cal_units if v["workers"] > 1 else min(cal_units, 6)
-        pool = ref_pipeline.ReferencePool(left[:n + 1], right[:n + 1], 3, a.nfeatures, v["workers"], variant=v["variant"], cv_threads=v["cv_threads"])
+        pool = ref_pipeline.ReferencePool(left[:n + 1], right[:n + 1], 7 if a.pnp else 3, a.nfeatures, v["workers"], variant=v["variant"], cv_threads=v["cv_threads"])
         dt, _ = pool.run()
         pool.close()
         speeds[name] = n / dt
     best = max(speeds, key=speeds.get)
     v = variants[best]
-    pool = ref_pipeline.ReferencePool(left, right, 3, a.nfeatures, v["workers"], variant=v["variant"], cv_threads=v["cv_threads"])
+    pool = ref_pipeline.ReferencePool(left, right, 7 if a.pnp else 3, a.nfeatures, v["workers"], variant=v["variant"], cv_threads=v["cv_threads"])
     for _ in range(a.warmup):
         pool.run()
     total = 0.0
@@ -458,7 +458,8 @@ def run_reference(a):
     sample = (f"{units} consecutive stereo frames of the same synthetic sequence per step ({units // max(workers, 1)} per worker + 1 warm-up frame each), "
               f"variant {best}: {workers} worker processes x {v['cv_threads']} OpenCV thread(s); cv2 4.13 FAST / BFMatcher / calcOpticalFlowPyrLK "
               f"(err computed) + ORBextractor as in the variant's name (ref = the reference's own src/ORBextractor.cpp compiled into oracle/_ref, "
-              f"cv2prim = cv2.resize / cv2.FAST per cell / cv2.GaussianBlur + the oracle's loops, port = C++ oracle port)")
+              f"cv2prim = cv2.resize / cv2.FAST per cell / cv2.GaussianBlur + the oracle's loops, port = C++ oracle port)"
+              + ("; pose step with the real cv2.triangulatePoints / convertPointsFromHomogeneous / solvePnPRansac on both filtered lists" if a.pnp else ""))
     cpu_model = ""
     try:
         cpu_model = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]

@@ -16,6 +16,9 @@
 #define CV_8UC1 0
 #define CV_32F 5
 #define CV_32FC1 5
+#define CV_64F 6
+#define CV_64FC1 6
+#define CV_32FC3 21
 #endif
 
 namespace cv {
@@ -61,7 +64,7 @@ struct DMatch {
     DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(0), distance(d) {}
 };
 
-// reference-counted 2-D matrix of 8-bit or 32-bit float elements
+// reference-counted 2-D matrix of 8-bit, 32-bit float (1 or 3 channels) or 64-bit float elements
 class Mat {
 public:
     int rows = 0, cols = 0;
@@ -92,7 +95,7 @@ public:
     // cv::_InputArray::getMat() / cv::_OutputArray::getMat(): here the array types ARE Mat references, so this is the identity
     Mat getMat() const { return *this; }
     int type() const { return type_; }
-    size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
+    size_t elemSize() const { return type_ == CV_32F ? 4 : type_ == CV_64F ? 8 : type_ == CV_32FC3 ? 12 : 1; }
     bool isContinuous() const { return step == (size_t)cols * elemSize(); }
     Mat clone() const {
         Mat m;

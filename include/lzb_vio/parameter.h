@@ -11,6 +11,10 @@ struct Parameter {
     std::string track_mode_ = "ORB_stereof2f_pnp";  // config/default.yaml:75
     double feature_match_error_ = 3;                 // config/default.yaml:66
     int num_features_tracking_ = 50;
+    double inlier_rate_ = 0.01;         // config/default.yaml:77
+    int iterationsCount_ = 500;         // :80
+    float reprojectionError_ = 0.5f;    // :81
+    float confidence_ = 0.99f;          // :82
     int nFeatures_ = 2000;        // config/default.yaml:93
     float fScaleFactor_ = 1.2f;   // :92
     int nLevels_ = 8;             // :91

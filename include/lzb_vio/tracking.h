@@ -4,9 +4,12 @@
 //   Detect_MyORBFeatures / Detect_OpenCVFASTFeatures                      (tracking.h:88-89,  tracking.cpp:94-113, 502-532)
 //   ORB_Robust_Find_MuliImage_MatchedFeatures                             (tracking.h:57-59,  tracking.cpp:534-581)
 //   LK_Robust_Find_MuliImage_MatchedFeatures / deleteBadmatchFeatures     (tracking.h:52-56, 91-95, tracking.cpp:583-660)
-// and the AddFrame / StereoInit_f2f / Track state machine around them (tracking.cpp:49-128).  Everything after the matched
-// point lists are filled (triangulatePoints, solvePnPRansac, pose gating, display: tracking.cpp:186-249, 288-344) is the
-// reference's own host code and is reached through pose_backend_, which the application sets.
+//   OpenCV_EstimatePose_PnP                                               (tracking.h:76-80,  tracking.cpp:464-501)
+// and the AddFrame / StereoInit_f2f / Track state machine around them (tracking.cpp:49-128).  Triangulation and the pose
+// estimate are device calls too (TriangulateMatched = the cv::triangulatePoints + convertPointsFromHomogeneous pair at
+// tracking.cpp:190-192; OpenCV_EstimatePose_PnP with the reference's own signature).  What follows them (pose gating, frame_pose_
+// bookkeeping, display: tracking.cpp:200-249, 300-344) is the reference's own host code and is reached through pose_backend_,
+// which the application sets.
 #pragma once
 #include <functional>
 #include <memory>
@@ -51,6 +54,15 @@ public:
                                                   std::vector<cv::Point2f>& points_t1_right);
     int Detect_MyORBFeatures();
     int Detect_OpenCVFASTFeatures();
+    // cv::triangulatePoints(projMatrl, projMatrr, t1_left, t1_right, points4D) + cv::convertPointsFromHomogeneous(points4D.t(),
+    // points3D) (tracking.cpp:190-192, 292-294): projection matrices 3 x 4 CV_64F, result n x 1 CV_32FC3
+    void TriangulateMatched(cv::Mat& projMatrl, cv::Mat& projMatrr, std::vector<cv::Point2f>& points_t1_left,
+                            std::vector<cv::Point2f>& points_t1_right, cv::Mat& points3D_t1);
+    // same signature and outputs as the reference (tracking.cpp:464-501): rotation 3 x 3 CV_64F, translation 3 x 1 CV_64F, the
+    // return value is the inlier-rate test; last_inliers_ keeps solvePnPRansac's `inliers` (indices)
+    bool OpenCV_EstimatePose_PnP(cv::Mat& projMatrl, std::vector<cv::Point2f>& pointsLeft_t2, cv::Mat& points3D_t1, cv::Mat& rotation,
+                                 cv::Mat& translation);
+    std::vector<int> last_inliers_;
     void deleteBadmatchFeatures(std::vector<cv::Point2f>& points0, std::vector<cv::Point2f>& points1, std::vector<cv::Point2f>& points2,
                                 std::vector<cv::Point2f>& points3, std::vector<cv::Point2f>& points0_return,
                                 std::vector<unsigned char>& status0, std::vector<unsigned char>& status1,
@@ -71,6 +83,9 @@ private:
     std::string track_mode_;
     double feature_match_error_ = 10;
     int num_features_tracking_ = 50;
+    double inlier_rate_ = 0.01;
+    int iterationsCount_ = 500;
+    float reprojectionError_ = 0.5f, confidence_ = 0.99f;
     int nFeatures_ = 2000, nLevels_ = 8, fIniThFAST_ = 20, fMinThFAST_ = 7;
     float fScaleFactor_ = 1.2f;
 };

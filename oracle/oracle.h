@@ -121,4 +121,13 @@ int lk_chain_filter(int n, const float* p0, const float* p1, const float* p2, co
 // (unit right singular vector of the smallest singular value, sign arbitrary), out3: n x 3 (float division like OpenCV).
 void triangulate_points(const double* P1, const double* P2, const float* pts1, const float* pts2, int n, float* out4, float* out3);
 
+// ---- pose from points (oracle_pnp.cpp; its header states what is pinned against cv2 4.13 and what cannot be) ----
+// cv::solvePnP(SOLVEPNP_EPNP) on n >= 5 points; cv::solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess = true) on the points with
+// mask != 0 (param = [rvec, tvec] in / out; returns LM iterations); the whole cv::solvePnPRansac call of tracking.cpp:486-488:
+// out15 = rvec, tvec, R (row-major); info3 = inliers, winning hypothesis, hypotheses evaluated; returns solvePnPRansac's bool.
+bool epnp(const double K[9], const float* pts3d, const float* pts2d, int n, double R[9], double t[3]);
+int refine_lm(const double K[9], const float* p3, const float* p2, int n, const uint8_t* mask, double param[6]);
+int solve_pnp_ransac(const double K[9], const float* p3, const float* p2, int n, int max_iters, float reproj_err, double confidence, uint8_t* mask,
+                     double out15[15], int info3[3]);
+
 }  // namespace orc

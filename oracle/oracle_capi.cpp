@@ -173,9 +173,25 @@ void orc_triangulate_points(const double* P1, const double* P2, const float* pts
 // ---------------------------------------------------------------------------------------------------------------
 // Whole front-end over a sequence, for the CPU baseline ("port"): per frame t: ORB on L_t and R_t, match(L_{t-1},R_{t-1}),
 // match(L_{t-1},L_t); FAST on L_t and the 4-call LK chain over (t-1, t).  Frames are split over `threads` workers in
-// contiguous chunks overlapping by one frame (same sharding rule as the GPU path).  mode bit0 = ORB, bit1 = LK.
+// contiguous chunks overlapping by one frame (same sharding rule as the GPU path).  mode bit0 = ORB, bit1 = LK, bit2 = the pose
+// step on every filtered list (triangulatePoints + convertPointsFromHomogeneous + solvePnPRansac(500, 0.5 px, 0.99), KITTI
+// sequence-00 projection matrices; tracking.cpp:190-200).
 // Returns a checksum so the work cannot be optimised away.
 // ---------------------------------------------------------------------------------------------------------------
+// triangulate (t1_left, t1_right), then the pose from those 3-D points and their pixels in left_t
+static uint64_t pose_step(const float* t1_left, const float* t1_right, const float* t2_left, int n) {
+    static const double P1[12] = {718.856, 0, 607.1928, 0, 0, 718.856, 185.2157, 0, 0, 0, 1, 0};
+    static const double P2[12] = {718.856, 0, 607.1928, -386.1448, 0, 718.856, 185.2157, 0, 0, 0, 1, 0};
+    static const double K[9] = {718.856, 0, 607.1928, 0, 718.856, 185.2157, 0, 0, 1};
+    std::vector<float> x4((size_t)4 * n), x3((size_t)3 * n);
+    triangulate_points(P1, P2, t1_left, t1_right, n, x4.data(), x3.data());
+    std::vector<uint8_t> mask((size_t)n);
+    double out[15];
+    int info[3];
+    solve_pnp_ransac(K, x3.data(), t2_left, n, 500, 0.5f, (double)0.99f, mask.data(), out, info);
+    return (uint64_t)info[0] * 31u + (uint64_t)info[2];
+}
+
 uint64_t orc_frontend_sequence(const uint8_t* left, const uint8_t* right, int n_frames, int w, int h, int nfeatures,
                                float scaleFactor, int nlevels, int iniTh, int minTh, int mode, int threads) {
     threads = std::max(1, std::min(threads, std::max(1, n_frames - 1)));
@@ -199,6 +215,14 @@ uint64_t orc_frontend_sequence(const uint8_t* left, const uint8_t* right, int n_
                     int na = orb_match_filter(i1.data(), d1.data(), i2.data(), d2.data(), nq, (int)lastR.keypoints.size(),
                                               (int)curL.keypoints.size(), lastL.keypoints.data(), lastR.keypoints.data(), 3.0, acc.data());
                     cs += (uint64_t)na * 1000003u;
+                    if ((mode & 4) && na > 0) {
+                        std::vector<float> a1((size_t)2 * na), a2((size_t)2 * na), a3((size_t)2 * na);
+                        for (int i = 0; i < na; ++i) {
+                            const KeyPoint &kl = lastL.keypoints[acc[3 * i]], &kr = lastR.keypoints[acc[3 * i + 1]], &kc = curL.keypoints[acc[3 * i + 2]];
+                            a1[2 * i] = kl.x, a1[2 * i + 1] = kl.y, a2[2 * i] = kr.x, a2[2 * i + 1] = kr.y, a3[2 * i] = kc.x, a3[2 * i + 1] = kc.y;
+                        }
+                        cs += pose_step(a1.data(), a2.data(), a3.data(), na);
+                    }
                     for (int i = 0; i < nq; ++i) cs += (uint64_t)(i1[i] + 3 * i2[i] + d1[i]);
                 }
                 std::swap(lastL, curL);
@@ -216,8 +240,19 @@ uint64_t orc_frontend_sequence(const uint8_t* left, const uint8_t* right, int n_
                     calc_optical_flow_pyr_lk(pR, R, p1.data(), n, p2.data(), s1.data(), err.data(), 21, 3, 30, 0.01, 0.001);
                     calc_optical_flow_pyr_lk(R, L, p2.data(), n, p3.data(), s2.data(), err.data(), 21, 3, 30, 0.01, 0.001);
                     calc_optical_flow_pyr_lk(L, pL, p3.data(), n, p0r.data(), s3.data(), err.data(), 21, 3, 30, 0.01, 0.001);
-                    cs += (uint64_t)lk_chain_filter(n, p0.data(), p1.data(), p2.data(), p3.data(), p0r.data(), s0.data(), s1.data(),
-                                                    s2.data(), s3.data(), 3.0, keep.data()) * 7919u;
+                    const int nk = lk_chain_filter(n, p0.data(), p1.data(), p2.data(), p3.data(), p0r.data(), s0.data(), s1.data(), s2.data(),
+                                                   s3.data(), 3.0, keep.data());
+                    cs += (uint64_t)nk * 7919u;
+                    if ((mode & 4) && nk > 0) {
+                        std::vector<float> a1((size_t)2 * nk), a2((size_t)2 * nk), a3((size_t)2 * nk);
+                        for (int i = 0, j = 0; i < n; ++i)
+                            if (keep[i]) {
+                                a1[2 * j] = p0[2 * i], a1[2 * j + 1] = p0[2 * i + 1], a2[2 * j] = p1[2 * i], a2[2 * j + 1] = p1[2 * i + 1];
+                                a3[2 * j] = p3[2 * i], a3[2 * j + 1] = p3[2 * i + 1];
+                                ++j;
+                            }
+                        cs += pose_step(a1.data(), a2.data(), a3.data(), nk);
+                    }
                 }
                 std::swap(last_fast, cur_fast);
             }

@@ -121,6 +121,21 @@ def _worker(args):
               minEigThreshold=1e-3)
     checksum = 0
     last = None
+    P1 = np.array([[718.856, 0, 607.1928, 0], [0, 718.856, 185.2157, 0], [0, 0, 1, 0]], np.float64)   # KITTI sequence 00
+    P2 = np.array([[718.856, 0, 607.1928, -386.1448], [0, 718.856, 185.2157, 0], [0, 0, 1, 0]], np.float64)
+
+    def pose_step(t1_left, t1_right, t2_left):
+        """tracking.cpp:190-200 / 464-501 with the real OpenCV calls: triangulatePoints, convertPointsFromHomogeneous, solvePnPRansac."""
+        if len(t2_left) < 5:
+            return 0
+        p4 = cv2.triangulatePoints(P1, P2, np.ascontiguousarray(t1_left.T), np.ascontiguousarray(t1_right.T))
+        p3 = cv2.convertPointsFromHomogeneous(p4.T)
+        ok, rvec, tvec, inl = cv2.solvePnPRansac(p3, np.ascontiguousarray(t2_left), P1[:, :3].copy(), np.zeros((4, 1)), rvec=np.zeros((3, 1)),
+                                                 tvec=np.zeros((3, 1)), useExtrinsicGuess=True, iterationsCount=500, reprojectionError=0.5,
+                                                 confidence=float(np.float32(0.99)), flags=cv2.SOLVEPNP_ITERATIVE)
+        cv2.Rodrigues(rvec)
+        return 0 if inl is None else len(inl)
+
     for t in range(u0, u1 + 1):  # frame u0 only warms up the "last frame"
         cur = {}
         L, R = left[t], right[t]
@@ -136,6 +151,10 @@ def _worker(args):
                 d2 = np.fromiter((m.distance for m in m2), np.int32, len(m2))
                 acc = O.orb_match_filter(i1, d1, i2, d2, len(last["dr"]), len(cur["dl"]), last["kl"], last["kr"], 3.0)
                 checksum += len(acc)
+                if (mode & 4) and len(acc):
+                    a = np.asarray(acc).reshape(-1, 3)
+                    xy = lambda k, idx: np.stack([k["x"][idx], k["y"][idx]], 1).astype(np.float32)  # noqa: E731
+                    checksum += pose_step(xy(last["kl"], a[:, 0]), xy(last["kr"], a[:, 1]), xy(cur["kl"], a[:, 2]))
         if mode & 2:
             kps = fast.detect(L)
             cur["pts"] = np.array([k.pt for k in kps], np.float32).reshape(-1, 1, 2)
@@ -148,6 +167,8 @@ def _worker(args):
                 keep = O.lk_chain_filter(p0.reshape(-1, 2), p1.reshape(-1, 2), p2.reshape(-1, 2), p3.reshape(-1, 2), p0r.reshape(-1, 2),
                                          s1.ravel(), s2.ravel(), s3.ravel(), s4.ravel(), 3.0)
                 checksum += int(keep.sum())
+                if (mode & 4) and keep.any():
+                    checksum += pose_step(p0.reshape(-1, 2)[keep], p1.reshape(-1, 2)[keep], p3.reshape(-1, 2)[keep])
             cur["L"], cur["R"] = L, R
         last = cur
     return checksum

@@ -1,6 +1,7 @@
 // host/tracking_frontend.cpp -- the front-end half of lzb_vio::Tracking over the C ABI.
 // Replaces the OpenCV calls at tracking.cpp:101 (cv::FAST), :508-509 (ORBextractor), :539-544 (BFMatcher), :593-618
-// (calcOpticalFlowPyrLK); the filters around them (:546-577, :623-660) are restated on the host as in the reference.
+// (calcOpticalFlowPyrLK), :190-192 (triangulatePoints + convertPointsFromHomogeneous), :486-489 (solvePnPRansac + Rodrigues);
+// the filters around them (:546-577, :623-660) are restated on the host as in the reference.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -24,6 +25,10 @@ void Tracking::Readparameter() {  // tracking.cpp:22-47, front-end fields
     feature_match_error_ = parameter_->feature_match_error_;
     track_mode_ = parameter_->track_mode_;
     num_features_tracking_ = parameter_->num_features_tracking_;
+    inlier_rate_ = parameter_->inlier_rate_;
+    iterationsCount_ = parameter_->iterationsCount_;
+    reprojectionError_ = parameter_->reprojectionError_;
+    confidence_ = parameter_->confidence_;
     nFeatures_ = parameter_->nFeatures_;
     fScaleFactor_ = parameter_->fScaleFactor_;
     nLevels_ = parameter_->nLevels_;
@@ -80,6 +85,58 @@ bool Tracking::LK_StereoF2F_PnP_Track() {  // tracking.cpp:258-288
     const int n = LK_Robust_Find_MuliImage_MatchedFeatures(matched_t2_left, matched_t2_right, matched_t1_left, matched_t1_right);
     if (n < num_features_tracking_) return false;
     return pose_backend_ ? pose_backend_(matched_t1_left, matched_t1_right, matched_t2_left) : true;
+}
+
+void Tracking::TriangulateMatched(cv::Mat& projMatrl, cv::Mat& projMatrr, std::vector<cv::Point2f>& points_t1_left,
+                                  std::vector<cv::Point2f>& points_t1_right, cv::Mat& points3D_t1) {  // tracking.cpp:190-192
+    const int n = (int)std::min(points_t1_left.size(), points_t1_right.size());
+    points3D_t1.create(n, 1, CV_32FC3);
+    if (n == 0) return;
+    double p1[12], p2[12];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) {
+            p1[4 * r + c] = projMatrl.at<double>(r, c);
+            p2[4 * r + c] = projMatrr.at<double>(r, c);
+        }
+    svo_ctx* c = mpORBextractorLeft_->context(current_frame_->left_img_.cols, current_frame_->left_img_.rows);
+    if (svo_triangulate_points(c, p1, p2, &points_t1_left[0].x, &points_t1_right[0].x, n, nullptr, points3D_t1.ptr<float>()) != SVO_OK)
+        throw std::runtime_error(std::string("svo_triangulate_points: ") + svo_last_error(c));
+}
+
+bool Tracking::OpenCV_EstimatePose_PnP(cv::Mat& projMatrl, std::vector<cv::Point2f>& pointsLeft_t2, cv::Mat& points3D_t1, cv::Mat& rotation,
+                                       cv::Mat& translation) {  // tracking.cpp:464-501
+    const int n = (int)pointsLeft_t2.size();
+    rotation.create(3, 3, CV_64F);
+    translation.create(3, 1, CV_64F);
+    last_inliers_.clear();
+    double K[9], rvec[3] = {0, 0, 0}, tvec[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) K[3 * r + c] = projMatrl.at<double>(r, c);  // intrinsic_matrix (:476-477)
+    int32_t ok = 0, n_inliers = 0;
+    if (n > 0) {
+        // points3D_t1: n x 1 CV_32FC3 (or n x 3 CV_32F), gathered row by row so that a non-continuous Mat works too
+        std::vector<float> p3((size_t)3 * n);
+        for (int i = 0; i < n; ++i) {
+            const float* row = points3D_t1.ptr<float>(i);
+            p3[3 * i] = row[0];
+            p3[3 * i + 1] = row[1];
+            p3[3 * i + 2] = row[2];
+        }
+        std::vector<uint8_t> mask((size_t)n);
+        svo_ctx* c = mpORBextractorLeft_->context(current_frame_->left_img_.cols, current_frame_->left_img_.rows);
+        const int32_t count = n;
+        if (svo_pnp_ransac(c, K, p3.data(), &pointsLeft_t2[0].x, &count, 1, n, iterationsCount_, reprojectionError_, (double)confidence_, rvec, tvec, R,
+                           mask.data(), &n_inliers, nullptr, &ok) != SVO_OK)
+            throw std::runtime_error(std::string("svo_pnp_ransac: ") + svo_last_error(c));
+        for (int i = 0; i < n; ++i)
+            if (mask[i]) last_inliers_.push_back(i);
+    }
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) rotation.at<double>(r, c) = R[3 * r + c];  // cv::Rodrigues(rvec, rotation) (:489)
+        translation.at<double>(r, 0) = tvec[r];
+    }
+    if (n == 0) return false;
+    return !((double)n_inliers / (double)n < inlier_rate_);  // :492-500
 }
 
 int Tracking::Detect_OpenCVFASTFeatures() {  // tracking.cpp:94-113

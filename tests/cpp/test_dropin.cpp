@@ -97,6 +97,56 @@ int main() {
         const int na = orc::orb_match_filter(i1.data(), d1.data(), i2.data(), d2.data(), nq, nr, nc, ll.data(), lr.data(), 3.0, acc.data());
         CHECK((size_t)na == last_n);
     }
+    // ---- 2b. the pose step as ORB_StereoF2F_PnP_Track runs it (tracking.cpp:186-200): triangulate (t1_left, t1_right), then
+    //          OpenCV_EstimatePose_PnP(projMatrl, matched_t2_left, points3D_t1, rotation, translation)
+    {
+        Parameter::Ptr p(new Parameter);
+        p->nFeatures_ = nfeat;
+        p->track_mode_ = "ORB_stereof2f_pnp";
+        Tracking tr(nullptr, p, nullptr);
+        cv::Mat projl(3, 4, CV_64F), projr(3, 4, CV_64F);
+        const double P1[12] = {718.856, 0, 607.1928, 0, 0, 718.856, 185.2157, 0, 0, 0, 1, 0};
+        for (int i = 0; i < 12; ++i) {
+            projl.at<double>(i / 4, i % 4) = P1[i];
+            projr.at<double>(i / 4, i % 4) = P1[i];
+        }
+        projr.at<double>(0, 3) = -386.1448;
+        bool called = false, pose_ok = false;
+        cv::Mat rotation, translation, points3D;
+        std::vector<cv::Point2f> t1l, t1r, t2l;
+        tr.pose_backend_ = [&](const std::vector<cv::Point2f>& a, const std::vector<cv::Point2f>& b, const std::vector<cv::Point2f>& c) {
+            called = true;
+            t1l = a; t1r = b; t2l = c;
+            tr.TriangulateMatched(projl, projr, t1l, t1r, points3D);
+            pose_ok = tr.OpenCV_EstimatePose_PnP(projl, t2l, points3D, rotation, translation);
+            return pose_ok;
+        };
+        Frame::Ptr f0 = make_frame(1000, 3, w, h), f1 = make_frame(1000, 4, w, h);
+        CHECK(tr.AddFrame(f0));
+        tr.AddFrame(f1);
+        CHECK(called && points3D.rows == (int)t2l.size() && rotation.rows == 3 && rotation.cols == 3 && translation.rows == 3);
+        const int n = (int)t2l.size();
+        std::vector<float> o4((size_t)4 * n), o3((size_t)3 * n);
+        double P2[12];
+        for (int i = 0; i < 12; ++i) P2[i] = P1[i];
+        P2[3] = -386.1448;
+        orc::triangulate_points(P1, P2, &t1l[0].x, &t1r[0].x, n, o4.data(), o3.data());
+        const float* g3 = points3D.ptr<float>();
+        for (int i = 0; i < 3 * n; ++i) CHECK(std::fabs(g3[i] - o3[i]) <= 2e-5f * std::fabs(o3[i]) + 1e-6f);
+        // the oracle on the 3-D points the device produced (so that both sides see the same input)
+        const double K[9] = {718.856, 0, 607.1928, 0, 718.856, 185.2157, 0, 0, 1};
+        std::vector<uint8_t> mask(n);
+        double out[15];
+        int info[3];
+        const int ok = orc::solve_pnp_ransac(K, g3, &t2l[0].x, n, 500, 0.5f, (double)0.99f, mask.data(), out, info);
+        CHECK((int)tr.last_inliers_.size() == info[0]);
+        size_t j = 0;
+        for (int i = 0; i < n; ++i)
+            if (mask[i]) CHECK(j < tr.last_inliers_.size() && tr.last_inliers_[j++] == i);
+        for (int i = 0; i < 9; ++i) CHECK(std::fabs(rotation.at<double>(i / 3, i % 3) - out[6 + i]) <= 1e-9);
+        for (int i = 0; i < 3; ++i) CHECK(std::fabs(translation.at<double>(i, 0) - out[3 + i]) <= 1e-9);
+        CHECK(pose_ok == (ok && !((double)info[0] / n < 0.01)));
+    }
     // ---- 3. Tracking, LK mode
     {
         Parameter::Ptr p(new Parameter);

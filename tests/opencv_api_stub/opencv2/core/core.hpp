@@ -15,6 +15,9 @@
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn)-1) << CV_CN_SHIFT))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_64F 6
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
+#define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
 
 namespace cv {
 
