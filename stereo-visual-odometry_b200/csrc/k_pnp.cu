@@ -29,7 +29,8 @@
 
 namespace {
 
-constexpr int PNP_THREADS = 128;
+constexpr int PNP_THREADS = 128;   // hypotheses per wave (one thread each in step B)
+constexpr int PNP_BLOCK = 256;     // threads per CTA: steps C and E use all of them
 constexpr int PNP_CHUNK = 1024;  // points staged per consensus chunk (20 KB)
 constexpr int PNP_DYN_SMEM = 144 * PNP_THREADS * 8;  // the 12 x 12 matrices of a wave: 147 KB
 
@@ -52,8 +53,8 @@ struct PnpProblemSet {  // problem b of a launch -> slot = (first + b) % ring (s
 
 // cv::SVD on n x n (core/src/lapack.cpp JacobiSVDImpl_<double>): rows of `at` are rotated pairwise until orthogonal, sorted by
 // decreasing norm and normalised -> at = U^T, w = singular values, vt = V^T (optional).  sqrt(p^2 + beta^2) stands for hypot.
-template <int ST>
-__device__ void jacobi_svd(double* at, const int n, double* w, double* vt) {
+template <int ST, int n>
+__device__ void jacobi_svd(double* at, double* w, double* vt) {
     double W[12];
     for (int i = 0; i < n; ++i) {
         double sd = 0;
@@ -64,13 +65,17 @@ __device__ void jacobi_svd(double* at, const int n, double* w, double* vt) {
     }
     const double eps = DBL_EPSILON * 10;
     const int max_iter = n > 30 ? n : 30;
+#pragma unroll 1
     for (int iter = 0; iter < max_iter; ++iter) {
         bool changed = false;
+#pragma unroll 1
         for (int i = 0; i < n - 1; ++i)
+#pragma unroll 1
             for (int j = i + 1; j < n; ++j) {
                 double* ai = at + i * n * ST;
                 double* aj = at + j * n * ST;
                 double a = W[i], p = 0, b = W[j];
+#pragma unroll
                 for (int k = 0; k < n; ++k) p += ai[k * ST] * aj[k * ST];
                 if (fabs(p) <= eps * sqrt(a * b)) continue;
                 p *= 2;
@@ -85,6 +90,7 @@ __device__ void jacobi_svd(double* at, const int n, double* w, double* vt) {
                     s = p / (gamma * c * 2);
                 }
                 a = b = 0;
+#pragma unroll
                 for (int k = 0; k < n; ++k) {
                     const double t0 = c * ai[k * ST] + s * aj[k * ST], t1 = -s * ai[k * ST] + c * aj[k * ST];
                     ai[k * ST] = t0;
@@ -237,7 +243,7 @@ __device__ double compute_R_and_t(EpnpState& e, const PnpParams& P, const double
             abtT[3 + j] += (e.pcs[3 * i + j] - pc0[j]) * (e.pws[3 * i + 1] - pw0[1]);
             abtT[6 + j] += (e.pcs[3 * i + j] - pc0[j]) * (e.pws[3 * i + 2] - pw0[2]);
         }
-    jacobi_svd<1>(abtT, 3, d, vt);
+    jacobi_svd<1, 3>(abtT, d, vt);
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) R[3 * i + j] = abtT[i] * vt[j] + abtT[3 + i] * vt[3 + j] + abtT[6 + i] * vt[6 + j];
     const double det = R[0] * R[4] * R[8] + R[1] * R[5] * R[6] + R[2] * R[3] * R[7] - R[2] * R[4] * R[6] - R[1] * R[3] * R[8] - R[0] * R[5] * R[7];
@@ -284,7 +290,7 @@ __device__ bool epnp5(const PnpParams& P, const float* s3, const float* s2, doub
                 for (int b = 0; b < 3; ++b) c[3 * a + b] += d[a] * d[b];
         }
         double dc[3];
-        jacobi_svd<1>(c, 3, dc, nullptr);
+        jacobi_svd<1, 3>(c, dc, nullptr);
         for (int i = 1; i < 4; ++i) {
             const double k = sqrt(dc[i - 1] / n);
             for (int j = 0; j < 3; ++j) e.cws[i][j] = e.cws[0][j] + k * c[3 * (i - 1) + j];
@@ -334,7 +340,7 @@ __device__ bool epnp5(const PnpParams& P, const float* s3, const float* s2, doub
     for (int r = 0; r < 12; ++r)
         for (int c = 0; c < r; ++c) mtm[(r * 12 + c) * ST] = mtm[(c * 12 + r) * ST];
     double d12[12];
-    jacobi_svd<ST>(mtm, 12, d12, nullptr);
+    jacobi_svd<ST, 12>(mtm, d12, nullptr);
     // the four rows epnp.cpp uses (v[i] = row 11 - i of U^T) move to thread-local storage: ut4[i * 12 + k]
     double ut4[48];
     for (int i = 0; i < 4; ++i)
@@ -549,7 +555,7 @@ __device__ __forceinline__ bool is_inlier(const PnpParams& P, const double* m, f
 
 // block-wide sum of NV doubles per thread; result valid in thread 0 (and broadcast through red[0..NV))
 template <int NV>
-__device__ void block_sum(double* v, double* red /* [4][NV] */) {
+__device__ void block_sum(double* v, double* red /* [PNP_BLOCK / 32][NV] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -561,12 +567,15 @@ __device__ void block_sum(double* v, double* red /* [4][NV] */) {
     __syncthreads();
     if (threadIdx.x < NV) {
         const int i = threadIdx.x;
-        red[i] = ((red[i] + red[NV + i]) + red[2 * NV + i]) + red[3 * NV + i];
+        double x = red[i];
+#pragma unroll
+        for (int wv = 1; wv < PNP_BLOCK / 32; ++wv) x += red[wv * NV + i];
+        red[i] = x;
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpProblemSet S, PnpParams P, const uint32_t* __restrict__ rng_table, int rng_table_n,
+__global__ void __launch_bounds__(PNP_BLOCK) k_pnp_ransac(PnpProblemSet S, PnpParams P, const uint32_t* __restrict__ rng_table, int rng_table_n,
                                                             uint64_t rng_table_end_state) {
     extern __shared__ double s_mtm[];  // [144][PNP_THREADS]: M^T M / U^T of every hypothesis of the wave
     __shared__ float s_p3[PNP_CHUNK * 3];
@@ -576,7 +585,7 @@ __global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpProblemSet S, Pnp
     __shared__ int s_count[PNP_THREADS];
     __shared__ unsigned char s_valid[PNP_THREADS];
     __shared__ double s_best[12];
-    __shared__ double s_red[4 * 28];
+    __shared__ double s_red[(PNP_BLOCK / 32) * 28];
     __shared__ double s_param[6];
     __shared__ double s_lm[48];
     __shared__ int s_ctl[8];  // 0 niters, 1 max_good, 2 best_iter, 3 done, 4 iter (hypotheses replayed so far), 5 LM go-on flag
@@ -594,7 +603,7 @@ __global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpProblemSet S, Pnp
     if (n < 5 || n > S.cap) {  // cv2 needs >= 4 points and switches to P3P at exactly 4; the reference rejects such frames earlier
         if (tid < 16) pose[tid] = (tid == 6 || tid == 10 || tid == 14) ? 1.0 : 0.0;
         if (tid < 4) info[tid] = 0;
-        for (int i = tid; i < (n > 0 && n <= S.cap ? n : 0); i += PNP_THREADS) mask[i] = 0;
+        for (int i = tid; i < (n > 0 && n <= S.cap ? n : 0); i += PNP_BLOCK) mask[i] = 0;
         return;
     }
     // generator position: index into the shared raw table, then the live state past its end
@@ -641,7 +650,7 @@ __global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpProblemSet S, Pnp
         const int niters_wave = s_ctl[0];
         const int wave_n = min(PNP_THREADS, niters_wave - base);  // >= 1
         // ---- B: one hypothesis per thread
-        s_count[tid] = 0;
+        if (tid < PNP_THREADS) s_count[tid] = 0;
         if (tid < wave_n) {
             float s3[15], s2[10];
             for (int i = 0; i < 5; ++i) {
@@ -653,17 +662,17 @@ __global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpProblemSet S, Pnp
             const bool ok = epnp5(P, s3, s2, model, s_mtm + tid);
             s_valid[tid] = ok ? 1 : 0;
             for (int i = 0; i < 12; ++i) s_model[tid][i] = model[i];
-        } else {
+        } else if (tid < PNP_THREADS) {
             s_valid[tid] = 0;
         }
         __syncthreads();
         // ---- C: consensus, points staged in chunks
         for (int c0 = 0; c0 < n; c0 += PNP_CHUNK) {
             const int cn = min(PNP_CHUNK, n - c0);
-            for (int i = tid; i < cn * 3; i += PNP_THREADS) s_p3[i] = p3[(size_t)c0 * 3 + i];
-            for (int i = tid; i < cn * 2; i += PNP_THREADS) s_p2[i] = p2[(size_t)c0 * 2 + i];
+            for (int i = tid; i < cn * 3; i += PNP_BLOCK) s_p3[i] = p3[(size_t)c0 * 3 + i];
+            for (int i = tid; i < cn * 2; i += PNP_BLOCK) s_p2[i] = p2[(size_t)c0 * 2 + i];
             __syncthreads();
-            for (int h = warp; h < wave_n; h += PNP_THREADS / 32) {
+            for (int h = warp; h < wave_n; h += PNP_BLOCK / 32) {
                 if (!s_valid[h]) continue;
                 double m[12];
 #pragma unroll
@@ -706,7 +715,7 @@ __global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpProblemSet S, Pnp
             info[2] = 0;
             info[3] = s_ctl[4];
         }
-        for (int i = tid; i < n; i += PNP_THREADS) mask[i] = 0;
+        for (int i = tid; i < n; i += PNP_BLOCK) mask[i] = 0;
         return;
     }
     // ---- E: inlier mask of the best model
@@ -714,7 +723,7 @@ __global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpProblemSet S, Pnp
         double m[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) m[i] = s_best[i];
-        for (int i = tid; i < n; i += PNP_THREADS)
+        for (int i = tid; i < n; i += PNP_BLOCK)
             mask[i] = is_inlier(P, m, p3[3 * i], p3[3 * i + 1], p3[3 * i + 2], p2[2 * i], p2[2 * i + 1]) ? 1 : 0;
     }
     __syncthreads();  // mask (global) written by this block is read below by other threads of the block
@@ -743,7 +752,7 @@ __global__ void __launch_bounds__(PNP_THREADS) k_pnp_ransac(PnpProblemSet S, Pnp
         rodrigues_vec_to_mat(param, R, need_jac ? jac : nullptr);
         double acc[28];
         for (int i = 0; i < 28; ++i) acc[i] = 0.0;
-        for (int i = tid; i < n; i += PNP_THREADS) {
+        for (int i = tid; i < n; i += PNP_BLOCK) {
             if (!mask[i]) continue;
             const double X = p3[3 * i], Y = p3[3 * i + 1], Z = p3[3 * i + 2];
             const double x = R[0] * X + R[1] * Y + R[2] * Z + param[3];
@@ -945,13 +954,13 @@ int launch_pnp_frontend(svo_ctx* c, int first, int ring, int n_frames) {
     StageTimer timer(c, 12);
     if (c->fe_mode & SVO_MODE_ORB) {  // 3-D points of the accepted matches (K12) and their pixels in left_t: list 0 (t2_left) of d_orb_pts
         PnpProblemSet S{c->d_orb_xyz, c->d_orb_pts, c->d_norb, c->kp_cap, 3, 0, first, ring, c->d_pnp_pose, c->d_pnp_info, c->d_pnp_mask_orb};
-        k_pnp_ransac<<<n_frames, PNP_THREADS, PNP_DYN_SMEM, c->stream>>>(S, P, c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
+        k_pnp_ransac<<<n_frames, PNP_BLOCK, PNP_DYN_SMEM, c->stream>>>(S, P, c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
         ++c->launches;
     }
     if (c->fe_mode & SVO_MODE_LK) {  // surviving tracks: list 3 (t2_left) of d_lkf_pts
         PnpProblemSet S{c->d_lkf_xyz, c->d_lkf_pts, c->d_nlkf, c->pt_cap, 5, 3, first, ring, c->d_pnp_pose + (size_t)16 * ring,
                         c->d_pnp_info + (size_t)4 * ring, c->d_pnp_mask_lk};
-        k_pnp_ransac<<<n_frames, PNP_THREADS, PNP_DYN_SMEM, c->stream>>>(S, P, c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
+        k_pnp_ransac<<<n_frames, PNP_BLOCK, PNP_DYN_SMEM, c->stream>>>(S, P, c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
         ++c->launches;
     }
     SVO_CUDA_TRY(c, cudaGetLastError());
@@ -986,7 +995,7 @@ extern "C" int svo_pnp_ransac(svo_ctx* c, const double* K, const float* pts3d, c
     SVO_CUDA_TRY(c, cudaMemcpyAsync(d2, pts2d, np * capz * 8, cudaMemcpyHostToDevice, c->stream));
     SVO_CUDA_TRY(c, cudaMemcpyAsync(dc, counts, np * 4, cudaMemcpyHostToDevice, c->stream));
     PnpProblemSet S{d3, d2, dc, (int)capz, 1, 0, 0, n_problems, dp, di, dm};
-    k_pnp_ransac<<<n_problems, PNP_THREADS, PNP_DYN_SMEM, c->stream>>>(S, make_params(K, iterations, reproj_error, confidence), c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
+    k_pnp_ransac<<<n_problems, PNP_BLOCK, PNP_DYN_SMEM, c->stream>>>(S, make_params(K, iterations, reproj_error, confidence), c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
     ++c->launches;
     SVO_CUDA_TRY(c, cudaGetLastError());
     std::vector<double> hp(np * 16);
