@@ -170,7 +170,7 @@ def run_b200(a):
     if world == 1 and not a.no_cpu_baseline:
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
-                                  "--config", a.config, "--width", str(w), "--height", str(h), "--nfeatures", str(a.nfeatures)],
+                                  "--config", a.config, "--width", str(w), "--height", str(h), "--nfeatures", str(a.nfeatures)] + (["--pnp"] if a.pnp else []),
                                  capture_output=True, text=True, timeout=900)
             cpu_baseline = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU measurement

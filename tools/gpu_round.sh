@@ -6,6 +6,11 @@ python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; t
 for cfg in ${CONFIGS:-c3 c4 c5}; do
   python bench.py --config $cfg ${CFG_ARGS:-} > gpurun_out/${TAG}_bench_${cfg}.json 2> gpurun_out/${TAG}_bench_${cfg}.err; tail -c 400 gpurun_out/${TAG}_bench_${cfg}.json; tail -2 gpurun_out/${TAG}_bench_${cfg}.err
 done
+# the pose step: bench line with K13 in the step (CPU arm with the real cv2.solvePnPRansac), and K13 alone on scenes with depth
+python bench.py --pnp > gpurun_out/${TAG}_bench_pnp.json 2> gpurun_out/${TAG}_bench_pnp.err; tail -c 300 gpurun_out/${TAG}_bench_pnp.json; tail -2 gpurun_out/${TAG}_bench_pnp.err
+python tools/bench_pnp.py > gpurun_out/${TAG}_pnp_alone.txt 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_pnp_alone_launches.csv python tools/bench_pnp.py > /dev/null 2>&1
+cat gpurun_out/${TAG}_pnp_alone.txt
 if [ -z "${NO_NCU:-}" ]; then
 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/ncu_l.log 2>&1
