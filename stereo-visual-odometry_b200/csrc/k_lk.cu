@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
     const int cur_u = P.first + f, cur = cur_u >= P.ring ? cur_u - P.ring : cur_u;
     const int seed_fs = cur == 0 ? P.ring - 1 : cur - 1;  // seeds: FAST corners of the previous left image
     const int n = P.standalone ? P.n_fixed : nfast[seed_fs];
-    const int pt = blockIdx.x * LW + warp;
-    if (pt >= n) return;  // warp-uniform; most warps of the fixed-size grid leave here
+    const int pt_first = blockIdx.x * LW + warp;
+    if (pt_first >= n) return;  // warp-uniform
     uint8_t* tile = s_mem + warp * WARP_SMEM;
     uint2* tmpl = reinterpret_cast<uint2*>(tile + TILE_AREA);  // [pixel y * 21 + x] = (256 - 512 * I, Ix | Iy << 16)
     // template layout: entry (round s, row-in-strip j, lane) at tmpl[(s * 7 + j) * 32 + lane]; strip g = 3 x + y / 7 of window
@@ -321,6 +321,11 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
 
     // the whole chain of calls for this point in one launch (tracking.cpp:593-618 chains four calls: each call's output list is
     // the next call's input, failed points included -- exactly what separate launches would read back from memory)
+    // grid-stride over the points of the frame: the grid is a fixed number of one-warp CTAs per frame (the point count is only
+    // known on the device), each takes points pt_first, pt_first + gridDim.x, ... -- with one CTA per POSSIBLE point (pt_cap) 82 %
+    // of the 933 k CTAs of a batch found nothing to do and still had to be scheduled
+    for (int pt = pt_first; pt < n; pt += gridDim.x * LW) {
+    __syncwarp();  // the previous point's last shared-memory reads are done before its tile / template are overwritten
     float px = 0.f, py = 0.f;
     for (int ci = 0; ci < P.ncalls; ++ci) {
     const LkCall& call = P.calls[ci];
@@ -673,6 +678,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
     px = nx;  // source point of the next call of the chain
     py = ny;
     }  // calls
+    }  // points
 }
 
 }  // namespace
@@ -744,7 +750,7 @@ int launch_lk_chain(svo_ctx* c, int first, int ring, int n_frames, int skip_firs
     }
     P.standalone = 0;
     P.want_err = want_err;
-    dim3 grid((c->pt_cap + LW - 1) / LW, n_frames);
+    dim3 grid(std::min((c->pt_cap + LW - 1) / LW, c->lk_grid_x), n_frames);
     auto kern = c->lk_deriv ? k_lk_track<true> : k_lk_track<false>;
     kern<<<grid, LW * 32, 0, c->stream>>>(P, c->d_fast_kps, c->d_nfast, c->d_lk_pts, c->d_lk_status, want_err ? c->d_lk_err : nullptr);
     ++c->launches;

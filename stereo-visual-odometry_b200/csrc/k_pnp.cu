@@ -2,7 +2,7 @@
 // SURVEY.md section 8f row 2): 3-D points of frame t-1 (K12) + their pixels in left_t -> rvec, tvec, rotation, inlier set.
 //
 // One CTA of 128 threads per problem (one matched list of one frame).  The RANSAC of OpenCV is sequential -- a better model
-// lowers the iteration limit (RANSACUpdateNumIters) -- so hypotheses are evaluated in WAVES of 128 and the sequential rule is
+// lowers the iteration limit (RANSACUpdateNumIters) -- so hypotheses are evaluated in WAVES of 64 and the sequential rule is
 // replayed over each wave's inlier counts afterwards; the result is what the sequential loop returns, because hypothesis k
 // depends only on the generator state, never on earlier models:
 //   A  thread 0 draws the wave's 5-point subsets: cv::RNG((uint64)-1) multiply-with-carry stream (the raw 32-bit stream is the
@@ -11,7 +11,7 @@
 //   B  thread h solves hypothesis h with EPnP in double (control points by PCA, barycentric coordinates, M^T M, OpenCV's
 //      one-sided Jacobi SVD on 12 x 12, three beta approximations x 5 Gauss-Newton steps, absolute orientation, the smallest
 //      mean reprojection error wins) -- one thread per hypothesis in local memory: the Jacobi sweeps are a sequential
-//      dependence chain, and 128 x 148 of them in flight is the parallelism;
+//      dependence chain, and 2 x 64 x 148 of them in flight is the parallelism;
 //   C  consensus: points staged through shared memory in chunks, warp w counts the inliers of hypotheses w, w + 4, ...:
 //      projection in double, rounded to float, squared distance in float, inlier iff <= (float)(thr * thr)  (ballot + popc);
 //   D  thread 0 replays `count > max(best, 4) -> keep, lower the limit` over the wave in hypothesis order; the loop ends when
@@ -29,10 +29,11 @@
 
 namespace {
 
-constexpr int PNP_THREADS = 128;   // hypotheses per wave (one thread each in step B)
-constexpr int PNP_BLOCK = 256;     // threads per CTA: steps C and E use all of them
+constexpr int PNP_THREADS = 64;    // hypotheses per wave (one thread each in step B)
+constexpr int PNP_BLOCK = 128;     // threads per CTA: steps C and E use all of them.  74 KB + 38 KB of shared memory and 128 x 255
+                                   // registers: two CTAs per SM, so the ORB and the LK list of every frame of a batch (2 x 128 CTAs) are resident at once
 constexpr int PNP_CHUNK = 1024;  // points staged per consensus chunk (20 KB)
-constexpr int PNP_DYN_SMEM = 144 * PNP_THREADS * 8;  // the 12 x 12 matrices of a wave: 147 KB
+constexpr int PNP_DYN_SMEM = 144 * PNP_THREADS * 8;  // the 12 x 12 matrices of a wave: 74 KB
 
 struct PnpParams {
     double fx, fy, cx, cy;
@@ -575,7 +576,7 @@ __device__ void block_sum(double* v, double* red /* [PNP_BLOCK / 32][NV] */) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(PNP_BLOCK) k_pnp_ransac(PnpProblemSet S, PnpParams P, const uint32_t* __restrict__ rng_table, int rng_table_n,
+__global__ void __launch_bounds__(PNP_BLOCK, 2) k_pnp_ransac(const PnpProblemSet S0, const PnpProblemSet S1, PnpParams P, const uint32_t* __restrict__ rng_table, int rng_table_n,
                                                             uint64_t rng_table_end_state) {
     extern __shared__ double s_mtm[];  // [144][PNP_THREADS]: M^T M / U^T of every hypothesis of the wave
     __shared__ float s_p3[PNP_CHUNK * 3];
@@ -591,6 +592,7 @@ __global__ void __launch_bounds__(PNP_BLOCK) k_pnp_ransac(PnpProblemSet S, PnpPa
     __shared__ int s_ctl[8];  // 0 niters, 1 max_good, 2 best_iter, 3 done, 4 iter (hypotheses replayed so far), 5 LM go-on flag
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const PnpProblemSet& S = blockIdx.y ? S1 : S0;  // list kind (front-end: 0 ORB associations, 1 LK tracks)
     int slot = S.first + blockIdx.x;
     if (slot >= S.ring) slot -= S.ring;
     const int n = S.counts[slot];
@@ -678,6 +680,9 @@ __global__ void __launch_bounds__(PNP_BLOCK) k_pnp_ransac(PnpProblemSet S, PnpPa
 #pragma unroll
                 for (int i = 0; i < 12; ++i) m[i] = s_model[h][i];
                 int cnt = 0;
+                // four points per lane in flight: one point is a ~45-instruction FP64 dependence chain (with a division), and a CTA
+                // has only four warps to hide it
+#pragma unroll 4
                 for (int i = lane; i < cn; i += 32) cnt += is_inlier(P, m, s_p3[3 * i], s_p3[3 * i + 1], s_p3[3 * i + 2], s_p2[2 * i], s_p2[2 * i + 1]) ? 1 : 0;
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
                 if (lane == 0) s_count[h] += cnt;
@@ -952,17 +957,14 @@ int launch_pnp_frontend(svo_ctx* c, int first, int ring, int n_frames) {
     const double K[9] = {c->proj1[0], c->proj1[1], c->proj1[2], c->proj1[4], c->proj1[5], c->proj1[6], c->proj1[8], c->proj1[9], c->proj1[10]};
     const PnpParams P = make_params(K, c->pnp_iters, c->pnp_reproj, c->pnp_conf);
     StageTimer timer(c, 12);
-    if (c->fe_mode & SVO_MODE_ORB) {  // 3-D points of the accepted matches (K12) and their pixels in left_t: list 0 (t2_left) of d_orb_pts
-        PnpProblemSet S{c->d_orb_xyz, c->d_orb_pts, c->d_norb, c->kp_cap, 3, 0, first, ring, c->d_pnp_pose, c->d_pnp_info, c->d_pnp_mask_orb};
-        k_pnp_ransac<<<n_frames, PNP_BLOCK, PNP_DYN_SMEM, c->stream>>>(S, P, c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
-        ++c->launches;
-    }
-    if (c->fe_mode & SVO_MODE_LK) {  // surviving tracks: list 3 (t2_left) of d_lkf_pts
-        PnpProblemSet S{c->d_lkf_xyz, c->d_lkf_pts, c->d_nlkf, c->pt_cap, 5, 3, first, ring, c->d_pnp_pose + (size_t)16 * ring,
-                        c->d_pnp_info + (size_t)4 * ring, c->d_pnp_mask_lk};
-        k_pnp_ransac<<<n_frames, PNP_BLOCK, PNP_DYN_SMEM, c->stream>>>(S, P, c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
-        ++c->launches;
-    }
+    // 3-D points of the accepted ORB matches (K12) and their pixels in left_t: list 0 (t2_left) of d_orb_pts;
+    // surviving LK tracks: list 3 (t2_left) of d_lkf_pts.  Both kinds in ONE launch (blockIdx.y), all CTAs resident at once.
+    const PnpProblemSet So{c->d_orb_xyz, c->d_orb_pts, c->d_norb, c->kp_cap, 3, 0, first, ring, c->d_pnp_pose, c->d_pnp_info, c->d_pnp_mask_orb};
+    const PnpProblemSet Sl{c->d_lkf_xyz, c->d_lkf_pts, c->d_nlkf, c->pt_cap, 5, 3, first, ring, c->d_pnp_pose + (size_t)16 * ring,
+                           c->d_pnp_info + (size_t)4 * ring, c->d_pnp_mask_lk};
+    const bool orb = c->fe_mode & SVO_MODE_ORB, lk = c->fe_mode & SVO_MODE_LK;
+    k_pnp_ransac<<<dim3(n_frames, orb && lk ? 2 : 1), PNP_BLOCK, PNP_DYN_SMEM, c->stream>>>(orb ? So : Sl, Sl, P, c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
+    ++c->launches;
     SVO_CUDA_TRY(c, cudaGetLastError());
     return SVO_OK;
 }
@@ -995,7 +997,7 @@ extern "C" int svo_pnp_ransac(svo_ctx* c, const double* K, const float* pts3d, c
     SVO_CUDA_TRY(c, cudaMemcpyAsync(d2, pts2d, np * capz * 8, cudaMemcpyHostToDevice, c->stream));
     SVO_CUDA_TRY(c, cudaMemcpyAsync(dc, counts, np * 4, cudaMemcpyHostToDevice, c->stream));
     PnpProblemSet S{d3, d2, dc, (int)capz, 1, 0, 0, n_problems, dp, di, dm};
-    k_pnp_ransac<<<n_problems, PNP_BLOCK, PNP_DYN_SMEM, c->stream>>>(S, make_params(K, iterations, reproj_error, confidence), c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
+    k_pnp_ransac<<<n_problems, PNP_BLOCK, PNP_DYN_SMEM, c->stream>>>(S, S, make_params(K, iterations, reproj_error, confidence), c->d_pnp_rng, c->pnp_rng_n, c->pnp_rng_end);
     ++c->launches;
     SVO_CUDA_TRY(c, cudaGetLastError());
     std::vector<double> hp(np * 16);

@@ -184,6 +184,7 @@ struct svo_ctx {
     // Scharr planes of the 4 LK levels (Ix | Iy << 16, zero border): the tracker's template setup interpolates them (K7c k_lk_deriv)
     LkLevelGeom lkd[SVO_LK_LEVELS];
     uint8_t* d_lkderiv = nullptr;
+    int lk_grid_x = 2048;   // one-warp CTAs per frame of the chain launch (grid-stride over the frame's points; SVO_LK_GRID overrides)
     bool lk_deriv = false;  // SVO_LK_DERIV=1 in the environment: template setup from Scharr planes (parity-green, but 4 % slower: more L1 / L2 traffic)
     std::vector<FastTile> ftiles;
     FastTile* d_ftiles = nullptr;

@@ -77,6 +77,7 @@ static int layout_aux(svo_ctx* c, int pt_cap) {
 
     // Scharr planes: 4 bytes per pixel, the same padding as the image planes, border zero (set once here: the kernel writes the interior)
     c->lk_deriv = getenv("SVO_LK_DERIV") != nullptr;  // measured alternative, off by default (see k_lk.cu / DESIGN.md)
+    if (const char* gx = getenv("SVO_LK_GRID")) c->lk_grid_x = std::max(32, atoi(gx));  // A/B measurements of the chain launch's grid
     if (c->lk_deriv) {
         size_t dtotal = 0;
         std::vector<size_t> doff(SVO_LK_LEVELS, 0);
