@@ -321,9 +321,8 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
 
     // the whole chain of calls for this point in one launch (tracking.cpp:593-618 chains four calls: each call's output list is
     // the next call's input, failed points included -- exactly what separate launches would read back from memory)
-    // grid-stride over the points of the frame: the grid is a fixed number of one-warp CTAs per frame (the point count is only
-    // known on the device), each takes points pt_first, pt_first + gridDim.x, ... -- with one CTA per POSSIBLE point (pt_cap) 82 %
-    // of the 933 k CTAs of a batch found nothing to do and still had to be scheduled
+    // grid-stride over the points of the frame (one pass with the default grid of pt_cap CTAs per frame; see svo_ctx::lk_grid_x: the
+    // 82 % of the 933 k one-warp CTAs of a batch that find no point cost nothing measurable)
     for (int pt = pt_first; pt < n; pt += gridDim.x * LW) {
     __syncwarp();  // the previous point's last shared-memory reads are done before its tile / template are overwritten
     float px = 0.f, py = 0.f;

@@ -184,7 +184,10 @@ struct svo_ctx {
     // Scharr planes of the 4 LK levels (Ix | Iy << 16, zero border): the tracker's template setup interpolates them (K7c k_lk_deriv)
     LkLevelGeom lkd[SVO_LK_LEVELS];
     uint8_t* d_lkderiv = nullptr;
-    int lk_grid_x = 2048;   // one-warp CTAs per frame of the chain launch (grid-stride over the frame's points; SVO_LK_GRID overrides)
+    // one-warp CTAs per frame of the chain launch; fewer than pt_cap makes the kernel grid-stride over the frame's points
+    // (SVO_LK_GRID; measured: 2048 is -0.4 % at 1241x376 / 128 frames but +8 % at 3840x2160 / 8 frames, where a CTA then walks ~10
+    // points and the last wave of CTAs runs half empty -- empty CTAs cost nothing measurable, so the default is one CTA per slot)
+    int lk_grid_x = 1 << 30;
     bool lk_deriv = false;  // SVO_LK_DERIV=1 in the environment: template setup from Scharr planes (parity-green, but 4 % slower: more L1 / L2 traffic)
     std::vector<FastTile> ftiles;
     FastTile* d_ftiles = nullptr;

@@ -2,9 +2,12 @@
 // Run / Step, System.cpp:28-104) on the B200 path: a KITTI-layout dataset directory is decoded by the frame source
 // (svo_source, System::NextFrame_kitti) and pushed through the throughput mode in batches; per frame it prints what
 // Tracking::ORB_StereoF2F_PnP_Track / LK_StereoF2F_PnP_Track hand to the pose back-end (number of matched / tracked points).
-// The pose back-end itself (solvePnPRansac, g2o, Pangolin viewer) is the reference's host code and is not part of this binary.
+// With --calib the pose step runs too (triangulation of (t1_left, t1_right) + solvePnPRansac against left_t, tracking.cpp:190-200 /
+// 464-501, on the device) and the per-frame rvec / tvec / inlier counts are printed.  Pose gating, g2o and the Pangolin viewer are the
+// reference's host code and are not part of this binary.
 //
 //   run_kitti_stereo <dataset_dir> [--mode orb|lk|both] [--batch 64] [--threads 8] [--width W --height H] [--nfeatures 1000] [--quiet]
+//                    [--calib fx fy cx cy baseline_times_fx]     (KITTI 00: 718.856 718.856 607.1928 185.2157 386.1448)
 // The image size is taken from the first left image unless given.
 #include <chrono>
 #include <cstdio>
@@ -40,7 +43,8 @@ int main(int argc, char** argv) {
     }
     const std::string dir = argv[1];
     int mode = SVO_MODE_ORB | SVO_MODE_LK, batch = 64, threads = 8, w = 0, h = 0, nfeatures = 1000;
-    bool quiet = false;
+    bool quiet = false, have_calib = false;
+    double calib[5] = {0, 0, 0, 0, 0};
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
         auto val = [&]() { return i + 1 < argc ? argv[++i] : ""; };
@@ -53,6 +57,10 @@ int main(int argc, char** argv) {
         else if (a == "--height") h = atoi(val());
         else if (a == "--nfeatures") nfeatures = atoi(val());
         else if (a == "--quiet") quiet = true;
+        else if (a == "--calib") {
+            for (double& v : calib) v = atof(val());
+            have_calib = calib[0] > 0 && calib[1] > 0;
+        }
     }
     if ((w <= 0 || h <= 0) && !probe_size(dir, &w, &h)) {
         fprintf(stderr, "cannot read %s/image_0/000000.png|pgm\n", dir.c_str());
@@ -76,7 +84,14 @@ int main(int argc, char** argv) {
     };
     if (svo_orb_configure(c, nfeatures, 1.2f, 8, 20, 7) != SVO_OK) die("svo_orb_configure");  // config/default.yaml ORBextractor.*
     if (svo_frontend_configure(c, w, h, mode, batch) != SVO_OK) die("svo_frontend_configure");
-    std::vector<int32_t> n_orb(batch), n_lk(batch), n_left(batch), n_fast(batch);
+    if (have_calib) {  // Sensors::projMatr1_ / projMatr2_ (sensors.cpp:8-24) and the parameters of config/default.yaml:80-82
+        const double P1[12] = {calib[0], 0, calib[2], 0, 0, calib[1], calib[3], 0, 0, 0, 1, 0};
+        const double P2[12] = {calib[0], 0, calib[2], -calib[4], 0, calib[1], calib[3], 0, 0, 0, 1, 0};
+        if (svo_frontend_set_projection(c, P1, P2) != SVO_OK) die("svo_frontend_set_projection");
+        if (svo_frontend_set_pnp(c, 1, 500, 0.5f, (double)0.99f) != SVO_OK) die("svo_frontend_set_pnp");
+    }
+    std::vector<int32_t> n_orb(batch), n_lk(batch), n_left(batch), n_fast(batch), info_orb((size_t)4 * batch), info_lk((size_t)4 * batch);
+    std::vector<double> pose_orb((size_t)16 * batch), pose_lk((size_t)16 * batch);
     svo_frontend_out out;
     memset(&out, 0, sizeof out);
     out.kp_cap = svo_orb_capacity(c, w, h);
@@ -85,6 +100,12 @@ int main(int argc, char** argv) {
     out.n_lk_matched = n_lk.data();
     out.n_left = n_left.data();
     out.n_fast = n_fast.data();
+    if (have_calib) {
+        out.orb_pose = pose_orb.data();
+        out.orb_pnp_info = info_orb.data();
+        out.lk_pose = pose_lk.data();
+        out.lk_pnp_info = info_lk.data();
+    }
     const auto t0 = std::chrono::steady_clock::now();
     const uint8_t *l = nullptr, *r = nullptr;
     int n = 0, frame = 0, pending = 0;
@@ -96,6 +117,16 @@ int main(int argc, char** argv) {
             if (!quiet)
                 printf("frame %06d: keypoints %d, ORB matches %d, FAST corners %d, LK tracks %d\n", frame, (mode & SVO_MODE_ORB) ? n_left[i] : 0,
                        (mode & SVO_MODE_ORB) ? n_orb[i] : 0, (mode & SVO_MODE_LK) ? n_fast[i] : 0, (mode & SVO_MODE_LK) ? n_lk[i] : 0);
+            if (!quiet && have_calib) {
+                const double* po = &pose_orb[(size_t)16 * i];
+                const double* pl = &pose_lk[(size_t)16 * i];
+                if (mode & SVO_MODE_ORB)
+                    printf("pose  %06d orb: ok %d inliers %d rvec %.6f %.6f %.6f tvec %.6f %.6f %.6f\n", frame, info_orb[4 * i], info_orb[4 * i + 1], po[0], po[1],
+                           po[2], po[3], po[4], po[5]);
+                if (mode & SVO_MODE_LK)
+                    printf("pose  %06d lk : ok %d inliers %d rvec %.6f %.6f %.6f tvec %.6f %.6f %.6f\n", frame, info_lk[4 * i], info_lk[4 * i + 1], pl[0], pl[1],
+                           pl[2], pl[3], pl[4], pl[5]);
+            }
         }
     };
     // pipelined: run(k + 1) is issued before download(k); the source's ring slot of batch k is recycled by the next svo_source_next

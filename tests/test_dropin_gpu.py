@@ -31,8 +31,8 @@ def test_run_kitti_stereo_app(pkg, tmp_path):
     w, h, F = 640, 200, 9
     left, right = pkg.synth_sequence(31, 0, F, w, h)
     pkg.write_sequence(str(tmp_path), left, right, fmt="png")
-    out = subprocess.run([exe, str(tmp_path), "--mode", "both", "--batch", "4", "--threads", "3", "--nfeatures", "400"], capture_output=True,
-                         text=True, timeout=300)
+    out = subprocess.run([exe, str(tmp_path), "--mode", "both", "--batch", "4", "--threads", "3", "--nfeatures", "400", "--calib", "718.856", "718.856",
+                          "607.1928", "185.2157", "386.1448"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = [l for l in out.stdout.splitlines() if l.startswith("frame ")]
     assert len(lines) == F and "done: 9 stereo pairs" in out.stdout
@@ -40,9 +40,24 @@ def test_run_kitti_stereo_app(pkg, tmp_path):
     ctx = pkg.Context(0, w, h, 2 * (F + 1))
     ctx.orb_configure(400, 1.2, 8, 20, 7)
     ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, F)
-    o = pkg.FrontendBuffers(F, ctx.orb_capacity(w, h), max(1024, w * h // 64), fields=("n_left", "n_orb_matched", "n_fast", "n_lk_matched"))
+    P1 = [718.856, 0, 607.1928, 0, 0, 718.856, 185.2157, 0, 0, 0, 1, 0]
+    P2 = [718.856, 0, 607.1928, -386.1448, 0, 718.856, 185.2157, 0, 0, 0, 1, 0]
+    ctx.frontend_set_projection(P1, P2)
+    ctx.frontend_set_pnp(True, 500, 0.5)
+    o = pkg.FrontendBuffers(F, ctx.orb_capacity(w, h), max(1024, w * h // 64),
+                            fields=("n_left", "n_orb_matched", "n_fast", "n_lk_matched", "orb_pose", "orb_pnp_info", "lk_pose", "lk_pnp_info"))
     ctx.frontend_batch(left, right, o)
     for i, l in enumerate(lines):
         nums = [int(t.strip(",")) for t in l.replace(":", " ").split() if t.strip(",").isdigit()]
         assert nums[1:] == [int(o.n_left[i]), int(o.n_orb_matched[i]), int(o.n_fast[i]), int(o.n_lk_matched[i])], l
+    # the pose lines (--calib): the app's batches of 4 and this single batch of 9 give the same per-frame poses
+    poses = [l.split() for l in out.stdout.splitlines() if l.startswith("pose ")]
+    assert len(poses) == 2 * F
+    for p in poses:
+        i, kind = int(p[1]), p[2].rstrip(":")
+        info, pose = (o.orb_pnp_info, o.orb_pose) if kind == "orb" else (o.lk_pnp_info, o.lk_pose)
+        vals = [t for t in p if t.replace(".", "").replace("-", "").isdigit()]
+        assert int(p[p.index("ok") + 1]) == int(info[i, 0]) and int(p[p.index("inliers") + 1]) == int(info[i, 1]), p
+        got = np.array([float(x) for x in p[p.index("rvec") + 1:p.index("rvec") + 4]] + [float(x) for x in p[p.index("tvec") + 1:p.index("tvec") + 4]])
+        assert np.abs(got - pose[i, :6]).max() <= 1e-6, (p, pose[i, :6])
     ctx.close()
