@@ -40,6 +40,15 @@ typedef Point_<float> Point2f;
 typedef Point_<int> Point2i;
 typedef Point2i Point;
 
+// cv::Vec3f (what Tracking::rotationMatrixToEulerAngles returns, tracking.h:99)
+struct Vec3f {
+    float val[3];
+    Vec3f() : val{0, 0, 0} {}
+    Vec3f(float a, float b, float c) : val{a, b, c} {}
+    float& operator[](int i) { return val[i]; }
+    const float& operator[](int i) const { return val[i]; }
+};
+
 struct Size {
     int width, height;
     Size() : width(0), height(0) {}

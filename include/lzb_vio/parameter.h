@@ -15,6 +15,8 @@ struct Parameter {
     int iterationsCount_ = 500;         // :80
     float reprojectionError_ = 0.5f;    // :81
     float confidence_ = 0.99f;          // :82
+    double minmove_ = 0.05;             // :87
+    double maxmove_ = 10;               // :88
     int nFeatures_ = 2000;        // config/default.yaml:93
     float fScaleFactor_ = 1.2f;   // :92
     int nLevels_ = 8;             // :91

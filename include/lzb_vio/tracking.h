@@ -63,6 +63,16 @@ public:
     bool OpenCV_EstimatePose_PnP(cv::Mat& projMatrl, std::vector<cv::Point2f>& pointsLeft_t2, cv::Mat& points3D_t1, cv::Mat& rotation,
                                  cv::Mat& translation);
     std::vector<int> last_inliers_;
+    // Sensors::projMatr1_ / projMatr2_ (sensors.cpp:8-24; 3 x 4 CV_64F).  The reference reads them from sensors_; Sensors (YAML /
+    // calibration files) is outside this library, so the application hands the two matrices over once.  With them set and no
+    // pose_backend_, *_StereoF2F_PnP_Track run the reference's whole tail except the display: triangulation, OpenCV_EstimatePose_PnP,
+    // the Euler-angle / step-length gates and frame_pose_ = frame_pose_ * [R t; 0 1]^-1 (tracking.cpp:186-246, 288-341).
+    void SetProjection(const cv::Mat& projMatrl, const cv::Mat& projMatrr);
+    cv::Vec3f rotationMatrixToEulerAngles(cv::Mat& R);  // tracking.cpp:440-463
+    bool EstimateAndAccumulatePose(std::vector<cv::Point2f>& matched_t1_left, std::vector<cv::Point2f>& matched_t1_right,
+                                   std::vector<cv::Point2f>& matched_t2_left, bool lk_mode);
+    cv::Mat frame_pose_;  // 4 x 4 CV_64F, identity at start (tracking.h:117)
+    double Px_ = 0, Py_ = 0, Pz_ = 0;
     void deleteBadmatchFeatures(std::vector<cv::Point2f>& points0, std::vector<cv::Point2f>& points1, std::vector<cv::Point2f>& points2,
                                 std::vector<cv::Point2f>& points3, std::vector<cv::Point2f>& points0_return,
                                 std::vector<unsigned char>& status0, std::vector<unsigned char>& status1,
@@ -86,6 +96,8 @@ private:
     double inlier_rate_ = 0.01;
     int iterationsCount_ = 500;
     float reprojectionError_ = 0.5f, confidence_ = 0.99f;
+    double minmove_ = 0.05, maxmove_ = 10;
+    cv::Mat projMatrl_, projMatrr_;
     int nFeatures_ = 2000, nLevels_ = 8, fIniThFAST_ = 20, fMinThFAST_ = 7;
     float fScaleFactor_ = 1.2f;
 };

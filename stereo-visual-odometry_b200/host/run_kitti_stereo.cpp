@@ -8,8 +8,11 @@
 //
 //   run_kitti_stereo <dataset_dir> [--mode orb|lk|both] [--batch 64] [--threads 8] [--width W --height H] [--nfeatures 1000] [--quiet]
 //                    [--calib fx fy cx cy baseline_times_fx]     (KITTI 00: 718.856 718.856 607.1928 185.2157 386.1448)
+//                    [--traj poses.txt]    with --calib: frame_pose_ after every frame (tracking.cpp:213-222 gates and accumulation, ORB list
+//                                          when the ORB mode runs, else the LK list), 12 numbers per line like the KITTI odometry ground truth
 // The image size is taken from the first left image unless given.
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +48,7 @@ int main(int argc, char** argv) {
     int mode = SVO_MODE_ORB | SVO_MODE_LK, batch = 64, threads = 8, w = 0, h = 0, nfeatures = 1000;
     bool quiet = false, have_calib = false;
     double calib[5] = {0, 0, 0, 0, 0};
+    std::string traj_path;
     for (int i = 2; i < argc; ++i) {
         const std::string a = argv[i];
         auto val = [&]() { return i + 1 < argc ? argv[++i] : ""; };
@@ -57,6 +61,7 @@ int main(int argc, char** argv) {
         else if (a == "--height") h = atoi(val());
         else if (a == "--nfeatures") nfeatures = atoi(val());
         else if (a == "--quiet") quiet = true;
+        else if (a == "--traj") traj_path = val();
         else if (a == "--calib") {
             for (double& v : calib) v = atof(val());
             have_calib = calib[0] > 0 && calib[1] > 0;
@@ -110,8 +115,54 @@ int main(int argc, char** argv) {
     const uint8_t *l = nullptr, *r = nullptr;
     int n = 0, frame = 0, pending = 0;
     long long sum_orb = 0, sum_lk = 0;
+    // Tracking::frame_pose_ (tracking.h:117): accumulated on the host from the per-frame pose, with the reference's gates
+    double frame_pose[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    int accepted = 0;
+    FILE* traj = (!traj_path.empty() && have_calib) ? fopen(traj_path.c_str(), "w") : nullptr;
+    auto accumulate = [&](const double* pose16, int ok, int inliers, int n_list, bool lk_mode) {
+        if (!ok || n_list <= 0 || (double)inliers / n_list < 0.01) return false;  // inlier_rate (config/default.yaml:77)
+        const double *R = pose16 + 6, *t = pose16 + 3;
+        const float sy = (float)std::sqrt(R[0] * R[0] + R[3] * R[3]);  // rotationMatrixToEulerAngles (tracking.cpp:440-463)
+        float ex, ey, ez;
+        if (sy >= 1e-6f) {
+            ex = (float)std::atan2(R[7], R[8]);
+            ey = (float)std::atan2(-R[6], sy);
+            ez = (float)std::atan2(R[3], R[0]);
+        } else {
+            ex = (float)std::atan2(-R[5], R[4]);
+            ey = (float)std::atan2(-R[6], sy);
+            ez = 0;
+        }
+        if (!(std::fabs(ex) < 0.1 && std::fabs(ey) < 0.1 && std::fabs(ez) < 0.1)) return false;
+        const double n2 = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+        const double hi = lk_mode ? 100.0 : 10.0 * 10.0, lo = lk_mode ? 0.0005 * 0.0005 : 0.05 * 0.05;  // :312 literals / maxmove, minmove
+        if (!(n2 < hi && n2 > lo)) return false;
+        double inv[16] = {0}, prod[16];
+        for (int r = 0; r < 3; ++r) {
+            for (int c2 = 0; c2 < 3; ++c2) inv[4 * r + c2] = R[3 * c2 + r];
+            inv[4 * r + 3] = -(R[r] * t[0] + R[3 + r] * t[1] + R[6 + r] * t[2]);
+        }
+        inv[15] = 1.0;
+        for (int r = 0; r < 4; ++r)
+            for (int c2 = 0; c2 < 4; ++c2) {
+                double v = 0;
+                for (int k2 = 0; k2 < 4; ++k2) v += frame_pose[4 * r + k2] * inv[4 * k2 + c2];
+                prod[4 * r + c2] = v;
+            }
+        memcpy(frame_pose, prod, sizeof prod);
+        return true;
+    };
     auto report = [&](int k) {
         for (int i = 0; i < k; ++i, ++frame) {
+            if (have_calib) {
+                const bool use_orb = mode & SVO_MODE_ORB;
+                const bool ok = use_orb ? accumulate(&pose_orb[(size_t)16 * i], info_orb[4 * i], info_orb[4 * i + 1], n_orb[i], false)
+                                        : accumulate(&pose_lk[(size_t)16 * i], info_lk[4 * i], info_lk[4 * i + 1], n_lk[i], true);
+                accepted += ok;
+                if (traj) {
+                    for (int q = 0; q < 12; ++q) fprintf(traj, "%.9e%c", frame_pose[q], q == 11 ? '\n' : ' ');
+                }
+            }
             sum_orb += n_orb[i];
             sum_lk += n_lk[i];
             if (!quiet)
@@ -147,6 +198,10 @@ int main(int argc, char** argv) {
     }
     const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("done: %d stereo pairs in %.3f s (%.1f pairs/s incl. decoding), ORB matches %lld, LK tracks %lld\n", frame, s, frame / s, sum_orb, sum_lk);
+    if (have_calib)
+        printf("trajectory: %d of %d frame-to-frame poses accepted, final position %.4f %.4f %.4f\n", accepted, frame > 0 ? frame - 1 : 0, frame_pose[3],
+               frame_pose[7], frame_pose[11]);
+    if (traj) fclose(traj);
     svo_source_close(src);
     svo_ctx_destroy(c);
     return frame == total ? 0 : 1;

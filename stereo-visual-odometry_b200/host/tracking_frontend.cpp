@@ -17,6 +17,9 @@ Tracking::Tracking(System* system, Parameter::Ptr parameter, std::shared_ptr<Sen
     Readparameter();
     mpORBextractorLeft_ = new ORBextractor(nFeatures_, fScaleFactor_, nLevels_, fIniThFAST_, fMinThFAST_);  // tracking.cpp:20
     mpORBextractorLeft_->SetExportPyramid(false);  // nothing in Tracking reads mvImagePyramid
+    frame_pose_.create(4, 4, CV_64F);
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) frame_pose_.at<double>(r, c) = r == c ? 1.0 : 0.0;
 }
 
 Tracking::~Tracking() { delete mpORBextractorLeft_; }
@@ -29,6 +32,8 @@ void Tracking::Readparameter() {  // tracking.cpp:22-47, front-end fields
     iterationsCount_ = parameter_->iterationsCount_;
     reprojectionError_ = parameter_->reprojectionError_;
     confidence_ = parameter_->confidence_;
+    minmove_ = parameter_->minmove_;
+    maxmove_ = parameter_->maxmove_;
     nFeatures_ = parameter_->nFeatures_;
     fScaleFactor_ = parameter_->fScaleFactor_;
     nLevels_ = parameter_->nLevels_;
@@ -74,7 +79,64 @@ bool Tracking::ORB_StereoF2F_PnP_Track() {  // tracking.cpp:168-186; the pose ba
     std::vector<cv::Point2f> matched_t1_left, matched_t2_left, matched_t1_right;
     const int n = ORB_Robust_Find_MuliImage_MatchedFeatures(matched_t2_left, matched_t1_left, matched_t1_right);
     if (n < num_features_tracking_) return false;
-    return pose_backend_ ? pose_backend_(matched_t1_left, matched_t1_right, matched_t2_left) : true;
+    if (pose_backend_) return pose_backend_(matched_t1_left, matched_t1_right, matched_t2_left);
+    return projMatrl_.empty() ? true : EstimateAndAccumulatePose(matched_t1_left, matched_t1_right, matched_t2_left, false);
+}
+
+void Tracking::SetProjection(const cv::Mat& projMatrl, const cv::Mat& projMatrr) {
+    projMatrl_ = projMatrl.clone();
+    projMatrr_ = projMatrr.clone();
+}
+
+cv::Vec3f Tracking::rotationMatrixToEulerAngles(cv::Mat& R) {  // tracking.cpp:440-463
+    const float sy = (float)std::sqrt(R.at<double>(0, 0) * R.at<double>(0, 0) + R.at<double>(1, 0) * R.at<double>(1, 0));
+    const bool singular = sy < 1e-6;
+    float x, y, z;
+    if (!singular) {
+        x = (float)std::atan2(R.at<double>(2, 1), R.at<double>(2, 2));
+        y = (float)std::atan2(-R.at<double>(2, 0), sy);
+        z = (float)std::atan2(R.at<double>(1, 0), R.at<double>(0, 0));
+    } else {
+        x = (float)std::atan2(-R.at<double>(1, 2), R.at<double>(1, 1));
+        y = (float)std::atan2(-R.at<double>(2, 0), sy);
+        z = 0;
+    }
+    return cv::Vec3f(x, y, z);
+}
+
+// tracking.cpp:186-246 (ORB mode) / 288-341 (LK mode) without the display calls
+bool Tracking::EstimateAndAccumulatePose(std::vector<cv::Point2f>& matched_t1_left, std::vector<cv::Point2f>& matched_t1_right,
+                                         std::vector<cv::Point2f>& matched_t2_left, bool lk_mode) {
+    cv::Mat points3D_t1, rotation, translation;
+    TriangulateMatched(projMatrl_, projMatrr_, matched_t1_left, matched_t1_right, points3D_t1);
+    if (!OpenCV_EstimatePose_PnP(projMatrl_, matched_t2_left, points3D_t1, rotation, translation)) return false;
+    const cv::Vec3f e = rotationMatrixToEulerAngles(rotation);
+    if (!(std::fabs(e[1]) < 0.1 && std::fabs(e[0]) < 0.1 && std::fabs(e[2]) < 0.1)) return false;
+    const double t[3] = {translation.at<double>(0, 0), translation.at<double>(1, 0), translation.at<double>(2, 0)};
+    const double pose_norm2 = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+    // the LK branch compares against the literals 100 and 0.0005^2 (:312), the ORB branch against maxmove_ / minmove_ (:213)
+    const double hi = lk_mode ? 100.0 : maxmove_ * maxmove_, lo = lk_mode ? 0.0005 * 0.0005 : minmove_ * minmove_;
+    if (!(pose_norm2 < hi && pose_norm2 > lo)) return false;
+    // rigid_body_transformation = [R t; 0 0 0 1]^-1 = [R^T, -R^T t]; frame_pose_ = frame_pose_ * rigid_body_transformation
+    double inv[16] = {0};
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) inv[4 * r + c] = rotation.at<double>(c, r);
+        inv[4 * r + 3] = -(rotation.at<double>(0, r) * t[0] + rotation.at<double>(1, r) * t[1] + rotation.at<double>(2, r) * t[2]);
+    }
+    inv[15] = 1.0;
+    double prod[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += frame_pose_.at<double>(r, k) * inv[4 * k + c];
+            prod[4 * r + c] = s;
+        }
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) frame_pose_.at<double>(r, c) = prod[4 * r + c];
+    Px_ = frame_pose_.at<double>(0, 3);
+    Py_ = frame_pose_.at<double>(1, 3);
+    Pz_ = frame_pose_.at<double>(2, 3);
+    return true;
 }
 
 bool Tracking::LK_StereoF2F_PnP_Track() {  // tracking.cpp:258-288
@@ -84,7 +146,8 @@ bool Tracking::LK_StereoF2F_PnP_Track() {  // tracking.cpp:258-288
     for (auto& feature : last_frame_->features_left_) matched_t1_left.push_back(feature->position_.pt);
     const int n = LK_Robust_Find_MuliImage_MatchedFeatures(matched_t2_left, matched_t2_right, matched_t1_left, matched_t1_right);
     if (n < num_features_tracking_) return false;
-    return pose_backend_ ? pose_backend_(matched_t1_left, matched_t1_right, matched_t2_left) : true;
+    if (pose_backend_) return pose_backend_(matched_t1_left, matched_t1_right, matched_t2_left);
+    return projMatrl_.empty() ? true : EstimateAndAccumulatePose(matched_t1_left, matched_t1_right, matched_t2_left, true);
 }
 
 void Tracking::TriangulateMatched(cv::Mat& projMatrl, cv::Mat& projMatrr, std::vector<cv::Point2f>& points_t1_left,

@@ -146,6 +146,25 @@ int main() {
         for (int i = 0; i < 9; ++i) CHECK(std::fabs(rotation.at<double>(i / 3, i % 3) - out[6 + i]) <= 1e-9);
         for (int i = 0; i < 3; ++i) CHECK(std::fabs(translation.at<double>(i, 0) - out[3 + i]) <= 1e-9);
         CHECK(pose_ok == (ok && !((double)info[0] / n < 0.01)));
+        // ---- 2c. the same frames with the projection matrices handed over and no pose_backend_: the reference's whole tail
+        //          (tracking.cpp:186-246 minus the display) -> frame_pose_ = [R t; 0 1]^-1 when the gates pass
+        Tracking tr2(nullptr, p, nullptr);
+        tr2.SetProjection(projl, projr);
+        CHECK(tr2.AddFrame(make_frame(1000, 3, w, h)));
+        const bool accepted = tr2.AddFrame(make_frame(1000, 4, w, h));
+        const cv::Vec3f e = tr.rotationMatrixToEulerAngles(rotation);
+        const double tx = translation.at<double>(0, 0), ty = translation.at<double>(1, 0), tz = translation.at<double>(2, 0), n2 = tx * tx + ty * ty + tz * tz;
+        const bool expect = pose_ok && std::fabs(e[0]) < 0.1 && std::fabs(e[1]) < 0.1 && std::fabs(e[2]) < 0.1 && n2 < 100.0 && n2 > 0.05 * 0.05;
+        CHECK(accepted == expect);
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c) {
+                double want = r == c ? 1.0 : 0.0;
+                if (expect && r < 3 && c < 3) want = rotation.at<double>(c, r);
+                if (expect && r < 3 && c == 3)
+                    want = -(rotation.at<double>(0, r) * tx + rotation.at<double>(1, r) * ty + rotation.at<double>(2, r) * tz);
+                CHECK(std::fabs(tr2.frame_pose_.at<double>(r, c) - want) <= 1e-9);
+            }
+        std::printf("pose step: %d of %d inliers, |t| = %.4f, accepted %d\n", info[0], n, std::sqrt(n2), (int)accepted);
     }
     // ---- 3. Tracking, LK mode
     {

@@ -36,6 +36,17 @@ typedef Point_<int> Point2i;
 typedef Point_<float> Point2f;
 typedef Point2i Point;
 
+template <typename _Tp, int cn>
+class Vec {
+public:
+    Vec();
+    Vec(_Tp v0, _Tp v1, _Tp v2);
+    _Tp& operator[](int i);
+    const _Tp& operator[](int i) const;
+    _Tp val[cn];
+};
+typedef Vec<float, 3> Vec3f;
+
 template <typename _Tp>
 class Size_ {
 public:
