@@ -32,7 +32,7 @@ def test_run_kitti_stereo_app(pkg, tmp_path):
     left, right = pkg.synth_sequence(31, 0, F, w, h)
     pkg.write_sequence(str(tmp_path), left, right, fmt="png")
     out = subprocess.run([exe, str(tmp_path), "--mode", "both", "--batch", "4", "--threads", "3", "--nfeatures", "400", "--calib", "718.856", "718.856",
-                          "607.1928", "185.2157", "386.1448"], capture_output=True, text=True, timeout=300)
+                          "607.1928", "185.2157", "386.1448", "--traj", str(tmp_path / "traj.txt")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = [l for l in out.stdout.splitlines() if l.startswith("frame ")]
     assert len(lines) == F and "done: 9 stereo pairs" in out.stdout
@@ -60,4 +60,19 @@ def test_run_kitti_stereo_app(pkg, tmp_path):
         assert int(p[p.index("ok") + 1]) == int(info[i, 0]) and int(p[p.index("inliers") + 1]) == int(info[i, 1]), p
         got = np.array([float(x) for x in p[p.index("rvec") + 1:p.index("rvec") + 4]] + [float(x) for x in p[p.index("tvec") + 1:p.index("tvec") + 4]])
         assert np.abs(got - pose[i, :6]).max() <= 1e-6, (p, pose[i, :6])
+    # --traj: one 3 x 4 pose per frame, the first the identity, every later one the previous times an accepted inverse step or unchanged
+    traj = np.loadtxt(str(tmp_path / "traj.txt")).reshape(-1, 3, 4)
+    assert traj.shape[0] == F and np.allclose(traj[0], np.eye(4)[:3])
+    acc = np.eye(4)
+    for i in range(1, F):
+        if o.orb_pnp_info[i, 0] and o.n_orb_matched[i] > 0 and o.orb_pnp_info[i, 1] / o.n_orb_matched[i] >= 0.01:
+            R, t = o.orb_pose[i, 6:15].reshape(3, 3), o.orb_pose[i, 3:6]
+            sy = np.float32(np.sqrt(R[0, 0] ** 2 + R[1, 0] ** 2))
+            e = (np.arctan2(R[2, 1], R[2, 2]), np.arctan2(-R[2, 0], sy), np.arctan2(R[1, 0], R[0, 0]))
+            if all(abs(np.float32(v)) < 0.1 for v in e) and 0.05 ** 2 < t @ t < 100:
+                T = np.eye(4)
+                T[:3, :3], T[:3, 3] = R.T, -R.T @ t
+                acc = acc @ T
+        assert np.abs(traj[i] - acc[:3]).max() <= 1e-7, i
+    assert "trajectory:" in out.stdout
     ctx.close()
