@@ -22,6 +22,7 @@ for (w, h, nfeat, B, total) in ((333, 257, 300, 2, 5), (1241, 376, 1000, 3, 7), 
     ctx.orb_configure(nfeat, 1.2, 8, 20, 7)
     ctx.frontend_configure(w, h, pkg.MODE_ORB | pkg.MODE_LK, B)
     ctx.frontend_set_projection(P1, P2)
+    ctx.frontend_set_pnp(True, 500 if w < 1500 else 70, 0.5)  # the pose step on both filtered lists of every frame (K13)
     kc, pc = ctx.orb_capacity(w, h), max(1024, w * h // 64)
     for f0 in range(0, total, B):  # several batches: the slot ring wraps
         n = min(B, total - f0)
@@ -49,8 +50,16 @@ for (w, h, nfeat, B, total) in ((333, 257, 300, 2, 5), (1241, 376, 1000, 3, 7), 
     p3, s3, _ = ctx.lk_track(right[1], left[1], p2)
     p0r, s4, _ = ctx.lk_track(left[1], left[0], p3)
     ctx.lk_chain_filter(pts, p1, p2, p3, p0r, s1, s2, s3, s4, 3.0)
-    ctx.triangulate_points(P1, P2, pts, p1)
-    calls += 6
+    _, xyz = ctx.triangulate_points(P1, P2, pts, p1)
+    # the standalone pose call: one list, then a ragged batch whose longest list fills its capacity exactly
+    ctx.pnp_ransac(P1[:, :3], xyz, p3, iterations=60)
+    nb = min(len(xyz), 700)
+    b3 = np.zeros((4, nb, 3), np.float32)
+    b2 = np.zeros((4, nb, 2), np.float32)
+    b3[:] = xyz[:nb]
+    b2[:] = p3[:nb]
+    ctx.pnp_ransac(P1[:, :3], b3, b2, [nb, 0, 5, nb // 2], iterations=40)
+    calls += 8
     bad = pkg.guard_check()
     if bad:
         print(f"GUARD {bad} {calls} at {w}x{h}")
