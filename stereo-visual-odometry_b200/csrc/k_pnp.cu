@@ -930,6 +930,7 @@ int svo_pnp_free_frontend(svo_ctx* c) {
 extern "C" int svo_frontend_set_pnp(svo_ctx* c, int enable, int iterations, float reproj_error, double confidence) {
     if (!c) return SVO_ERR_INVALID;
     if (!c->fe_configured) return c->fail(SVO_ERR_INVALID, "svo_frontend_configure() first");
+    if (c->fe_nq > 0) return c->fail(SVO_ERR_INVALID, "svo_frontend_set_pnp: download (or discard) the pending runs first: their pose buffers would be freed");
     cudaSetDevice(c->device);
     SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (!enable) return svo_pnp_free_frontend(c);
