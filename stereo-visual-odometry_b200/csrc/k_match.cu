@@ -243,7 +243,10 @@ __global__ void __launch_bounds__(MTHR) k_match_mma_frontend(const uint32_t* __r
 
 int launch_match_frontend(svo_ctx* c, int first, int ring, int n_frames, int skip_first) {
     StageTimer t(c, 5);
-    if (c->match_mma && c->kp_cap < 65536 && c->d_xdesc) {
+    if (c->match_tc && c->kp_cap < 65536) {  // tcgen05 form: packed descriptors in, no expansion pass (k_match_tc.cu)
+        int rc = launch_match_tc_frontend(c, first, ring, n_frames, skip_first);
+        if (rc != SVO_OK) return rc;
+    } else if (c->match_mma && c->kp_cap < 65536 && c->d_xdesc) {
         // expand the descriptors of the batch's frames (both sides; the carried frame was expanded by the batch that produced it)
         const SlotMap both{2, ring, first, ring};
         std::vector<int> slots(2 * n_frames);
@@ -281,7 +284,8 @@ extern "C" int svo_match_hamming(svo_ctx* c, const uint8_t* q, int nq, const uin
     cudaSetDevice(c->device);
     const size_t qb = svo_align((size_t)nq * 32, 256), tb = svo_align((size_t)std::max(nt, 1) * 32, 256), ob = svo_align((size_t)nq * 4, 256);
     // the tensor-core path needs the descriptors expanded to one byte per bit (256 B each) and their popcounts
-    const bool mma = getenv("SVO_MATCH_POPC") == nullptr && nt > 0 && nt < 65536;
+    const bool tc = getenv("SVO_MATCH_POPC") == nullptr && getenv("SVO_MATCH_IMMA") == nullptr && nt < 65536;
+    const bool mma = !tc && getenv("SVO_MATCH_POPC") == nullptr && nt > 0 && nt < 65536;
     const size_t xq = mma ? svo_align((size_t)nq * 256, 256) : 0, xt = mma ? svo_align((size_t)nt * 256, 256) : 0;
     const size_t pqb = mma ? svo_align((size_t)nq * 4, 256) : 0, ptb = mma ? svo_align((size_t)nt * 4, 256) : 0;
     int rc = svo_ensure_scratch(c, qb + tb + 2 * ob + xq + xt + pqb + ptb);
@@ -298,7 +302,9 @@ extern "C" int svo_match_hamming(svo_ctx* c, const uint8_t* q, int nq, const uin
     if (nt > 0) SVO_CUDA_TRY(c, cudaMemcpyAsync(dt, t, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
     {
         StageTimer tm(c, 5);
-        if (mma) {
+        if (tc) {
+            if ((rc = launch_match_tc_one(c, dq, nq, dt, nt, di, dd)) != SVO_OK) return rc;
+        } else if (mma) {
             k_match_expand<<<dim3((nq + 63) / 64, 1), 256, 0, c->stream>>>(dq, nullptr, nq, dxq, dpq, nullptr, nq);
             k_match_expand<<<dim3((nt + 63) / 64, 1), 256, 0, c->stream>>>(dt, nullptr, nt, dxt, dpt, nullptr, nt);
             k_match_mma_one<<<(nq + MQ - 1) / MQ, MTHR, 0, c->stream>>>(dxq, dpq, nq, dxt, dpt, nt, di, dd);

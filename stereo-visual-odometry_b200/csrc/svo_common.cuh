@@ -236,6 +236,7 @@ struct svo_ctx {
     int* d_xslots = nullptr;
     size_t xslots_cap = 0;
     bool match_mma = true;        // SVO_MATCH_POPC=1 in the environment selects the POPC kernel (A/B measurements)
+    bool match_tc = true;         // K6 on tcgen05 (k_match_tc.cu); SVO_MATCH_IMMA=1 / SVO_MATCH_POPC=1 select the older forms
 
     // ---- frontend state
     int fe_mode = 0, fe_max_frames = 0, fe_ring = 0, fe_head = -1, fe_pending = 0, fe_first = 0;
@@ -302,6 +303,8 @@ int launch_fast_cells(svo_ctx* c, const SlotMap& map, int n_img);               
 int launch_octree(svo_ctx* c, const SlotMap& map, int n_img);                        // K3
 int launch_describe(svo_ctx* c, const SlotMap& map, int n_img);                      // K4 + K5
 int launch_match_frontend(svo_ctx* c, int first, int ring, int n_frames, int skip_first);  // K6
+int launch_match_tc_frontend(svo_ctx* c, int first, int ring, int n_frames, int skip_first);             // K6, tcgen05 form (k_match_tc.cu)
+int launch_match_tc_one(svo_ctx* c, const uint8_t* dq, int nq, const uint8_t* dt, int nt, int* di, int* dd);
 int launch_orb_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_first);      // K10
 int launch_lk_filter(svo_ctx* c, int first, int ring, int n_frames, int skip_first);       // K11
 int launch_triangulate_frontend(svo_ctx* c, int first, int ring, int n_frames);            // K12

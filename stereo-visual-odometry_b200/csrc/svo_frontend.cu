@@ -219,7 +219,8 @@ extern "C" int svo_frontend_configure(svo_ctx* c, int w, int h, int mode, int ma
         }
         SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_match, sizeof(int) * 4 * (size_t)c->kp_cap * c->fe_ring));
         c->match_mma = getenv("SVO_MATCH_POPC") == nullptr;
-        if (c->match_mma) {
+        c->match_tc = c->match_mma && getenv("SVO_MATCH_IMMA") == nullptr;  // default: the tcgen05 form, which needs no expanded copies
+        if (c->match_mma && !c->match_tc) {
             SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_xdesc, (size_t)256 * c->kp_cap * c->max_images));
             SVO_CUDA_TRY(c, svo_dev_malloc(&c->d_xpop, sizeof(int) * (size_t)c->kp_cap * c->max_images));
             c->xslots_cap = (size_t)2 * max_frames;
