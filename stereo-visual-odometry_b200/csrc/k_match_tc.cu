@@ -58,7 +58,10 @@ __device__ __forceinline__ void match_core_tc(const uint32_t* __restrict__ q, in
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t s_mbar;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_tpop[TN];
+    // per train column of the tile: (|t| + 256) << 16 | train index; 0xFFFFFFFF past the end of the train set.  The key of (q, t) is
+    // base - (<q, t> << 17) + (|q| << 16) - (256 << 16); the +256 keeps the partial key non-negative (2 <q, t> <= 2 |t|), |q| is added once
+    // at the end (the minimum over t does not depend on it)
+    __shared__ __align__(16) uint32_t s_tkey[TN];
     __shared__ uint32_t s_best[TM];
     uint8_t* sm = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = sm;
@@ -90,7 +93,11 @@ __device__ __forceinline__ void match_core_tc(const uint32_t* __restrict__ q, in
     uint32_t best = 0xFFFFFFFFu;
     uint32_t parity = 0;
     for (int t0 = 0; t0 < nt; t0 += TN) {
-        s_tpop[tid] = expand_row(sB, tid, t + (size_t)(t0 + tid) * 8, t0 + tid < nt);
+        {
+            const bool tv = t0 + tid < nt;
+            const int tp = expand_row(sB, tid, t + (size_t)(t0 + tid) * 8, tv);
+            s_tkey[tid] = tv ? ((uint32_t)(tp + 256) << 16) | (uint32_t)(t0 + tid) : 0xFFFFFFFFu;
+        }
         asm volatile("fence.proxy.async.shared::cta;");  // the expanded operands (generic-proxy stores) become visible to the tensor core
         __syncthreads();
         if (tid == 0) {
@@ -130,14 +137,13 @@ __device__ __forceinline__ void match_core_tc(const uint32_t* __restrict__ q, in
                   "=r"(v[31])
                 : "r"(tbase + (uint32_t)c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;");
-            const int col0 = 128 * (warp >> 2) + c0;
+            const uint4* kb = reinterpret_cast<const uint4*>(s_tkey + 128 * (warp >> 2) + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = col0 + j;
-                if (t0 + col < nt) {
-                    const uint32_t d = (uint32_t)(my_qpop + s_tpop[col] - 2 * (int)v[j]);
-                    best = min(best, (d << 16) | (uint32_t)(t0 + col));
-                }
+            for (int j = 0; j < 32; j += 4) {  // per element: one IMAD (key = base - <q, t> * 2^17) and half a three-way minimum
+                const uint4 b4 = kb[j >> 2];
+                const uint32_t k0 = b4.x - (v[j] << 17), k1 = b4.y - (v[j + 1] << 17), k2 = b4.z - (v[j + 2] << 17), k3 = b4.w - (v[j + 3] << 17);
+                best = __vimin3_u32(best, k0, k1);
+                best = __vimin3_u32(best, k2, k3);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;");
@@ -152,7 +158,7 @@ __device__ __forceinline__ void match_core_tc(const uint32_t* __restrict__ q, in
         if (qi < nq) {
             const bool any = best != 0xFFFFFFFFu;
             idx_out[qi] = any ? (int)(best & 0xFFFFu) : -1;
-            dist_out[qi] = any ? (int)(best >> 16) : -1;
+            dist_out[qi] = any ? (int)(best >> 16) - 256 + my_qpop : -1;
         }
     }
     __syncthreads();
