@@ -14,9 +14,9 @@ cat gpurun_out/${TAG}_pnp_alone.txt
 if [ -z "${NO_NCU:-}" ]; then
 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/ncu_l.log 2>&1
-# one full step: 22 kernels per step (repitch, pyramid_fused, fast_cells, compact_scan, compact_gather, octree, describe, match_expand, match_mma, orb_filter, fast_full, compact_full, 4 lk_pad + 3 pyr_down, lk_track (whole chain), lk_filter, accum_flags)
+# one full step: 21 kernels per step (repitch, pyramid_fused, fast_cells, compact_scan, compact_gather, octree, describe, match_tc, orb_filter, fast_full, compact_full, 4 lk_pad + 3 pyr_down, lk_track (whole chain), lk_filter, accum_flags)
 python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -s 66 -c 22 -f -o gpurun_out/${TAG}_full python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/ncu_f.log 2>&1
+ncu --set full --clock-control none --import-source on -s 63 -c 21 -f -o gpurun_out/${TAG}_full python bench.py --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/ncu_f.log 2>&1
 tail -2 gpurun_out/ncu_f.log | cut -c1-200
 fi
 ls -la gpurun_out | tail -8
