@@ -10,10 +10,12 @@
 //      by modulo, re-draw on a repeated index;
 //   B  thread h solves hypothesis h with EPnP in double (control points by PCA, barycentric coordinates, M^T M, OpenCV's
 //      one-sided Jacobi SVD on 12 x 12, three beta approximations x 5 Gauss-Newton steps, absolute orientation, the smallest
-//      mean reprojection error wins) -- one thread per hypothesis in local memory: the Jacobi sweeps are a sequential
-//      dependence chain, and 2 x 64 x 148 of them in flight is the parallelism;
+//      mean reprojection error wins) -- one thread per hypothesis, its 12 x 12 matrix in shared memory ([element][thread]:
+//      conflict-free), the rest in registers / local memory: the Jacobi sweeps are a sequential dependence chain, and
+//      2 x 64 x 148 of them in flight is the parallelism;
 //   C  consensus: points staged through shared memory in chunks, warp w counts the inliers of hypotheses w, w + 4, ...:
-//      projection in double, rounded to float, squared distance in float, inlier iff <= (float)(thr * thr)  (ballot + popc);
+//      projection in double, rounded to float, squared distance in float, inlier iff <= (float)(thr * thr); four points per
+//      lane in flight, warp reduction of the count;
 //   D  thread 0 replays `count > max(best, 4) -> keep, lower the limit` over the wave in hypothesis order; the loop ends when
 //      the hypothesis index reaches the limit;
 //   E  inlier mask of the best model, then the Levenberg-Marquardt refinement of [rvec, tvec] over the inliers (CvLevMarq
@@ -21,8 +23,9 @@
 // Steps A-D use + - * / sqrt only and the library is compiled with --fmad=false: every hypothesis is bit-identical to a scalar
 // CPU evaluation in the same operation order, so the discrete outputs (best hypothesis, iteration count, inlier mask) can be
 // tested for equality.  FP64 is deliberate: cv2 computes all of this in double and a 0.5-px threshold on ~1000-px coordinates
-// leaves no room for float.  Bound: FP64 issue + local-memory latency of the Jacobi sweeps (no HBM or tensor bound: a problem
-// reads 20 bytes per point).
+// leaves no room for float.  Bound: the latency of one thread's EPnP (~0.5 ms per wave whatever its size: dependent FP64 and
+// shared-memory instructions; issue slots 11 % used) -- no HBM or tensor bound, a problem reads 20 bytes per point.
+// The ORB list and the LK list of every frame of a batch are problems of ONE launch (blockIdx.y = list kind).
 #include <cfloat>
 
 #include "svo_common.cuh"
@@ -30,7 +33,7 @@
 namespace {
 
 constexpr int PNP_THREADS = 64;    // hypotheses per wave (one thread each in step B)
-constexpr int PNP_BLOCK = 128;     // threads per CTA: steps C and E use all of them.  74 KB + 38 KB of shared memory and 128 x 255
+constexpr int PNP_BLOCK = 128;     // threads per CTA: steps C and E use all of them.  74 KB + 30 KB of shared memory and 128 x 255
                                    // registers: two CTAs per SM, so the ORB and the LK list of every frame of a batch (2 x 128 CTAs) are resident at once
 constexpr int PNP_CHUNK = 1024;  // points staged per consensus chunk (20 KB)
 constexpr int PNP_DYN_SMEM = 144 * PNP_THREADS * 8;  // the 12 x 12 matrices of a wave: 74 KB
