@@ -268,3 +268,34 @@ def test_pnp_degenerate_inputs(orc, gold_pnp):
     orc.pnp_ransac(K, p3, p2)  # n == model size: one hypothesis from points 0..4, no crash
     res = orc.pnp_ransac(K, np.zeros((50, 3), np.float32), np.zeros((50, 2), np.float32))  # all points identical: nothing usable
     assert not res["ok"] or res["n_inliers"] >= 5
+
+
+def test_pnp_ransac_live_cv2(orc, gold_pnp):
+    """Fresh scenes against cv2 itself (when importable): the same statement as the fixture test on other seeds and sizes."""
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    K = gold_pnp["K"]
+    rng = np.random.default_rng(99)
+    exact, n_scenes = 0, 24
+    for k in range(n_scenes):
+        n = int(rng.integers(30, 900))
+        P = np.stack([rng.uniform(-15, 15, n), rng.uniform(-3, 3, n), rng.uniform(5, 50, n)], 1).astype(np.float32)
+        rv, tv = rng.normal(0, 0.02, 3), np.array([rng.normal(0, .1), rng.normal(0, .05), -rng.uniform(0.3, 1.5)])
+        Xc = P.astype(np.float64) @ cv2.Rodrigues(rv)[0].T + tv
+        uv = (Xc[:, :2] / Xc[:, 2:]) * [K[0, 0], K[1, 1]] + [K[0, 2], K[1, 2]] + rng.normal(0, 0.15, (n, 2))
+        no = int(rng.uniform(0.05, 0.5) * n)
+        uv[:no] += rng.uniform(-30, 30, (no, 2))
+        uv = uv.astype(np.float32)
+        ok, r, t, inl = cv2.solvePnPRansac(P, uv, K, np.zeros((4, 1)), rvec=np.zeros((3, 1)), tvec=np.zeros((3, 1)), useExtrinsicGuess=True,
+                                           iterationsCount=500, reprojectionError=0.5, confidence=0.99, flags=cv2.SOLVEPNP_ITERATIVE)
+        m = np.zeros(n, bool)
+        if inl is not None:
+            m[inl.ravel()] = True
+        res = orc.pnp_ransac(K, P, uv)
+        assert res["ok"] == bool(ok)
+        if np.array_equal(m, res["mask"]):
+            exact += 1
+            assert max(np.abs(res["rvec"] - r.ravel()).max(), np.abs(res["tvec"] - t.ravel()).max()) <= 1e-8, k
+        else:
+            assert (m & res["mask"]).sum() / max((m | res["mask"]).sum(), 1) >= 0.8, k
+    assert exact >= (3 * n_scenes) // 4, (exact, n_scenes)
