@@ -208,3 +208,26 @@ def test_long_sequence_is_independent_of_batching(pkg):
     a, b = run(128), run(48)
     assert len(a) == F and a == b
     assert min(r[3] for r in a[1:]) > 20 and min(r[4] for r in a[1:]) > 200
+
+
+def test_match_random_sizes_against_oracle(pkg, orc):
+    """The tcgen05 Hamming match on 120 random (query, train) sizes around its tile edges (128 queries / 256 train descriptors per tile),
+    with duplicated train descriptors (ties) and near-duplicates: indices and distances bit-exact, first minimum wins."""
+    rng = np.random.default_rng(4242)
+    ctx = pkg.Context(0, 64, 64, 2)
+    sizes = [(1, 1), (127, 255), (128, 256), (129, 257), (1, 513), (1000, 1), (300, 0)] + [(int(rng.integers(1, 1500)), int(rng.integers(1, 2200))) for _ in range(113)]
+    for nq, nt in sizes:
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+        t = rng.integers(0, 256, (max(nt, 1), 32), dtype=np.uint8)[:nt]
+        if nt >= 4:
+            k = min(nq, nt // 2)
+            t[nt // 2:nt // 2 + k // 2] = q[:k // 2]            # exact copies of queries ...
+            t[:k // 4] = q[:k // 4]                              # ... twice (the lower index must win)
+            t[nt - 1] = q[nq - 1] ^ np.uint8(1)                  # distance-1 neighbour in the last column
+        gi, gd = ctx.match_hamming(q, t)
+        if nt == 0:
+            assert (gi == -1).all()
+            continue
+        oi, od = orc.match_hamming(q, t)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od), (nq, nt)
+    ctx.close()
