@@ -1008,7 +1008,7 @@ extern "C" int svo_pnp_ransac(svo_ctx* c, const double* K, const float* pts3d, c
     std::vector<int> hi(np * 4);
     SVO_CUDA_TRY(c, cudaMemcpyAsync(hp.data(), dp, np * 128, cudaMemcpyDeviceToHost, c->stream));
     SVO_CUDA_TRY(c, cudaMemcpyAsync(hi.data(), di, np * 16, cudaMemcpyDeviceToHost, c->stream));
-    if (inlier_mask) SVO_CUDA_TRY(c, cudaMemcpyAsync(inlier_mask, dm, np * capz, cudaMemcpyDeviceToHost, c->stream));
+    if (inlier_mask && cap > 0) SVO_CUDA_TRY(c, cudaMemcpyAsync(inlier_mask, dm, np * capz, cudaMemcpyDeviceToHost, c->stream));  // (cap == 0: the caller's array is empty)
     SVO_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < np; ++i) {
         for (int k = 0; k < 3; ++k) {
@@ -1023,7 +1023,7 @@ extern "C" int svo_pnp_ransac(svo_ctx* c, const double* K, const float* pts3d, c
             info[2 * i] = hi[4 * i + 2];
             info[2 * i + 1] = hi[4 * i + 3];
         }
-        if (inlier_mask && !hi[4 * i])
+        if (inlier_mask && cap > 0 && !hi[4 * i])
             for (int k = 0; k < counts[i]; ++k) inlier_mask[i * capz + k] = 0;
     }
     return SVO_OK;
