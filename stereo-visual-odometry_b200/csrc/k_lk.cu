@@ -270,6 +270,20 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const uint8_t* __restr
     }
 }
 
+// element-wise stores into the template for the forms that produce one pixel at a time (e = byte address of entry (j, lane'), s = round)
+__device__ __forceinline__ void tmpl_store_x(uint8_t* e, int s, uint32_t x) { *reinterpret_cast<uint32_t*>(e + 4 * s) = x; }
+__device__ __forceinline__ void tmpl_store_g(uint8_t* e, int s, int ixv, int iyv) {
+    *reinterpret_cast<unsigned short*>(e + 8 + 2 * s) = (unsigned short)ixv;
+    *reinterpret_cast<unsigned short*>(e + 12 + 2 * s) = (unsigned short)iyv;
+}
+
+// d = c + a.lo16 * b.byte2 + a.hi16 * b.byte3 with SIGNED bytes (the high bytes of two differences) -- one IDP.2A.HI
+__device__ __forceinline__ int dp2_hi_s8(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // One warp per point, all pyramid levels in one launch.
 //  setup (previous image): the Scharr gradient and the bilinear interpolation -- both linear with integer weights -- are commuted
 //    EXACTLY when every gradient tap lies inside the image: the staged 24 x 24 neighbourhood is interpolated once (Ib, un-descaled,
@@ -293,11 +307,15 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
     const int pt_first = blockIdx.x * LW + warp;
     if (pt_first >= n) return;  // warp-uniform
     uint8_t* tile = s_mem + warp * WARP_SMEM;
-    uint2* tmpl = reinterpret_cast<uint2*>(tile + TILE_AREA);  // [pixel y * 21 + x] = (256 - 512 * I, Ix | Iy << 16)
-    // template layout: entry (round s, row-in-strip j, lane) at tmpl[(s * 7 + j) * 32 + lane]; strip g = 3 x + y / 7 of window
-    // pixel (x, y) belongs to lane g & 31 in round g >> 5.  Strip 63 (lane 31, round 1) does not exist: zero gradient, never
-    // rewritten, so it contributes nothing to the sums.
-    if (lane < SEG) tmpl[(SEG + lane) * 32 + 31] = make_uint2(0u, 0u);
+    // template: entry (row-in-strip j, lane) = uint4 {x of round 0, x of round 1, Ix0 | Ix1 << 16, Iy0 | Iy1 << 16} at tmpl[j * 32 + lane],
+    // x = 256 - 512 * I; strip g = 3 x + y / 7 of window pixel (x, y) belongs to lane g & 31 in round g >> 5.  The two rounds of a
+    // lane sit side by side so that the iterations read both pixels with one LDS.128 and multiply BOTH gradients of the pair with
+    // the pair's differences in IDP.2A (see the iteration loop).  Strip 63 (lane 31, round 1) does not exist: its gradient halves
+    // are zero (written here and by every two-phase setup, never touched by the other forms), so it contributes nothing to the sums.
+    uint4* tmpl = reinterpret_cast<uint4*>(tile + TILE_AREA);
+    uint8_t* tmb = tile + TILE_AREA;
+    const uint32_t tm32 = (uint32_t)__cvta_generic_to_shared(tmb);
+    if (lane < SEG) tmpl[lane * 32 + 31] = make_uint4(0u, 0u, 0u, 0u);
     int offJ[NROUND];  // byte offset of the strip's first pair (column x, row 7 * seg) in a tile whose byte 0 is column x = 0
 #pragma unroll
     for (int sr = 0; sr < NROUND; ++sr) {
@@ -309,13 +327,6 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
     for (int sr = 0; sr < NROUND; ++sr) {
         const int g = min(lane + 32 * sr, 62), x = g / 3, sg = g - 3 * x;
         offB[sr] = irow_off(SEG * sg) + x;
-    }
-    // setup (column-lane form): where this lane's column x = lane - 1 stores row y: base of segment y / 7, plus (y % 7) * 32
-    int tbase[3];
-#pragma unroll
-    for (int sg = 0; sg < 3; ++sg) {
-        const int g = 3 * (lane - 1) + sg;
-        tbase[sg] = (g >> 5) * SEG * 32 + (g & 31);
     }
     const int ccol = min(lane, 23);  // setup: tile column of this lane
 
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 for (int j = 0; j < SEG; ++j) {
                     const uint32_t pb = lds_u16(tp + (row_off(j + 1) - row_off(0)));
                     const int iv = dp2(Wbot, pb, dp2(Wtop, pa, 256)) >> 9;
-                    if (real) tmpl[(sr * SEG + j) * 32 + lane].x = (uint32_t)(256 - 512 * iv);
+                    if (real) tmpl_store_x(tmb + (j * 32 + lane) * 16, sr, (uint32_t)(256 - 512 * iv));
                     pa = pb;
                 }
             }
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                             const int ixv = (ptx + ixA * iw10 + ixB * iw11 + (1 << 13)) >> 14;
                             const int iyv = (pty + iyA * iw10 + iyB * iw11 + (1 << 13)) >> 14;
                             if (real) {
-                                tmpl[(sr * SEG + j - 1) * 32 + lane].y = ((uint32_t)ixv & 0xFFFFu) | ((uint32_t)iyv << 16);
+                                tmpl_store_g(tmb + ((j - 1) * 32 + lane) * 16, sr, ixv, iyv);
                                 a11 += ixv * ixv;
                                 a12 += ixv * iyv;
                                 a22 += iyv * iyv;
@@ -478,32 +489,33 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 }
             }
             __syncwarp();
-#pragma unroll
-            for (int sr = 0; sr < NROUND; ++sr) {
-                const int* ip = ibw + offB[sr];
-                uint2* to = tmpl + sr * SEG * 32 + lane;
-                const bool real = lane + 32 * sr < 63;
-                int dHa = 0, dHb = 0, Sa = 0, Sb = 0, Cb = 0;
+            // both strips of the lane side by side: one STS.128 per template entry (the pair the iterations read with one LDS.128)
+            {
+                const int* ip0 = ibw + offB[0];
+                const int* ip1 = ibw + offB[1];
+                uint4* to = tmpl + lane;
+                const int m1 = lane < 31 ? -1 : 0;  // strip 63 does not exist: zero gradient
+                int dHa0 = 0, dHb0 = 0, Sa0 = 0, Sb0 = 0, Cb0 = 0, dHa1 = 0, dHb1 = 0, Sa1 = 0, Sb1 = 0, Cb1 = 0;
 #pragma unroll
                 for (int j = 0; j < SEG + 2; ++j) {
                     const int o = irow_off(j);  // relative to the strip's first row (7 sg): 23 words per row, rows 7 and 8 carry the next segment's skew
-                    const int L = ip[o], C = ip[o + 1], R = ip[o + 2];
-                    const int dH = R - L, S = 3 * (L + R) + 10 * C;
+                    const int L0 = ip0[o], C0 = ip0[o + 1], R0 = ip0[o + 2];
+                    const int L1 = ip1[o], C1 = ip1[o + 1], R1 = ip1[o + 2];
+                    const int dH0 = R0 - L0, S0 = 3 * (L0 + R0) + 10 * C0;
+                    const int dH1 = R1 - L1, S1 = 3 * (L1 + R1) + 10 * C1;
                     if (j >= 2) {  // window row 7 sg + j - 2
-                        const int ixv = (3 * (dHa + dH) + 10 * dHb + (1 << 13)) >> 14;
-                        const int iyv = (S - Sa + (1 << 13)) >> 14;
-                        if (real) {
-                            to[(j - 2) * 32] = make_uint2((uint32_t)(256 - (Cb & ~511)), __byte_perm((uint32_t)ixv, (uint32_t)iyv, 0x5410));
-                            a11 += ixv * ixv;
-                            a12 += ixv * iyv;
-                            a22 += iyv * iyv;
-                        }
+                        const int ixv0 = (3 * (dHa0 + dH0) + 10 * dHb0 + (1 << 13)) >> 14;
+                        const int iyv0 = (S0 - Sa0 + (1 << 13)) >> 14;
+                        const int ixv1 = ((3 * (dHa1 + dH1) + 10 * dHb1 + (1 << 13)) >> 14) & m1;
+                        const int iyv1 = ((S1 - Sa1 + (1 << 13)) >> 14) & m1;
+                        to[(j - 2) * 32] = make_uint4((uint32_t)(256 - (Cb0 & ~511)), (uint32_t)(256 - (Cb1 & ~511)),
+                                                      __byte_perm((uint32_t)ixv0, (uint32_t)ixv1, 0x5410), __byte_perm((uint32_t)iyv0, (uint32_t)iyv1, 0x5410));
+                        a11 += ixv0 * ixv0 + ixv1 * ixv1;
+                        a12 += ixv0 * iyv0 + ixv1 * iyv1;
+                        a22 += iyv0 * iyv0 + iyv1 * iyv1;
                     }
-                    dHa = dHb;
-                    dHb = dH;
-                    Sa = Sb;
-                    Sb = S;
-                    Cb = C;
+                    dHa0 = dHb0; dHb0 = dH0; Sa0 = Sb0; Sb0 = S0; Cb0 = C0;
+                    dHa1 = dHb1; dHb1 = dH1; Sa1 = Sb1; Sb1 = S1; Cb1 = C1;
                 }
             }
         } else {
@@ -517,7 +529,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
             int top = 256, tgx = 0, tgxn = 0, tgy = 0, tgyn = 0;
             // one row of the general form: the Scharr gradient at (X, Y = ipy + r) (tile row r + 1) from tile rows r .. r + 2, and -- for
             // r >= 1 -- the template entry of window row r - 1 from the gradients / pixels of rows r - 1 and r
-            auto grow = [&](int r, int p2, uint32_t pr, uint2* trow) {
+            auto grow = [&](int r, int p2, uint32_t pr, bool emit, uint32_t te) {  // emit: window row r - 1 goes to shared-memory address te
                 const int V = 3 * (p0 + p2) + 10 * p1, Dv = p2 - p0;
                 const int Vl = __shfl_up_sync(0xFFFFFFFFu, V, 1), Vr = __shfl_down_sync(0xFFFFFFFFu, V, 1);
                 const int Dl = __shfl_up_sync(0xFFFFFFFFu, Dv, 1), Dr = __shfl_down_sync(0xFFFFFFFFu, Dv, 1);
@@ -526,11 +538,14 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 const int gx = in ? Vr - Vl : 0;
                 const int gy = in ? 3 * (Dl + Dr) + 10 * Dv : 0;
                 const int gxn = __shfl_down_sync(0xFFFFFFFFu, gx, 1), gyn = __shfl_down_sync(0xFFFFFFFFu, gy, 1);
-                if (trow) {
+                if (emit) {
                     const int ib = dp2(Wbot, pr, top);  // interpolated pixel + 256
                     const int ixv = descale(tgx * iw00 + tgxn * iw01 + gx * iw10 + gxn * iw11, 14);
                     const int iyv = descale(tgy * iw00 + tgyn * iw01 + gy * iw10 + gyn * iw11, 14);
-                    if (wlane) *trow = make_uint2((uint32_t)(256 - (ib & ~511)), __byte_perm((uint32_t)ixv, (uint32_t)iyv, 0x5410));
+                    if (wlane)  // (a plain 32-bit shared address: as a generic pointer the compiler re-derived the shared window base at every store)
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(te), "r"((uint32_t)(256 - (ib & ~511))),
+                                     "r"(__byte_perm((uint32_t)ixv, (uint32_t)iyv, 0x5410))
+                                     : "memory");
                     a11 += ixv * ixv;
                     a12 += ixv * iyv;
                     a22 += iyv * iyv;
@@ -540,17 +555,26 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 p0 = p1;
                 p1 = p2;
             };
-            grow(0, tb[row_off(2)], lds_u16(tp + row_off(1)), nullptr);
+            grow(0, tb[row_off(2)], lds_u16(tp + row_off(1)), false, 0u);
             // rows 1 .. 21 = three segments of 7: the segment loop stays rolled (this form runs for ~1 setup in 5; unrolling all 22
             // rows made the kernel's executed code outgrow the instruction cache once the err pass ran too)
 #pragma unroll 1
             for (int sg = 0; sg < 3; ++sg) {
                 const uint8_t* tbs = tb + sg * (row_off(SEG) - row_off(0));
                 const uint8_t* tps = tp + sg * (row_off(SEG) - row_off(0));
+                // this lane's strip of the segment belongs to lane g & 31, round g >> 5: the pixel goes there as (x, Ix | Iy << 16) first
                 const int g = 3 * (lane - 1) + sg;
-                uint2* trow = tmpl + (g >> 5) * SEG * 32 + (g & 31);
+                const uint32_t te = tm32 + (uint32_t)((g & 31) * 16 + (g >> 5) * 8);
 #pragma unroll
-                for (int jj = 0; jj < SEG; ++jj) grow(1 + SEG * sg + jj, tbs[row_off(3 + jj)], lds_u16(tps + row_off(2 + jj)), trow + jj * 32);
+                for (int jj = 0; jj < SEG; ++jj) grow(1 + SEG * sg + jj, tbs[row_off(3 + jj)], lds_u16(tps + row_off(2 + jj)), true, te + jj * 512);
+            }
+            // {x0, g0, x1, g1} -> {x0, x1, Ix0 | Ix1 << 16, Iy0 | Iy1 << 16}: every lane repacks its own seven entries
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < SEG; ++j) {
+                uint4 v = tmpl[j * 32 + lane];
+                if (lane == 31) v.w = 0u;  // strip 63 does not exist: zero gradient
+                tmpl[j * 32 + lane] = make_uint4(v.x, v.z, __byte_perm(v.y, v.w, 0x5410), __byte_perm(v.y, v.w, 0x7632));
             }
         }
         }  // !DERIV
@@ -571,7 +595,7 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
         nx = __fsub_rn(nx, half);
         ny = __fsub_rn(ny, half);
         float pdx = 0.f, pdy = 0.f;
-        const uint2* tl = tmpl + lane;
+        const uint4* tl = tmpl + lane;
         int tx = INT_MIN, ty = INT_MIN;  // origin of the staged next-image tile (none yet: the tile holds the previous image)
         for (int j = 0; j < P.max_iter; ++j) {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
@@ -589,22 +613,31 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                 tx = inx;
                 ty = iny;
             }
-            int b1 = 0, b2 = 0;
-#pragma unroll
-            for (int sr = 0; sr < NROUND; ++sr) {
-                const uint8_t* tp = tile + offJ[sr];
-                uint32_t pa = lds_u16(tp);  // the pair of row j; row j + 1's pair is reused as the next row's upper pair
+            // Both strips of the lane side by side.  A difference d (|d| <= 8160) is 256 * (signed byte 1) + (unsigned byte 0); one PRMT
+            // gathers the four bytes of the pair's differences, and each gradient pair (Ix0 | Ix1 << 16 resp. Iy0 | Iy1 << 16, as the
+            // template stores them) takes two IDP.2A: low bytes (unsigned) and high bytes (signed) -- 5 instructions for the four
+            // products of a pixel pair instead of two sign extensions and two IMAD per pixel.  The sums are the same exact integers.
+            int b1l = 0, b1h = 0, b2l = 0, b2h = 0;
+            {
+                const uint8_t* tp0 = tile + offJ[0];
+                const uint8_t* tp1 = tile + offJ[1];
+                uint32_t pa0 = lds_u16(tp0), pa1 = lds_u16(tp1);  // the pair of row j; row j + 1's pair is reused as the next row's upper pair
 #pragma unroll
                 for (int j = 0; j < SEG; ++j) {
-                    const uint32_t pb = lds_u16(tp + (row_off(j + 1) - row_off(0)));
-                    const uint2 t = tl[(sr * SEG + j) * 32];
-                    const int diff = dp2(Wbot, pb, dp2(Wtop, pa, (int)t.x)) >> 9;  // descale(J interpolated, 9) - I
-                    const int gxv = (int)(short)(t.y & 0xFFFFu), gyv = (int)t.y >> 16;
-                    b1 += diff * gxv;
-                    b2 += diff * gyv;
-                    pa = pb;
+                    const uint32_t pb0 = lds_u16(tp0 + (row_off(j + 1) - row_off(0))), pb1 = lds_u16(tp1 + (row_off(j + 1) - row_off(0)));
+                    const uint4 t = tl[j * 32];
+                    const int d0 = dp2(Wbot, pb0, dp2(Wtop, pa0, (int)t.x)) >> 9;  // descale(J interpolated, 9) - I
+                    const int d1 = dp2(Wbot, pb1, dp2(Wtop, pa1, (int)t.y)) >> 9;
+                    const uint32_t dd = __byte_perm((uint32_t)d0, (uint32_t)d1, 0x5140);  // (d0.b0, d1.b0, d0.b1, d1.b1)
+                    b1l = dp2(t.z, dd, b1l);
+                    b1h = dp2_hi_s8(t.z, dd, b1h);
+                    b2l = dp2(t.w, dd, b2l);
+                    b2h = dp2_hi_s8(t.w, dd, b2h);
+                    pa0 = pb0;
+                    pa1 = pb1;
                 }
             }
+            const int b1 = b1l + (b1h << 8), b2 = b2l + (b2h << 8);
             // |diff| <= 8160 (pixels carry 5 fraction bits) and |Ix|, |Iy| <= 4080 (Scharr of 8-bit pixels): a lane's 14 products stay
             // below 2^29, but the window sum can reach 441 * 8160 * 4080 ~ 2^34 (sharp stripes one pixel out of register), so the
             // exact sum takes three hardware reductions: the two high parts (b >> 8, |sum| < 2^26) and both low bytes packed in one
@@ -652,13 +685,13 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
 #pragma unroll 1  // (rolled: the err pass runs once per call; its code must stay small)
                 for (int sr = 0; sr < NROUND; ++sr) {
                     const uint8_t* tp = tile + (sr ? offJ[1] : offJ[0]);
-                    const uint2* tls = tl + sr * SEG * 32;
+                    const uint32_t* tls = reinterpret_cast<const uint32_t*>(tl) + sr;  // x = 256 - 512 * I of round sr: word sr of every entry
                     uint32_t pa = lds_u16(tp);
                     int es = 0;
 #pragma unroll
                     for (int j = 0; j < SEG; ++j) {
                         const uint32_t pb = lds_u16(tp + (row_off(j + 1) - row_off(0)));
-                        es += abs(dp2(Wbot, pb, dp2(Wtop, pa, (int)tls[j * 32].x)) >> 9);
+                        es += abs(dp2(Wbot, pb, dp2(Wtop, pa, (int)tls[j * 128])) >> 9);
                         pa = pb;
                     }
                     if (lane + 32 * sr < 63) e += es;
