@@ -243,7 +243,7 @@ __host__ __device__ constexpr int irow_off(int r) { return r * 23 + (r / 7) * 10
 constexpr int ITILE_BYTES = (irow_off(22) + 23) * 4;
 constexpr int TILE_MAX = DTILE_BYTES > ITILE_BYTES ? (DTILE_BYTES > TILE_BYTES ? DTILE_BYTES : TILE_BYTES) : (ITILE_BYTES > TILE_BYTES ? ITILE_BYTES : TILE_BYTES);
 constexpr int TILE_AREA = ((TILE_MAX + 63) / 64) * 64;
-static_assert(TILE_BYTES <= 32 * SEG * 8, "the previous image's tile must fit below the second round of the template area");
+static_assert(TILE_BYTES <= 32 * NROUND * SEG * 8, "the two-phase setup stages the previous image's tile in the template area");
 constexpr int WARP_SMEM = TILE_AREA + 32 * NROUND * SEG * 8;
 
 __device__ __forceinline__ int pair_off(int c) {  // byte offset in a tile row of the aligned u16 holding tile bytes (c, c+1)
@@ -290,8 +290,9 @@ __device__ __forceinline__ int dp2_hi_s8(uint32_t a, uint32_t b, int c) {
 //    2 IDP.2A per value, lane = column) into shared memory and Scharr is applied to Ib in the iterations' strip layout with all 32
 //    lanes.  Otherwise (window across the image border) the general form with OpenCV's constant-0 derivative outside the image
 //    runs (lane = column, neighbours by shuffle).  The template (I, Ix, Iy) goes to shared memory in FLATTENED pixel order.
-//  iterations (next image): the window is cut into 63 strips (21 columns x 3 segments of 7 rows), two per lane: 8 pair loads
-//    per strip (vertical reuse), and per pixel one 64-bit template load, 2 IDP.2A, one shift, two sign extensions, two IMAD.
+//  iterations (next image): the window is cut into 63 strips (21 columns x 3 segments of 7 rows), two per lane, walked side by side:
+//    8 pair loads per strip (vertical reuse), and per PAIR of pixels one 128-bit template load, 4 IDP.2A + 2 shifts for the two
+//    differences, one PRMT gathering their bytes and 4 IDP.2A for the four products with the packed gradient pairs.
 // All window sums are exact integers; float expressions follow OpenCV's scalar order with _rn intrinsics.
 template <bool DERIV>
 __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_keypoint* __restrict__ fast_kps, const int* __restrict__ nfast,
@@ -637,13 +638,12 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                     pa1 = pb1;
                 }
             }
-            const int b1 = b1l + (b1h << 8), b2 = b2l + (b2h << 8);
-            // |diff| <= 8160 (pixels carry 5 fraction bits) and |Ix|, |Iy| <= 4080 (Scharr of 8-bit pixels): a lane's 14 products stay
-            // below 2^29, but the window sum can reach 441 * 8160 * 4080 ~ 2^34 (sharp stripes one pixel out of register), so the
-            // exact sum takes three hardware reductions: the two high parts (b >> 8, |sum| < 2^26) and both low bytes packed in one
-            const int hb1 = __reduce_add_sync(0xFFFFFFFFu, b1 >> 8), hb2 = __reduce_add_sync(0xFFFFFFFFu, b2 >> 8);
-            const uint32_t lb = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)(b1 & 255) | ((uint32_t)(b2 & 255) << 16));  // each <= 32 * 255
-            const long long sb1 = ((long long)hb1 << 8) + (long long)(lb & 0xFFFFu), sb2 = ((long long)hb2 << 8) + (long long)(lb >> 16);
+            // |diff| <= 8160 (pixels carry 5 fraction bits) and |Ix|, |Iy| <= 4080 (Scharr of 8-bit pixels): the window sum can reach
+            // 441 * 8160 * 4080 ~ 2^34 (sharp stripes one pixel out of register), but its two parts fit 32 bits -- low bytes
+            // <= 441 * 255 * 4080 < 2^29, high bytes <= 441 * 32 * 4080 < 2^26 -- so the exact sum is four hardware reductions
+            const int r1l = __reduce_add_sync(0xFFFFFFFFu, b1l), r1h = __reduce_add_sync(0xFFFFFFFFu, b1h);
+            const int r2l = __reduce_add_sync(0xFFFFFFFFu, b2l), r2h = __reduce_add_sync(0xFFFFFFFFu, b2h);
+            const long long sb1 = ((long long)r1h << 8) + (long long)r1l, sb2 = ((long long)r2h << 8) + (long long)r2l;
             const float b1f = __fmul_rn((float)sb1, FLT_SCALE), b2f = __fmul_rn((float)sb2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2f), __fmul_rn(A22, b1f)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1f), __fmul_rn(A11, b2f)), D);
