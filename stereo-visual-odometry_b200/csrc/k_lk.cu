@@ -682,19 +682,21 @@ __global__ void __launch_bounds__(LW * 32, 32) k_lk_track(LkParams P, const svo_
                     __syncwarp();
                 }
                 int e = 0;
-#pragma unroll 1  // (rolled: the err pass runs once per call; its code must stay small)
-                for (int sr = 0; sr < NROUND; ++sr) {
-                    const uint8_t* tp = tile + (sr ? offJ[1] : offJ[0]);
-                    const uint32_t* tls = reinterpret_cast<const uint32_t*>(tl) + sr;  // x = 256 - 512 * I of round sr: word sr of every entry
-                    uint32_t pa = lds_u16(tp);
-                    int es = 0;
+                {   // both strips side by side like the iterations: one 64-bit load brings the pair's two x = 256 - 512 * I
+                    const uint8_t* tp0 = tile + offJ[0];
+                    const uint8_t* tp1 = tile + offJ[1];
+                    uint32_t pa0 = lds_u16(tp0), pa1 = lds_u16(tp1);
+                    int e1 = 0;
 #pragma unroll
                     for (int j = 0; j < SEG; ++j) {
-                        const uint32_t pb = lds_u16(tp + (row_off(j + 1) - row_off(0)));
-                        es += abs(dp2(Wbot, pb, dp2(Wtop, pa, (int)tls[j * 128])) >> 9);
-                        pa = pb;
+                        const uint32_t pb0 = lds_u16(tp0 + (row_off(j + 1) - row_off(0))), pb1 = lds_u16(tp1 + (row_off(j + 1) - row_off(0)));
+                        const uint2 tx2 = *reinterpret_cast<const uint2*>(tl + j * 32);
+                        e += abs(dp2(Wbot, pb0, dp2(Wtop, pa0, (int)tx2.x)) >> 9);
+                        e1 += abs(dp2(Wbot, pb1, dp2(Wtop, pa1, (int)tx2.y)) >> 9);
+                        pa0 = pb0;
+                        pa1 = pb1;
                     }
-                    if (lane + 32 * sr < 63) e += es;
+                    if (lane < 31) e += e1;  // strip 63 does not exist
                 }
                 const int se = __reduce_add_sync(0xFFFFFFFFu, e);  // <= 441 * 8160
                 err = __fdiv_rn((float)se, (float)(32 * WIN * WIN));
