@@ -76,3 +76,43 @@ def test_source_errors_are_loud(pkg, tmp_path):
     src.close()
     with pytest.raises(pkg.SvoError):
         pkg.FrameSource(str(tmp_path), w, h, 2, ring_batches=2, threads=2)  # ring needs >= 3 batches (two stay lent)
+
+
+def test_source_corrupt_png_never_crashes(pkg, tmp_path):
+    """Flipped bytes, truncations, overwritten chunk headers and trailing garbage in a PNG end in SvoError or in a clean decode --
+    never in a crash or a hang (the decoder threads read files the reference would hand to cv::imread, System.cpp:79-86)."""
+    w, h = 97, 61
+    left, right = _seq(pkg, 2, w, h)
+    pkg.write_sequence(str(tmp_path), left, right, fmt="png", zlib_level=6)
+    path = tmp_path / "image_0" / "000000.png"
+    good = path.read_bytes()
+    rng = np.random.default_rng(5)
+    decoded = failed = 0
+    for it in range(120):
+        b = bytearray(good)
+        mode = it % 4
+        if mode == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(8, len(b)))] = int(rng.integers(0, 256))
+        elif mode == 1:
+            b = b[:int(rng.integers(0, len(b)))]
+        elif mode == 2:
+            p = int(rng.integers(8, len(b) - 8))
+            b[p:p + 4] = int(rng.integers(0, 2**32)).to_bytes(4, "big")
+        else:
+            b += bytes(rng.integers(0, 256, int(rng.integers(1, 64)), dtype=np.uint8))
+        path.write_bytes(bytes(b))
+        try:
+            src = pkg.FrameSource(str(tmp_path), w, h, 2, ring_batches=3, threads=2)
+        except pkg.SvoError:
+            failed += 1
+            continue
+        try:
+            got = src.next()
+            if got is not None and mode == 3:  # trailing bytes after IEND do not change the image
+                assert np.array_equal(got[0][0], left[0])
+            decoded += 1
+        except pkg.SvoError:
+            failed += 1
+        src.close()
+    assert decoded >= 30 and failed >= 60  # every appended-garbage case decodes, (nearly) every damaged stream is refused
