@@ -9,9 +9,10 @@
 //                   shared memory as (row, row shifted by one byte) word pairs, so the two horizontal taps of the bilinear
 //                   stencil are one aligned 16-bit load feeding IDP.2A.  Scharr gradients are derived on the fly (constant 0
 //                   outside the image, exactly like OpenCV's padded derivative buffer -- no derivative image is ever written
-//                   to HBM); the interpolated 21x21 template (I, Ix, Iy) lives in shared memory in flattened pixel order and
-//                   the Gauss-Newton iterations spread its 441 pixels over all 32 lanes.  All window sums are exact integers
-//                   (int64 across the warp), converted to float once.
+//                   to HBM); the interpolated 21x21 template (I, Ix, Iy) lives in shared memory as pixel PAIRS (the two strips of a
+//                   lane) and the Gauss-Newton iterations spread its 441 pixels over all 32 lanes, multiplying both gradients of a
+//                   pair with the pair's differences in IDP.2A.  All window sums are exact integers (int64 across the warp),
+//                   converted to float once.
 //
 // f32 arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) to follow OpenCV's scalar expressions.
 #include <algorithm>
